@@ -1,0 +1,125 @@
+// Curve arithmetic of the Schnorr sub-AIR (reference: src/utils/ecc.rs), shared by the host witness builder and
+// the constraint kernels.  Fp2 = Fp[u]/(u^2 - 2u - 2), Fp6 = Fp2[v]/(v^3 + v + 1); curve y^2 = x^3 + x + B over
+// Fp6 with the complete projective formulas of Renes-Costello-Batina (Alg. 1/2/3, a = 1, b3 = 3B).
+// The AIR compares coordinates, not projective classes, so these exact polynomial formulas are part of the spec.
+#pragma once
+#include "field.cuh"
+#include "ref_constants.h"
+
+namespace ecc {
+using f63::fe;
+
+struct fp2 { fe c0, c1; };
+struct fp6 { fe c[6]; };
+struct point { fp6 x, y, z; };
+
+CSG_HD fp2 add(fp2 a, fp2 b) { return {f63::add(a.c0, b.c0), f63::add(a.c1, b.c1)}; }
+CSG_HD fp2 sub(fp2 a, fp2 b) { return {f63::sub(a.c0, b.c0), f63::sub(a.c1, b.c1)}; }
+CSG_HD fp2 dbl(fp2 a) { return {f63::dbl(a.c0), f63::dbl(a.c1)}; }
+CSG_HD fp2 neg(fp2 a) { return {f63::neg(a.c0), f63::neg(a.c1)}; }
+// (a0 b0 + 2 a1 b1) + (a0 b1 + a1 b0 + 2 a1 b1) u : three base multiplications (ecc.rs:424-439)
+CSG_HD fp2 mul(fp2 a, fp2 b) {
+    fe p00 = f63::mul(a.c0, b.c0), p11 = f63::mul(a.c1, b.c1);
+    fe cross = f63::mul(f63::sub(a.c0, a.c1), f63::sub(b.c1, b.c0));
+    fe c0 = f63::add(f63::dbl(p11), p00);
+    return {c0, f63::add(f63::add(p11, c0), cross)};
+}
+CSG_HD fp2 sqr(fp2 a) { return mul(a, a); }
+
+CSG_HD fp6 add(const fp6 &a, const fp6 &b) { fp6 r; for (int i = 0; i < 6; i++) r.c[i] = f63::add(a.c[i], b.c[i]); return r; }
+CSG_HD fp6 sub(const fp6 &a, const fp6 &b) { fp6 r; for (int i = 0; i < 6; i++) r.c[i] = f63::sub(a.c[i], b.c[i]); return r; }
+CSG_HD fp6 dbl(const fp6 &a) { fp6 r; for (int i = 0; i < 6; i++) r.c[i] = f63::dbl(a.c[i]); return r; }
+// (a + b v + c v^2)(d + e v + f v^2) with v^3 = -v - 1: six Fp2 products (ecc.rs:506-548)
+CSG_HD fp6 mul(const fp6 &x, const fp6 &y) {
+    fp2 a = {x.c[0], x.c[1]}, b = {x.c[2], x.c[3]}, c = {x.c[4], x.c[5]};
+    fp2 d = {y.c[0], y.c[1]}, e = {y.c[2], y.c[3]}, f = {y.c[4], y.c[5]};
+    fp2 ad = mul(a, d), be = mul(b, e), cf = mul(c, f);
+    fp2 s_ab = mul(add(a, b), add(d, e)), s_ac = mul(add(a, c), add(d, f)), s_bc = mul(add(b, c), add(e, f));
+    fp2 sum = add(add(ad, be), cf);
+    fp2 r0 = sub(sum, s_bc);
+    fp2 r1 = sub(sub(s_ab, s_bc), ad);
+    fp2 r2 = add(sub(sub(s_ac, sum), cf), dbl(be));
+    return {{r0.c0, r0.c1, r1.c0, r1.c1, r2.c0, r2.c1}};
+}
+CSG_HD fp6 sqr(const fp6 &a) { return mul(a, a); }
+CSG_HD fp6 b3() { return {{CSG_B3_M[0], CSG_B3_M[1], CSG_B3_M[2], CSG_B3_M[3], CSG_B3_M[4], CSG_B3_M[5]}}; }
+CSG_HD fp6 load6(const fe *p) { return {{p[0], p[1], p[2], p[3], p[4], p[5]}}; }
+
+// RCB15 Alg. 3 (ecc.rs:186-246)
+CSG_HD point double_point(const point &p) {
+    const fp6 B3 = b3();
+    fp6 t0 = sqr(p.x), t1 = sqr(p.y), t2 = sqr(p.z);
+    fp6 t3 = dbl(mul(p.x, p.y));
+    fp6 z3 = dbl(mul(p.x, p.z));
+    fp6 y3 = add(z3, mul(B3, t2));
+    fp6 x3 = sub(t1, y3);
+    y3 = add(t1, y3);
+    y3 = mul(x3, y3);
+    x3 = mul(t3, x3);
+    z3 = mul(B3, z3);
+    t3 = add(sub(t0, t2), z3);
+    t0 = add(add(dbl(t0), t0), t2);
+    t0 = mul(t0, t3);
+    y3 = add(y3, t0);
+    t2 = dbl(mul(p.y, p.z));
+    x3 = sub(x3, mul(t2, t3));
+    z3 = dbl(dbl(mul(t2, t1)));
+    return {x3, y3, z3};
+}
+// RCB15 Alg. 2: projective + affine (ecc.rs:329-404)
+CSG_HD point add_mixed(const point &p, const fp6 &qx, const fp6 &qy) {
+    const fp6 B3 = b3();
+    fp6 t0 = mul(p.x, qx), t1 = mul(p.y, qy);
+    fp6 t3 = sub(mul(add(qx, qy), add(p.x, p.y)), add(t0, t1));
+    fp6 t4 = add(mul(qx, p.z), p.x);
+    fp6 t5 = add(mul(qy, p.z), p.y);
+    fp6 z3 = add(mul(p.z, B3), t4);
+    fp6 x3 = sub(t1, z3);
+    z3 = add(t1, z3);
+    fp6 y3 = mul(x3, z3);
+    t1 = add(add(dbl(t0), t0), p.z);
+    t4 = add(mul(t4, B3), sub(t0, p.z));
+    y3 = add(y3, mul(t1, t4));
+    x3 = sub(mul(t3, x3), mul(t5, t4));
+    z3 = add(mul(t5, z3), mul(t3, t1));
+    return {x3, y3, z3};
+}
+// RCB15 Alg. 1: projective + projective (ecc.rs:248-327)
+CSG_HD point add_full(const point &p, const point &q) {
+    const fp6 B3 = b3();
+    fp6 t0 = mul(p.x, q.x), t1 = mul(p.y, q.y), t2 = mul(p.z, q.z);
+    fp6 t3 = sub(mul(add(p.x, p.y), add(q.x, q.y)), add(t0, t1));
+    fp6 t4 = sub(mul(add(p.x, p.z), add(q.x, q.z)), add(t0, t2));
+    fp6 t5 = sub(mul(add(p.y, p.z), add(q.y, q.z)), add(t1, t2));
+    fp6 z3 = add(mul(B3, t2), t4);
+    fp6 x3 = sub(t1, z3);
+    z3 = add(t1, z3);
+    fp6 y3 = mul(x3, z3);
+    t1 = add(add(dbl(t0), t0), t2);
+    t4 = add(mul(B3, t4), sub(t0, t2));
+    y3 = add(y3, mul(t1, t4));
+    x3 = sub(mul(t3, x3), mul(t5, t4));
+    z3 = add(mul(t5, z3), mul(t3, t1));
+    return {x3, y3, z3};
+}
+
+#if !defined(__CUDA_ARCH__)
+// host-only inversions for the final X/Z reduction of the witness (ecc.rs:441-446, 551-591)
+inline fp2 inv(fp2 a) {
+    fe t = f63::inv(f63::sub(f63::add(f63::sqr(a.c0), f63::mul(f63::dbl(a.c0), a.c1)), f63::dbl(f63::sqr(a.c1))));
+    return {f63::mul(f63::add(a.c0, f63::dbl(a.c1)), t), f63::mul(f63::neg(a.c1), t)};
+}
+inline fp6 inv(const fp6 &x) {
+    fp2 a = {x.c[0], x.c[1]}, b = {x.c[2], x.c[3]}, c = {x.c[4], x.c[5]};
+    fp2 a2 = sqr(a), b2 = sqr(b), c2 = sqr(c);
+    fp2 t = sub(mul(a, add(a2, b2)), mul(b, b2));
+    t = add(t, mul(add(a, sub(c, b)), c2));
+    fp2 w = mul(sub(dbl(a2), mul(add(dbl(a), a), b)), c);
+    t = inv(sub(t, w));
+    fp2 r0 = mul(sub(add(add(a2, b2), c2), mul(sub(dbl(a), b), c)), t);
+    fp2 r1 = mul(neg(add(mul(a, b), c2)), t);
+    fp2 r2 = mul(add(sub(b2, mul(a, c)), c2), t);
+    return {{r0.c0, r0.c1, r1.c0, r1.c1, r2.c0, r2.c1}};
+}
+#endif
+}  // namespace ecc

@@ -1,0 +1,106 @@
+// f63 arithmetic shared by the host driver (C++) and the sm_100a kernels.
+//
+// The field is winterfell::math::fields::f63::BaseElement of the reference (src/prover.rs:2, src/air.rs:41):
+//   p = 2^62 + 2^56 + 2^55 + 1 = 0x4180000000000001   (reference: src/range/tests.rs:59, benches/range.rs:23)
+// Elements are kept in Montgomery form (R = 2^64) end to end on the device, as the reference does on the CPU
+// (src/utils/ecc.rs:23-36 stores GENERATOR as raw Montgomery limbs); bytes that get hashed or serialised are
+// converted to canonical little-endian first.
+//
+// p and -p^-1 = p - 2 are both sparse, so the Montgomery reduction needs no multiplier: on the device it is
+// shifts and adds on the ALU pipe, leaving the fma pipe for the 4 IMAD.WIDE of the 64x64 product.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define CSG_HD __host__ __device__ __forceinline__
+#define CSG_D __device__ __forceinline__
+#else
+#define CSG_HD inline
+#endif
+
+namespace f63 {
+
+typedef uint64_t fe;  // Montgomery form, reduced to [0, p)
+
+constexpr uint64_t P = 0x4180000000000001ULL;
+constexpr uint64_t NPRIME = 0x417fffffffffffffULL;  // -p^-1 mod 2^64 == p - 2
+constexpr uint64_t R = 0x3b7ffffffffffffdULL;       // 2^64 mod p  (Montgomery form of 1)
+constexpr uint64_t R2 = 0x32734c36b7b1d512ULL;      // 2^128 mod p
+constexpr unsigned TWO_ADICITY = 55;
+constexpr uint64_t GENERATOR = 3;                          // multiplicative generator / LDE domain offset (canonical)
+constexpr uint64_t TWO_ADIC_ROOT = 0x0141727b75b35c50ULL;  // 3^131 mod p, canonical
+constexpr fe ZERO = 0, ONE = R;
+
+struct u128 { uint64_t lo, hi; };
+
+CSG_HD u128 mul_wide(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return {a * b, __umul64hi(a, b)};
+#else
+    unsigned __int128 t = (unsigned __int128)a * b;
+    return {(uint64_t)t, (uint64_t)(t >> 64)};
+#endif
+}
+
+// Montgomery reduction of t = hi * 2^64 + lo, t < p * 2^64.  Returns t * 2^-64 mod p in [0, p).
+CSG_HD fe redc(uint64_t lo, uint64_t hi) {
+    // m = lo * (p - 2) mod 2^64 = ((lo * 131) << 55) - lo        (p - 2 = 131 * 2^55 - 1)
+    // (t + m * p) / 2^64 = hi + floor(m * p / 2^64) + (lo != 0)  with  m * p = m + ((m * 131) << 55)
+    uint64_t m = ((lo * 131ULL) << 55) - lo;
+    // floor(m * p / 2^64): m*131 is a 72-bit number (h8 : l64); (m*131) << 55 contributes (m*131) >> 9 to the high
+    // word, and its low word ((m*131) & 511) << 55 can carry once when added to m.
+#if defined(__CUDA_ARCH__)
+    uint64_t l64 = m * 131ULL, h8 = __umul64hi(m, 131ULL);
+#else
+    unsigned __int128 w = (unsigned __int128)m * 131ULL;
+    uint64_t l64 = (uint64_t)w, h8 = (uint64_t)(w >> 64);
+#endif
+    uint64_t mp_hi = (l64 >> 9) | (h8 << 55);
+    uint64_t low = (l64 << 55);
+    uint64_t s = low + m;  // == -lo mod 2^64: the low words of t and m*p cancel
+    uint64_t u = hi + mp_hi + (s < low ? 1 : 0) + (lo != 0 ? 1 : 0);
+    return u >= P ? u - P : u;
+}
+
+CSG_HD fe mul(fe a, fe b) { u128 t = mul_wide(a, b); return redc(t.lo, t.hi); }
+CSG_HD fe sqr(fe a) { return mul(a, a); }
+CSG_HD fe add(fe a, fe b) { uint64_t s = a + b; return s >= P ? s - P : s; }
+CSG_HD fe sub(fe a, fe b) { return a >= b ? a - b : a + P - b; }
+CSG_HD fe neg(fe a) { return a ? P - a : 0; }
+CSG_HD fe dbl(fe a) { return add(a, a); }
+CSG_HD fe to_mont(uint64_t canonical) { return mul(canonical, R2); }   // canonical must be < p
+CSG_HD uint64_t from_mont(fe a) { return redc(a, 0); }
+CSG_HD fe pow(fe b, uint64_t e) {
+    fe r = ONE;
+    while (e) { if (e & 1) r = mul(r, b); b = sqr(b); e >>= 1; }
+    return r;
+}
+CSG_HD fe inv(fe a) { return pow(a, P - 2); }
+
+// ---- lazily reduced 128-bit accumulator: sum of up to 14 products a_i * b_i (each < p^2) fits in 128 bits
+struct acc128 {
+    uint64_t lo, hi;
+    CSG_HD acc128() : lo(0), hi(0) {}
+    CSG_HD void mac(fe a, fe b) {
+        u128 t = mul_wide(a, b);
+        lo += t.lo;
+        hi += t.hi + (lo < t.lo ? 1 : 0);
+    }
+    // value mod p (Montgomery-reduced): bring hi below p first so that t < p * 2^64
+    CSG_HD fe reduce() const {
+        uint64_t h = hi;
+        if (h >= 2 * P) h -= 2 * P;
+        if (h >= P) h -= P;
+        return redc(lo, h);
+    }
+};
+
+#if !defined(__CUDA_ARCH__)
+inline fe root_of_unity(unsigned logn) {  // primitive 2^logn-th root (winterfell StarkField::get_root_of_unity)
+    fe r = to_mont(TWO_ADIC_ROOT);
+    for (unsigned i = logn; i < TWO_ADICITY; i++) r = sqr(r);
+    return r;
+}
+#endif
+
+}  // namespace f63

@@ -1,0 +1,131 @@
+/* csg.h -- C ABI of libcsg.so, the B200-native proving backend for certificate-stark.
+ *
+ * The reference has no FFI: its hot path is entered through the Rust trait call
+ *     prover.prove(trace)                      /root/reference/src/lib.rs:140
+ * (also src/schnorr/mod.rs:171, src/merkle/init/mod.rs:105, src/merkle/update/mod.rs:105, src/range/mod.rs:99,
+ * benches/rescue.rs:84), which dispatches into winterfell's generic `Prover::prove` with the AIR the crate defines
+ * through `impl Air` (src/air.rs:70-189 and the five sub-AIRs).  Generic Rust cannot cross an FFI boundary, so the
+ * AIR is selected by id and everything the Rust side owns (trace, public inputs, ProofOptions, Fiat-Shamir
+ * challenges) crosses as plain integers in CANONICAL form (BaseElement::to_repr), little-endian u64.
+ *
+ * Two levels are exported:
+ *   1. csg_prove()            one call = Prover::prove(trace) -> StarkProof::to_bytes()
+ *   2. csg_set_air() .. csg_open()   the per-stage calls a patched winterfell `generate_proof` would make,
+ *                             keeping the transcript (RandomCoin) and proof serialisation on the Rust side.
+ * plus the witness builders (build_trace of each prover) and a few kernel-level entry points used by the
+ * parity tests and the kernel sweep.  All functions return 0 on success; they never unwind.  A context is
+ * single-threaded and owns all device memory; every pointer argument is a HOST pointer owned by the caller.
+ */
+#ifndef CSG_H
+#define CSG_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { CSG_OK = 0, CSG_ERR_ARG = 1, CSG_ERR_CUDA = 2, CSG_ERR_STATE = 3, CSG_ERR_UNSUPPORTED = 4, CSG_ERR_COIN = 5 };
+
+/* AIR ids: the six `impl Air` of the reference */
+enum {
+    CSG_AIR_TRANSACTION = 0,   /* TransactionAir   src/air.rs:64-189            94 cols, 115 constraints */
+    CSG_AIR_MERKLE_UPDATE = 1, /* MerkleAir        src/merkle/update/air.rs     65 cols, 106 constraints */
+    CSG_AIR_MERKLE_INIT = 2,   /* PreMerkleAir     src/merkle/init/air.rs       58 cols,  56 constraints */
+    CSG_AIR_SCHNORR = 3,       /* SchnorrAir       src/schnorr/air.rs           56 cols,  56 constraints */
+    CSG_AIR_RANGE = 4,         /* RangeProofAir    src/range/air.rs              2 cols,   2 constraints */
+    CSG_AIR_RESCUE = 5         /* RescueAir        benches/rescue.rs:163-268    14 cols,  14 constraints */
+};
+enum { CSG_HASH_BLAKE3_256 = 2, CSG_HASH_SHA3_256 = 3 }; /* HashFunction (src/lib.rs:82, examples/state-transition.rs:67-71) */
+enum { CSG_FIELD_EXT_NONE = 1 };                          /* FieldExtension::None (src/lib.rs:83) */
+
+/* ProofOptions::new(num_queries, blowup_factor, grinding_factor, hash_fn, field_extension, fri_folding_factor,
+ * fri_max_remainder_size)  -- src/lib.rs:78-86 */
+typedef struct {
+    uint32_t num_queries, blowup_factor, grinding_factor, hash_fn, field_extension, fri_folding_factor, fri_max_remainder_size;
+} csg_options;
+
+typedef struct csg_ctx csg_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------------- */
+csg_ctx *csg_create(int device);            /* NULL if the device cannot be opened */
+void csg_destroy(csg_ctx *ctx);
+const char *csg_last_error(const csg_ctx *ctx);
+void csg_free(void *p);                     /* frees buffers returned by csg_prove */
+
+/* ---- level 1: replaces `prover.prove(trace)` (src/lib.rs:140) -------------------------------------------------
+ * trace: column-major [width][trace_len], canonical, exactly TraceTable's storage.
+ * pub:   the AIR's PublicInputs as canonical words in write_into() order:
+ *        TRANSACTION / MERKLE_UPDATE  initial_root[7] final_root[7]      (src/air.rs:57-62)
+ *        MERKLE_INIT                  s_inputs[14] r_inputs[14] delta    (src/merkle/init/air.rs:36-42)
+ *        SCHNORR                      per signature: message[28] Rx[6] s[4 LE words]  (src/schnorr/air.rs:38-46)
+ *        RANGE                        number                              (src/range/air.rs:33-37)
+ *        RESCUE                       seed[7] result[7]                   (benches/rescue.rs:136-141)
+ * proof: malloc'ed StarkProof::to_bytes(); release with csg_free. */
+int csg_prove(csg_ctx *ctx, int air_id, const uint64_t *trace, size_t trace_len, const uint64_t *pub, size_t npub,
+              const csg_options *opt, uint8_t **proof, size_t *proof_len);
+
+/* ---- level 2: the stages of Prover::prove, transcript on the caller's side --------------------------------------
+ * call order: set_air, load_trace, [extend_and_commit_trace, eval_constraints, commit_composition, ood, deep,
+ * (fri_commit_layer, fri_fold)*, fri_remainder, open]; prove_loaded() runs the bracketed part with the built-in
+ * transcript.  Challenges are canonical field elements drawn by the caller's RandomCoin. */
+int csg_set_air(csg_ctx *ctx, int air_id, size_t trace_len, const csg_options *opt, const uint64_t *pub, size_t npub);
+int csg_load_trace(csg_ctx *ctx, const uint64_t *trace);                     /* H2D copy of width*trace_len words */
+int csg_prove_loaded(csg_ctx *ctx, uint8_t **proof, size_t *proof_len);      /* proof of the resident trace */
+int csg_extend_and_commit_trace(csg_ctx *ctx, uint8_t root[32]);             /* Trace::extend + build_commitment */
+/* t_coeffs: (alpha,beta) per transition constraint; b_coeffs: (alpha,beta) per assertion in winterfell's sorted order */
+int csg_eval_constraints(csg_ctx *ctx, const uint64_t *t_coeffs, const uint64_t *b_coeffs);
+int csg_commit_composition(csg_ctx *ctx, uint8_t root[32]);                  /* into_poly + evaluate + commit */
+/* OOD frame at z: trace polys at z and z*g (width each), composition columns at z^m (m = ce blowup) */
+int csg_ood(csg_ctx *ctx, uint64_t z, uint64_t *frame_cur, uint64_t *frame_next, uint64_t *comp);
+/* DEEP coefficients: per trace column (alpha, beta), per composition column delta, then (lambda, mu) */
+int csg_deep(csg_ctx *ctx, const uint64_t *trace_ab, const uint64_t *comp_d, const uint64_t lambda_mu[2]);
+int csg_fri_commit_layer(csg_ctx *ctx, uint8_t root[32]);                    /* transpose/4, hash, Merkle */
+int csg_fri_fold(csg_ctx *ctx, uint64_t alpha);                              /* degree-respecting projection */
+int csg_fri_remainder(csg_ctx *ctx, uint64_t *out, size_t cap, size_t *len);
+/* openings at the query positions: rows are written row-major, paths in BatchMerkleProof::serialize_nodes() form */
+int csg_open_trace(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len);
+int csg_open_composition(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len);
+int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len);
+
+/* per-stage device times of the last proof, milliseconds (CUDA events on the proving stream) */
+typedef struct {
+    float h2d, lde, commit_trace, constraints, composition, ood_deep, fri, queries, total;
+    uint64_t kernel_launches; /* kernels launched by the last proof */
+} csg_timings;
+int csg_get_timings(const csg_ctx *ctx, csg_timings *out);
+
+/* ---- witness builders: build_trace() of each prover -------------------------------------------------------------
+ * Traces are column-major canonical; `pub` receives get_pub_inputs(). */
+typedef struct csg_tx_batch csg_tx_batch;   /* TransactionMetadata  (src/lib.rs:188-232) */
+typedef struct csg_sig_batch csg_sig_batch; /* SchnorrExample's messages + signatures (src/schnorr/mod.rs:71-76) */
+csg_tx_batch *csg_tx_batch_new(uint64_t seed, size_t num_tx, unsigned tree_depth); /* build_random, seeded (src/lib.rs:235-464) */
+void csg_tx_batch_free(csg_tx_batch *b);
+size_t csg_tx_batch_size(const csg_tx_batch *b);
+void csg_tx_batch_roots(const csg_tx_batch *b, uint64_t initial_root[7], uint64_t final_root[7]);
+int csg_build_trace_transaction(const csg_tx_batch *b, uint64_t *trace /* 94 x 1024*num_tx */, uint64_t pub[14]);   /* src/prover.rs:37-98 */
+int csg_build_trace_merkle_update(const csg_tx_batch *b, uint64_t *trace /* 65 x 512*num_tx */, uint64_t pub[14]); /* src/merkle/update/prover.rs:37-80 */
+int csg_build_trace_merkle_init(const uint64_t s_inputs[14], const uint64_t r_inputs[14], uint64_t delta,
+                                uint64_t *trace /* 58 x 16 */, uint64_t pub[29]);                                   /* src/merkle/init/prover.rs:35-53 */
+csg_sig_batch *csg_sig_batch_new(uint64_t seed, size_t num_sig);
+void csg_sig_batch_free(csg_sig_batch *b);
+size_t csg_sig_batch_size(const csg_sig_batch *b);
+int csg_build_trace_schnorr(const csg_sig_batch *b, uint64_t *trace /* 56 x 512*num_sig */, uint64_t *pub /* 38*num_sig */); /* src/schnorr/prover.rs:52-80 */
+int csg_build_trace_range(uint64_t number, uint64_t *trace /* 2 x 64 */, uint64_t pub[1]);                          /* src/range/prover.rs:36-56 */
+int csg_build_trace_rescue(const uint64_t seed[7], size_t chain_length, uint64_t *trace /* 14 x 8*len */, uint64_t pub[14]); /* benches/rescue.rs:279-321 */
+
+/* ---- kernel-level entry points (parity tests, kernel sweep).  Host buffers in/out; values canonical ------------- */
+/* per-column inverse NTT + coset LDE: cols [width][n] -> lde [width][n*blowup], natural order x_j = 3 * w^j */
+int csg_k_lde(csg_ctx *ctx, const uint64_t *cols, size_t width, size_t n, size_t blowup, uint64_t *lde);
+/* Blake3/SHA3 of every row of a column-major matrix [width][rows] -> rows*32 bytes */
+int csg_k_hash_rows(csg_ctx *ctx, int hash_fn, const uint64_t *cols, size_t width, size_t rows, uint8_t *digests);
+/* Merkle tree over nleaves 32-byte leaves -> nodes[2*nleaves][32], nodes[1] = root */
+int csg_k_merkle(csg_ctx *ctx, int hash_fn, const uint8_t *leaves, size_t nleaves, uint8_t *nodes);
+/* one FRI fold by 4 (domain offset 3, size n) */
+int csg_k_fri_fold4(csg_ctx *ctx, const uint64_t *evals, size_t n, uint64_t alpha, uint64_t *out);
+/* kernel sweep: LDE + row hash + Merkle over device-resident synthetic columns; returns per-stage ms */
+int csg_k_sweep(csg_ctx *ctx, size_t width, size_t n, size_t blowup, int hash_fn, int iters, float ms_out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

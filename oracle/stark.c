@@ -71,7 +71,7 @@ static fe poly_eval(const fe *c, size_t n, fe x) { fe r = 0; for (size_t i = n; 
 
 /* ------------------------------------------------------------------ hashing of elements, Merkle trees */
 void hash_elements(int hash_fn, const fe *e, size_t n, uint8_t out[32]) {
-    uint8_t stackbuf[1024], *b = n * 8 <= sizeof stackbuf ? stackbuf : malloc(n * 8);
+    uint8_t stackbuf[1024] = {0}, *b = n * 8 <= sizeof stackbuf ? stackbuf : malloc(n * 8);
     for (size_t i = 0; i < n; i++) { uint64_t v = fe_to_u64(e[i]); memcpy(b + 8 * i, &v, 8); }
     hash_bytes(hash_fn, b, n * 8, out);
     if (b != stackbuf) free(b);
@@ -438,9 +438,11 @@ int stark_prove(int air_id, const uint64_t *trace, size_t n, const uint64_t *pub
             fe *poly = malloc(P * sizeof(fe));
             memcpy(poly, air->periodic[c], P * sizeof(fe));
             ntt_natural(poly, P, 1);
-            ptab[c] = malloc(per * sizeof(fe));
-            fe y0 = fe_exp(offset, n / P), gy = fe_exp(g_ce, n / P), y = y0;
-            for (size_t s = 0; s < per; s++) { ptab[c][s] = poly_eval(poly, P, y); y = fe_mul(y, gy); }
+            /* values at y_s = offset^(n/P) * w_per^s, s < per: one size-`per` NTT of the coefficients scaled by offset^(n/P * i) */
+            ptab[c] = calloc(per, sizeof(fe));
+            fe y0 = fe_exp(offset, n / P), sc = FE_ONE;
+            for (size_t i = 0; i < P; i++) { ptab[c][i] = fe_mul(poly[i], sc); sc = fe_mul(sc, y0); }
+            ntt_natural(ptab[c], per, 0);
             free(poly);
         }
 #pragma omp parallel
