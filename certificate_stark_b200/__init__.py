@@ -1,0 +1,314 @@
+"""certificate_stark_b200 -- B200-native proving backend for the STARK prover of toposware/certificate-stark.
+
+The product is ``lib/libcsg.so`` (hand-written sm_100a CUDA kernels + a C++ host driver) behind the C ABI declared in
+``include/csg.h``.  This module is the thin host-side mirror of the reference's example/prover interface
+(``TransactionExample::{new, prove}`` at /root/reference/src/lib.rs:75-141, ``ProofOptions`` at src/lib.rs:78-86, and the
+five sub-AIR examples), implemented over that C ABI with ctypes.  There is no CPU fallback: if the shared library is
+missing or no CUDA device can be opened, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+LIB_PATH = ROOT / "lib" / "libcsg.so"
+P = 0x4180000000000001  # f63 modulus (/root/reference/src/range/tests.rs:59)
+
+AIR_TRANSACTION, AIR_MERKLE_UPDATE, AIR_MERKLE_INIT, AIR_SCHNORR, AIR_RANGE, AIR_RESCUE = range(6)
+HASH_BLAKE3_256, HASH_SHA3_256 = 2, 3
+FIELD_EXTENSION_NONE = 1
+TRACE_WIDTH = {AIR_TRANSACTION: 94, AIR_MERKLE_UPDATE: 65, AIR_MERKLE_INIT: 58, AIR_SCHNORR: 56, AIR_RANGE: 2, AIR_RESCUE: 14}
+_ERRORS = {1: "invalid argument", 2: "CUDA error", 3: "call out of order", 4: "unsupported", 5: "random coin failure"}
+
+
+class CsgError(RuntimeError):
+    pass
+
+
+class ProofOptions(C.Structure):
+    """ProofOptions::new(num_queries, blowup_factor, grinding_factor, hash_fn, field_extension, fri_folding_factor,
+    fri_max_remainder_size) -- same argument order as the reference (src/lib.rs:78-86)."""
+    _fields_ = [(n, C.c_uint32) for n in ("num_queries", "blowup_factor", "grinding_factor", "hash_fn", "field_extension",
+                                          "fri_folding_factor", "fri_max_remainder_size")]
+
+    def __init__(self, num_queries=42, blowup_factor=8, grinding_factor=0, hash_fn=HASH_BLAKE3_256,
+                 field_extension=FIELD_EXTENSION_NONE, fri_folding_factor=4, fri_max_remainder_size=256):
+        super().__init__(num_queries, blowup_factor, grinding_factor, hash_fn, field_extension, fri_folding_factor, fri_max_remainder_size)
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d", "lde", "commit_trace", "constraints", "composition", "ood_deep", "fri", "queries", "total")] + \
+               [("kernel_launches", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def build(force: bool = False) -> Path:
+    """Compile lib/libcsg.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.check_call(["make", "-C", str(ROOT / "csrc"), "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", str(ROOT / "csrc"), "-j", str(min(8, os.cpu_count() or 1))], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+_u64p, _u8p, _szp = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_size_t)
+
+
+def lib() -> C.CDLL:
+    """The loaded C-ABI library.  Raises if it has not been built: there is no other implementation to fall back to."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise CsgError(f"{LIB_PATH} is missing: run certificate_stark_b200.build() (needs nvcc); there is no CPU fallback")
+    L = C.CDLL(str(LIB_PATH))
+    vp, opt = C.c_void_p, C.POINTER(ProofOptions)
+    sig = {
+        "csg_create": (vp, [C.c_int]), "csg_destroy": (None, [vp]), "csg_last_error": (C.c_char_p, [vp]), "csg_free": (None, [vp]),
+        "csg_prove": (C.c_int, [vp, C.c_int, _u64p, C.c_size_t, _u64p, C.c_size_t, opt, C.POINTER(_u8p), _szp]),
+        "csg_set_air": (C.c_int, [vp, C.c_int, C.c_size_t, opt, _u64p, C.c_size_t]),
+        "csg_load_trace": (C.c_int, [vp, _u64p]), "csg_reload_resident_trace": (C.c_int, [vp]),
+        "csg_prove_loaded": (C.c_int, [vp, C.POINTER(_u8p), _szp]),
+        "csg_extend_and_commit_trace": (C.c_int, [vp, _u8p]), "csg_eval_constraints": (C.c_int, [vp, _u64p, _u64p]),
+        "csg_commit_composition": (C.c_int, [vp, _u8p]), "csg_ood": (C.c_int, [vp, C.c_uint64, _u64p, _u64p, _u64p]),
+        "csg_deep": (C.c_int, [vp, _u64p, _u64p, _u64p]), "csg_fri_commit_layer": (C.c_int, [vp, _u8p]),
+        "csg_fri_fold": (C.c_int, [vp, C.c_uint64]), "csg_fri_remainder": (C.c_int, [vp, _u64p, C.c_size_t, _szp]),
+        "csg_open_trace": (C.c_int, [vp, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
+        "csg_open_composition": (C.c_int, [vp, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
+        "csg_open_fri_layer": (C.c_int, [vp, C.c_size_t, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
+        "csg_get_timings": (C.c_int, [vp, C.POINTER(Timings)]),
+        "csg_tx_batch_new": (vp, [C.c_uint64, C.c_size_t, C.c_uint]), "csg_tx_batch_free": (None, [vp]), "csg_tx_batch_size": (C.c_size_t, [vp]),
+        "csg_tx_batch_roots": (None, [vp, _u64p, _u64p]),
+        "csg_build_trace_transaction": (C.c_int, [vp, _u64p, _u64p]), "csg_build_trace_merkle_update": (C.c_int, [vp, _u64p, _u64p]),
+        "csg_build_trace_merkle_init": (C.c_int, [_u64p, _u64p, C.c_uint64, _u64p, _u64p]),
+        "csg_sig_batch_new": (vp, [C.c_uint64, C.c_size_t]), "csg_sig_batch_free": (None, [vp]), "csg_sig_batch_size": (C.c_size_t, [vp]),
+        "csg_build_trace_schnorr": (C.c_int, [vp, _u64p, _u64p]), "csg_build_trace_range": (C.c_int, [C.c_uint64, _u64p, _u64p]),
+        "csg_build_trace_rescue": (C.c_int, [_u64p, C.c_size_t, _u64p, _u64p]),
+        "csg_k_lde": (C.c_int, [vp, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
+        "csg_k_hash_rows": (C.c_int, [vp, C.c_int, _u64p, C.c_size_t, C.c_size_t, _u8p]),
+        "csg_k_merkle": (C.c_int, [vp, C.c_int, _u8p, C.c_size_t, _u8p]),
+        "csg_k_fri_fold4": (C.c_int, [vp, _u64p, C.c_size_t, C.c_uint64, _u64p]),
+        "csg_k_sweep": (C.c_int, [vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _p64(a):
+    return a.ctypes.data_as(_u64p)
+
+
+def _p8(a):
+    return a.ctypes.data_as(_u8p)
+
+
+class Context:
+    """One proving context = one CUDA device + one stream; owns all device memory (csg_create / csg_destroy)."""
+
+    def __init__(self, device: int = 0):
+        self._h = lib().csg_create(device)
+        if not self._h:
+            raise CsgError(f"cannot open CUDA device {device}: the CUDA backend is required, there is no CPU fallback")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().csg_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = lib().csg_last_error(self._h)
+            raise CsgError(f"{_ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def _take_proof(self, out, n):
+        proof = C.string_at(out, n.value)
+        lib().csg_free(out)
+        return proof
+
+    # ---- level 1: Prover::prove(trace)
+    def prove(self, air_id: int, trace: np.ndarray, pub: np.ndarray, options: ProofOptions) -> bytes:
+        """trace: (width, n) canonical uint64 column-major table (TraceTable's layout) in HOST memory -> StarkProof bytes."""
+        trace = np.ascontiguousarray(trace, dtype=np.uint64)
+        pub = np.ascontiguousarray(pub, dtype=np.uint64)
+        if trace.ndim != 2 or trace.shape[0] != TRACE_WIDTH[air_id]:
+            raise CsgError(f"trace must be ({TRACE_WIDTH[air_id]}, n)")
+        out, n = _u8p(), C.c_size_t()
+        self._check(lib().csg_prove(self._h, air_id, _p64(trace), trace.shape[1], _p64(pub), pub.size, C.byref(options), C.byref(out), C.byref(n)))
+        return self._take_proof(out, n)
+
+    # ---- level 2 pieces used by benchmarks: trace resident in HBM, proved repeatedly
+    def set_air(self, air_id, trace_len, pub, options):
+        pub = np.ascontiguousarray(pub, dtype=np.uint64)
+        self._check(lib().csg_set_air(self._h, air_id, trace_len, C.byref(options), _p64(pub), pub.size))
+
+    def load_trace(self, trace):
+        trace = np.ascontiguousarray(trace, dtype=np.uint64)
+        self._check(lib().csg_load_trace(self._h, _p64(trace)))
+
+    def load_trace_ptr(self, host_ptr: int):
+        """same, from a raw host pointer (e.g. a pinned torch tensor's data_ptr())"""
+        self._check(lib().csg_load_trace(self._h, C.cast(host_ptr, _u64p)))
+
+    def reload_resident_trace(self):
+        self._check(lib().csg_reload_resident_trace(self._h))
+
+    def prove_loaded(self) -> bytes:
+        out, n = _u8p(), C.c_size_t()
+        self._check(lib().csg_prove_loaded(self._h, C.byref(out), C.byref(n)))
+        return self._take_proof(out, n)
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(lib().csg_get_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    # ---- kernel-level entry points (parity tests, kernel sweep); canonical values in host arrays
+    def lde(self, cols: np.ndarray, blowup: int) -> np.ndarray:
+        cols = np.ascontiguousarray(cols, dtype=np.uint64)
+        out = np.empty((cols.shape[0], cols.shape[1] * blowup), dtype=np.uint64)
+        self._check(lib().csg_k_lde(self._h, _p64(cols), cols.shape[0], cols.shape[1], blowup, _p64(out)))
+        return out
+
+    def hash_rows(self, cols: np.ndarray, hash_fn: int = HASH_BLAKE3_256) -> np.ndarray:
+        cols = np.ascontiguousarray(cols, dtype=np.uint64)
+        out = np.empty((cols.shape[1], 32), dtype=np.uint8)
+        self._check(lib().csg_k_hash_rows(self._h, hash_fn, _p64(cols), cols.shape[0], cols.shape[1], _p8(out)))
+        return out
+
+    def merkle(self, leaves: np.ndarray, hash_fn: int = HASH_BLAKE3_256) -> np.ndarray:
+        leaves = np.ascontiguousarray(leaves, dtype=np.uint8).reshape(-1, 32)
+        out = np.empty((2 * leaves.shape[0], 32), dtype=np.uint8)
+        self._check(lib().csg_k_merkle(self._h, hash_fn, _p8(leaves), leaves.shape[0], _p8(out)))
+        return out
+
+    def fri_fold4(self, evals: np.ndarray, alpha: int) -> np.ndarray:
+        evals = np.ascontiguousarray(evals, dtype=np.uint64)
+        out = np.empty(evals.size // 4, dtype=np.uint64)
+        self._check(lib().csg_k_fri_fold4(self._h, _p64(evals), evals.size, alpha, _p64(out)))
+        return out
+
+    def sweep(self, width: int, n: int, blowup: int, hash_fn: int = HASH_BLAKE3_256, iters: int = 3) -> dict:
+        ms = (C.c_float * 4)()
+        self._check(lib().csg_k_sweep(self._h, width, n, blowup, hash_fn, iters, ms))
+        return dict(zip(("lde_ms", "hash_rows_ms", "merkle_ms", "fri_fold_ms"), [float(v) for v in ms]))
+
+
+# ---------------------------------------------------------------------------------------------- witness builders (host)
+def build_rescue_trace(seed, chain_length):
+    """RescueProver::build_trace (benches/rescue.rs:279-321) -> (trace (14, 8*len), pub = seed[7] result[7])"""
+    seed = np.ascontiguousarray(seed, dtype=np.uint64)
+    trace, pub = np.zeros((14, 8 * chain_length), dtype=np.uint64), np.zeros(14, dtype=np.uint64)
+    if lib().csg_build_trace_rescue(_p64(seed), chain_length, _p64(trace), _p64(pub)):
+        raise CsgError("chain length must be a power of two")
+    return trace, pub
+
+
+def build_range_trace(number):
+    """RangeProver::build_trace (src/range/prover.rs:36-56)"""
+    trace, pub = np.zeros((2, 64), dtype=np.uint64), np.zeros(1, dtype=np.uint64)
+    lib().csg_build_trace_range(number, _p64(trace), _p64(pub))
+    return trace, pub
+
+
+def build_merkle_init_trace(s_inputs, r_inputs, delta):
+    """PreMerkleProver::build_trace (src/merkle/init/prover.rs:35-53)"""
+    s, r = np.ascontiguousarray(s_inputs, dtype=np.uint64), np.ascontiguousarray(r_inputs, dtype=np.uint64)
+    trace, pub = np.zeros((58, 16), dtype=np.uint64), np.zeros(29, dtype=np.uint64)
+    lib().csg_build_trace_merkle_init(_p64(s), _p64(r), delta, _p64(trace), _p64(pub))
+    return trace, pub
+
+
+class TransactionBatch:
+    """Seeded stand-in for TransactionMetadata::build_random (src/lib.rs:235-464): accounts in a Rescue Merkle tree,
+    num_tx signed transfers.  The reference draws from OsRng; here everything derives from `seed`."""
+
+    def __init__(self, seed: int, num_tx: int, tree_depth: int = 15):
+        self._h = lib().csg_tx_batch_new(seed, num_tx, tree_depth)
+        if not self._h:
+            raise CsgError("bad transaction batch parameters")
+        self.num_tx = num_tx
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().csg_tx_batch_free(self._h)
+            self._h = None
+
+    def transaction_trace(self, out: np.ndarray | None = None):
+        """TransactionProver::build_trace (src/prover.rs:37-98) -> (trace (94, 1024*num_tx), pub[14])"""
+        trace = out if out is not None else np.zeros((94, 1024 * self.num_tx), dtype=np.uint64)
+        pub = np.zeros(14, dtype=np.uint64)
+        if lib().csg_build_trace_transaction(self._h, _p64(trace), _p64(pub)):
+            raise CsgError("number of transactions must be a power of two")
+        return trace, pub
+
+    def merkle_update_trace(self):
+        """MerkleProver::build_trace (src/merkle/update/prover.rs:37-80) -> (trace (65, 512*num_tx), pub[14])"""
+        trace, pub = np.zeros((65, 512 * self.num_tx), dtype=np.uint64), np.zeros(14, dtype=np.uint64)
+        if lib().csg_build_trace_merkle_update(self._h, _p64(trace), _p64(pub)):
+            raise CsgError("number of transactions must be a power of two")
+        return trace, pub
+
+
+class SignatureBatch:
+    """Seeded stand-in for SchnorrExample::new's random messages and signatures (src/schnorr/mod.rs:79-141)."""
+
+    def __init__(self, seed: int, num_sig: int):
+        self._h = lib().csg_sig_batch_new(seed, num_sig)
+        if not self._h:
+            raise CsgError("bad signature batch parameters")
+        self.num_sig = num_sig
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().csg_sig_batch_free(self._h)
+            self._h = None
+
+    def schnorr_trace(self):
+        """SchnorrProver::build_trace (src/schnorr/prover.rs:52-80) -> (trace (56, 512*num_sig), pub[38*num_sig])"""
+        trace, pub = np.zeros((56, 512 * self.num_sig), dtype=np.uint64), np.zeros(38 * self.num_sig, dtype=np.uint64)
+        if lib().csg_build_trace_schnorr(self._h, _p64(trace), _p64(pub)):
+            raise CsgError("number of signatures must be a power of two")
+        return trace, pub
+
+
+# ---------------------------------------------------------------------------------------------- the reference's example façade
+def get_example(num_transactions: int, seed: int = 1, device: int = 0) -> "TransactionExample":
+    """get_example() of the reference (src/lib.rs:75-89): default options 42 queries, blowup 8, Blake3_256, no extension,
+    FRI folding 4, max remainder 256."""
+    return TransactionExample(ProofOptions(), num_transactions, seed=seed, device=device)
+
+
+class TransactionExample:
+    """TransactionExample::{new, prove} (src/lib.rs:92-141): a batch of transactions and the proof of their state transition.
+    `verify` is not part of the GPU path (src/lib.rs:144-150 calls winterfell::verify on the host) and is not provided."""
+
+    def __init__(self, options: ProofOptions, num_transactions: int, seed: int = 1, device: int = 0):
+        if num_transactions < 1 or num_transactions & (num_transactions - 1):
+            raise CsgError("number of transactions must be a power of 2")  # src/lib.rs:100-103
+        self.options = options
+        self.batch = TransactionBatch(seed, num_transactions)
+        self.ctx = Context(device)
+        self.pub_inputs = None
+
+    def prove(self) -> bytes:
+        trace, pub = self.batch.transaction_trace()      # prover.build_trace(&tx_metadata)   src/lib.rs:130
+        self.pub_inputs = pub
+        return self.ctx.prove(AIR_TRANSACTION, trace, pub, self.options)   # prover.prove(trace)   src/lib.rs:140

@@ -1,0 +1,407 @@
+// Per-row transition-constraint evaluation of the six AIRs of the reference, fused with winterfell's random linear
+// combination (K5 of SURVEY.md section 2.2).  What the reference computes per constraint-evaluation-domain row is
+//     result[] = 0;  Air::evaluate_transition(frame, periodic_values, result);      (src/air.rs:114-173 -> :383-610)
+//     T(x) = sum_i result[i] * (alpha_i + beta_i * x^adj(group(i)))                    (winterfell ConstraintEvaluator)
+// Here result[] is never materialised: every contribution `result[slot] += flag * value` (agg_constraint,
+// src/utils/mod.rs:58-62) is folded straight into the 192-bit lazily reduced accumulator of T, grouped by flag so
+// that a flag is multiplied in once per group.  All arithmetic is exact modulo p, so the value of T is identical to
+// the reference's whatever the order of evaluation.
+//
+// Reference functions restated (polynomial identities only, no code shared):
+//   TransactionAir::evaluate_transition / evaluate_constraints      src/air.rs:114-173, 383-610
+//   merkle::init::evaluate_constraints                              src/merkle/init/air.rs:159-202
+//   merkle::update::evaluate_constraints / evaluate_merkle_update_auth   src/merkle/update/air.rs:215-369
+//   schnorr::evaluate_constraints / enforce_hash_copy               src/schnorr/air.rs:394-531, 309-330
+//   ecc::enforce_point_doubling / _addition_mixed / _addition_reduce_x   src/utils/ecc.rs:73-172
+//   rescue::enforce_round                                           src/utils/rescue.rs:269-300
+//   field::enforce_double_and_add_step(_constrained)                src/utils/field.rs:31-70
+//   RangeProofAir / RescueAir evaluate_transition                   src/range/air.rs:69-105, benches/rescue.rs:205-222
+#pragma once
+#include "ecc.cuh"
+#include "rescue.cuh"
+
+namespace airs {
+using f63::fe;
+
+enum : int { TRANSACTION = 0, MERKLE_UPDATE = 1, MERKLE_INIT = 2, SCHNORR = 3, RANGE = 4, RESCUE = 5 };
+
+// ---- layout (src/merkle/constants.rs:27-56, src/constants.rs:35-116, src/schnorr/constants.rs) ----
+enum : int {
+    HSW = 14, HRW = 7, APW = 12, PPW = 18, PCW = 6,
+    SENDER_INITIAL = 0, SENDER_BIT = 14, SENDER_UPDATED = 15, RECEIVER_INITIAL = 29, RECEIVER_BIT = 43, RECEIVER_UPDATED = 44,
+    PREV_ROOT = 58, VALUE_RES = 65, BALANCE_RES = 90, NONCE_RES = 91, INT_ROOT_RES = 92, ROOT_MATCH_RES = 99,
+    SENDER_KEY = 65, RECEIVER_KEY = 77, DELTA_COPY = 89, SIGMA_COPY = 90, NONCE_COPY = 91,
+    SENDER_KEY_RES = 101, RECEIVER_KEY_RES = 103, DELTA_COPY_RES = 105, SIGMA_COPY_RES = 106, NONCE_COPY_RES = 107,
+    DELTA_RANGE_RES = 108, SIGMA_RANGE_RES = 109,
+    DELTA_BIT = 56, DELTA_ACC = 57, SIGMA_BIT = 92, SIGMA_ACC = 93,
+    LIMBS = 2 * PPW + 1,   // 37: h bit, then the four limb accumulators
+    SIG_HASH = 2 * PPW + 6  // 42: Rescue state of the message hash
+};
+// periodic-column indices of the transaction AIR (src/constants.rs:85-116)
+enum : int {
+    TX_SETUP = 0, TX_MERKLE = 1, TX_HASH_INPUT = 2, TX_FINISH = 3, TX_HASH = 4, TX_SCHNORR = 5, TX_SCALAR_MULT = 6, TX_DOUBLING = 7,
+    TX_DIGEST = 8, TX_SCHNORR_HASH = 12, TX_INTERNAL = 13, TX_RANGE_STEP = 17, TX_RANGE_FINISH = 18, TX_VALUE_COPY = 19, TX_ARK = 20
+};
+
+constexpr int MAX_GROUPS = 8;
+
+// two consecutive rows of the (extended) trace; column c of the current row is cur_p[c * stride]
+struct Frame {
+    const fe *cur_p, *next_p;
+    size_t stride;
+    CSG_HD fe cur(int c) const { return cur_p[(size_t)c * stride]; }
+    CSG_HD fe next(int c) const { return next_p[(size_t)c * stride]; }
+};
+// periodic column c at this row: tab[off[c] + (i & mask[c])]
+struct Periodic {
+    const fe *tab;
+    const uint32_t *off, *mask;
+    uint32_t i;
+    CSG_HD fe operator()(int c) const { return tab[off[c] + (i & mask[c])]; }
+};
+
+// the random linear combination: coefficient of result slot s at this row is alpha[s] + beta[s] * xp[group[s]]
+struct Comb {
+    const fe *alpha, *beta;
+    const uint8_t *group;
+    const fe *xp;        // x^adj per degree group, element g at xp[g * xp_stride]
+    size_t xp_stride;
+    f63::acc192 sum;
+    CSG_HD fe coef(int slot) const { return f63::add(alpha[slot], f63::mul(beta[slot], xp[group[slot] * xp_stride])); }
+    CSG_HD void add(int slot, fe v) { sum.mac(coef(slot), v); }
+};
+// contributions that share one flag: sum_k coef(slot_k) * v_k, multiplied by the flag once at the end
+struct FlagAcc {
+    f63::acc192 s;
+    CSG_HD void add(const Comb &C, int slot, fe v) { s.mac(C.coef(slot), v); }
+    CSG_HD void flush(Comb &C, fe flag) { C.sum.mac(flag, s.reduce()); }
+};
+
+CSG_HD fe f_not(fe a) { return f63::sub(f63::ONE, a); }
+CSG_HD fe f_bin(fe a) { return f63::sub(f63::sqr(a), a); }
+
+// ---- Rescue round: backward_half(next) - forward_half(cur) of the 14-wide state at column col0, round constants from
+// periodic columns ark0..ark0+27; up to two (flag, first slot) users of the same residual
+template <class PV>
+CSG_HD void rescue_state(const Frame &f, const PV &pv, Comb &C, int col0, int ark0, fe flag_a, int slot_a, bool second, fe flag_b, int slot_b) {
+    fe cur[14], next[14], ark[28], d[14];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 14; i++) { cur[i] = f.cur(col0 + i); next[i] = f.next(col0 + i); }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 28; i++) ark[i] = pv(ark0 + i);
+    rescue::round_residual(cur, next, ark, d);
+    FlagAcc a;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 0; i < 14; i++) a.add(C, slot_a + i, d[i]);
+    a.flush(C, flag_a);
+    if (second) {
+        FlagAcc b;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int i = 0; i < 14; i++) b.add(C, slot_b + i, d[i]);
+        b.flush(C, flag_b);
+    }
+}
+
+// ---- merkle::update::evaluate_merkle_update_auth without its two Rescue rounds (src/merkle/update/air.rs:291-369)
+CSG_HD void merkle_auth_path(const Frame &f, Comb &C, int base, fe tx_hash, fe hash_input, fe hashf) {
+    const fe copy_flag = f63::mul(tx_hash, f_not(f63::add(hashf, hash_input)));
+    const fe init_flag = f63::mul(tx_hash, hash_input);
+    const fe bit = f.next(base + HSW), nbit = f_not(bit);
+    C.add(base + HSW, f63::mul(tx_hash, f_bin(bit)));
+    FlagAcc keep, to_rate, place_bit, place_nbit;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 0; k < 2; k++) {
+        const int o = base + k * (HSW + 1);
+        for (int i = 0; i < HRW; i++) {
+            fe c = f.cur(o + i);
+            keep.add(C, o + i, f63::sub(c, f.next(o + i)));                 // copy_flag and init_flag*(1-bit) share this difference
+            to_rate.add(C, o + HRW + i, f63::sub(c, f.next(o + HRW + i)));  // init_flag*bit: the hash moves to the rate half
+        }
+    }
+    for (int i = 0; i < HRW; i++) place_bit.add(C, base + i, f63::sub(f.next(base + HSW + 1 + i), f.next(base + i)));
+    for (int i = HRW; i < HSW; i++) place_nbit.add(C, base + i, f63::sub(f.next(base + HSW + 1 + i), f.next(base + i)));
+    const fe init_bit = f63::mul(init_flag, bit), init_nbit = f63::mul(init_flag, nbit);
+    keep.flush(C, f63::add(copy_flag, init_nbit));
+    to_rate.flush(C, init_bit);
+    place_bit.flush(C, init_bit);
+    place_nbit.flush(C, init_nbit);
+}
+// root bookkeeping of merkle::update::evaluate_constraints (src/merkle/update/air.rs:250-288)
+CSG_HD void merkle_roots(const Frame &f, Comb &C, fe finish) {
+    FlagAcc carry, fin;
+    for (int i = 0; i < HRW; i++) {
+        fe nr = f.next(PREV_ROOT + i), cr = f.cur(PREV_ROOT + i);
+        carry.add(C, PREV_ROOT + i, f63::sub(nr, cr));
+        fin.add(C, PREV_ROOT + i, f63::sub(nr, f.next(RECEIVER_UPDATED + i)));
+        fin.add(C, INT_ROOT_RES + i, f63::sub(f.cur(SENDER_UPDATED + i), f.cur(RECEIVER_INITIAL + i)));
+        fin.add(C, ROOT_MATCH_RES + i, f63::sub(f.next(SENDER_INITIAL + i), cr));
+    }
+    carry.flush(C, f_not(finish));
+    fin.flush(C, finish);
+}
+// value / balance / nonce block (src/merkle/update/air.rs:96-144 and src/air.rs:405-453), added to `a`
+CSG_HD void value_block(const Frame &f, const Comb &C, FlagAcc &a) {
+    for (int i = 0; i < APW; i++) {
+        a.add(C, VALUE_RES + i, f63::sub(f.cur(SENDER_INITIAL + i), f.cur(SENDER_UPDATED + i)));
+        a.add(C, VALUE_RES + APW + i, f63::sub(f.cur(RECEIVER_INITIAL + i), f.cur(RECEIVER_UPDATED + i)));
+    }
+    a.add(C, VALUE_RES + 2 * APW, f63::sub(f.cur(RECEIVER_INITIAL + APW + 1), f.cur(RECEIVER_UPDATED + APW + 1)));
+    a.add(C, BALANCE_RES, f63::sub(f63::sub(f.cur(SENDER_INITIAL + APW), f.cur(SENDER_UPDATED + APW)),
+                                   f63::sub(f.cur(RECEIVER_UPDATED + APW), f.cur(RECEIVER_INITIAL + APW))));
+    a.add(C, NONCE_RES, f63::sub(f.cur(SENDER_UPDATED + APW + 1), f63::add(f.cur(SENDER_INITIAL + APW + 1), f63::ONE)));
+}
+
+// ---- curve part of schnorr::evaluate_constraints: one scalar multiplication register bank (point at column o, its
+// bit at o+18) against the affine point q (src/schnorr/air.rs:415-452, src/utils/ecc.rs:73-144)
+CSG_HD void scalar_mult_bank(const Frame &f, Comb &C, int o, const fe (&q)[12], fe doubling, fe addition) {
+    ecc::point p;
+    fe nx[18];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; i++) { p.x.c[i] = f.cur(o + i); p.y.c[i] = f.cur(o + 6 + i); p.z.c[i] = f.cur(o + 12 + i); }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 18; i++) nx[i] = f.next(o + i);
+    const fe bit = f.cur(o + PPW), nbit = f_not(bit);
+    {
+        ecc::point d = ecc::double_point(p);
+        FlagAcc a;
+        for (int i = 0; i < 6; i++) {
+            a.add(C, o + i, f63::sub(nx[i], d.x.c[i]));
+            a.add(C, o + 6 + i, f63::sub(nx[6 + i], d.y.c[i]));
+            a.add(C, o + 12 + i, f63::sub(nx[12 + i], d.z.c[i]));
+        }
+        a.add(C, o + PPW, f_bin(bit));
+        a.flush(C, doubling);
+    }
+    {
+        ecc::fp6 qx = ecc::load6(q), qy = ecc::load6(q + 6);
+        ecc::point m = ecc::add_mixed(p, qx, qy);
+        FlagAcc a;
+        for (int i = 0; i < 6; i++) {
+            a.add(C, o + i, f63::sub(nx[i], f63::add(f63::mul(bit, m.x.c[i]), f63::mul(nbit, p.x.c[i]))));
+            a.add(C, o + 6 + i, f63::sub(nx[6 + i], f63::add(f63::mul(bit, m.y.c[i]), f63::mul(nbit, p.y.c[i]))));
+            a.add(C, o + 12 + i, f63::sub(nx[12 + i], f63::add(f63::mul(bit, m.z.c[i]), f63::mul(nbit, p.z.c[i]))));
+        }
+        a.add(C, o + PPW, f63::sub(bit, f.next(o + PPW)));
+        a.flush(C, addition);
+    }
+}
+// everything of schnorr::evaluate_constraints except the Rescue round of the message hash.
+// PK(j): limb j of the signer's affine public key; IN(i): message element injected into the hash at this row.
+template <class PK, class IN>
+CSG_HD void schnorr_block(const Frame &f, Comb &C, fe doubling, fe addition, const fe (&digest)[4], PK pk, fe final_add, fe copy_hash, IN in) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int bank = 0; bank < 2; bank++) {
+        fe q[12];
+        const uint64_t *gen = CSG_TABLE(CSG_GENERATOR);
+        for (int j = 0; j < 12; j++) q[j] = bank == 0 ? gen[j] : pk(j);
+        scalar_mult_bank(f, C, bank * (PPW + 1), q, doubling, addition);
+    }
+    // the four limbs of h are rebuilt from its bits while its scalar multiplication runs (src/schnorr/air.rs:454-486)
+    const fe hbit_next = f.next(LIMBS);
+    {
+        FlagAcc hold;
+        for (int i = 0; i < 4; i++) {
+            const int c = LIMBS + 4 - i;
+            fe cv = f.cur(c), nv = f.next(c);
+            C.add(c, f63::mul(f63::mul(digest[i], doubling), f63::sub(nv, f63::add(f63::dbl(cv), hbit_next))));
+            C.add(c, f63::mul(f63::mul(f_not(digest[i]), doubling), f63::sub(cv, nv)));
+            hold.add(C, LIMBS + 1 + i, f63::sub(f.cur(LIMBS + 1 + i), f.next(LIMBS + 1 + i)));
+        }
+        hold.flush(C, addition);
+    }
+    // enforce_hash_copy (src/schnorr/air.rs:309-330)
+    {
+        FlagAcc a;
+        for (int i = 0; i < HRW; i++) {
+            a.add(C, SIG_HASH + i, f63::sub(f.cur(SIG_HASH + i), f.next(SIG_HASH + i)));
+            a.add(C, SIG_HASH + HRW + i, f63::sub(f.next(SIG_HASH + HRW + i), in(i)));
+        }
+        a.flush(C, copy_hash);
+    }
+    // last step: S + h.P, x reduced to affine, and h must equal the hash output (src/schnorr/air.rs:506-530, ecc.rs:146-172)
+    {
+        ecc::point s, hp;
+        for (int i = 0; i < 6; i++) {
+            s.x.c[i] = f.cur(i); s.y.c[i] = f.cur(6 + i); s.z.c[i] = f.cur(12 + i);
+            hp.x.c[i] = f.cur(PPW + 1 + i); hp.y.c[i] = f.cur(PPW + 7 + i); hp.z.c[i] = f.cur(PPW + 13 + i);
+        }
+        ecc::point r = ecc::add_full(s, hp);
+        ecc::fp6 nx;
+        for (int i = 0; i < 6; i++) nx.c[i] = f.next(i);
+        ecc::fp6 xz = ecc::mul(nx, r.z);
+        FlagAcc a;
+        for (int i = 0; i < 6; i++) {
+            a.add(C, i, f63::sub(xz.c[i], r.x.c[i]));
+            a.add(C, 6 + i, f63::sub(f.next(6 + i), r.y.c[i]));
+            a.add(C, 12 + i, f63::sub(f.next(12 + i), r.z.c[i]));
+        }
+        for (int i = 0; i < 4; i++) a.add(C, LIMBS + 1 + i, f63::sub(f.cur(LIMBS + 1 + i), f.cur(SIG_HASH + i)));
+        a.flush(C, final_add);
+    }
+}
+
+// ================================================================================================ the six AIRs
+template <class PV>
+CSG_HD void eval_transaction(const Frame &f, const PV &pv, Comb &C) {
+    const fe setup = pv(TX_SETUP), tx_hash = pv(TX_MERKLE), hash_input = pv(TX_HASH_INPUT), finish = pv(TX_FINISH), hashf = pv(TX_HASH);
+    const fe schnorr_mask = pv(TX_SCHNORR), scalar_mult = pv(TX_SCALAR_MULT), doubling = pv(TX_DOUBLING), schnorr_hash = pv(TX_SCHNORR_HASH);
+    const fe copy_hash = f63::mul(f_not(schnorr_hash), schnorr_mask);
+    const fe final_add = f63::mul(f_not(scalar_mult), schnorr_mask);
+    const fe addition = f63::mul(f_not(doubling), scalar_mult);
+
+    // the four leaf/path hash states serve both the leaf-hash phase (setup flag, slots 0,14,28,42: src/merkle/init/air.rs:171-201)
+    // and the authentication paths (hash flag, slots = columns); the fifth state is the Schnorr message hash
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = 0; s < 5; s++) {
+        const int col0 = s < 4 ? 15 * s - (s >> 1) : SIG_HASH;
+        if (s < 4) rescue_state(f, pv, C, col0, TX_ARK, setup, 14 * s, true, hashf, col0);
+        else rescue_state(f, pv, C, col0, TX_ARK, schnorr_hash, SIG_HASH, false, 0, 0);
+    }
+    {   // setup row of a transaction: leaf consistency and copies into the carried registers (src/air.rs:405-504)
+        FlagAcc a;
+        value_block(f, C, a);
+        for (int o = 0; o < APW; o++) {
+            a.add(C, SENDER_KEY_RES + o, f63::sub(f.next(SENDER_KEY + o), f.cur(SENDER_INITIAL + o)));
+            a.add(C, RECEIVER_KEY_RES + o, f63::sub(f.next(RECEIVER_KEY + o), f.cur(RECEIVER_INITIAL + o)));
+        }
+        a.add(C, DELTA_COPY_RES, f63::sub(f.next(DELTA_COPY), f63::sub(f.cur(SENDER_INITIAL + APW), f.cur(SENDER_UPDATED + APW))));
+        a.add(C, SIGMA_COPY_RES, f63::sub(f.next(SIGMA_COPY), f.cur(SENDER_UPDATED + APW)));
+        a.add(C, NONCE_COPY_RES, f63::sub(f.next(NONCE_COPY), f.cur(SENDER_INITIAL + APW + 1)));
+        a.flush(C, setup);
+    }
+    {   // carried registers stay put afterwards (src/air.rs:506-529); note the overlapping slot ranges are the reference's
+        FlagAcc a;
+        for (int o = 0; o < APW; o++) {
+            a.add(C, SENDER_KEY_RES + o, f63::sub(f.next(SENDER_KEY + o), f.cur(SENDER_KEY + o)));
+            a.add(C, RECEIVER_KEY_RES + o, f63::sub(f.next(RECEIVER_KEY + o), f.cur(RECEIVER_KEY + o)));
+        }
+        a.add(C, DELTA_COPY_RES, f63::sub(f.next(DELTA_COPY), f.cur(DELTA_COPY)));
+        a.add(C, SIGMA_COPY_RES, f63::sub(f.next(SIGMA_COPY), f.cur(SIGMA_COPY)));
+        a.add(C, NONCE_COPY_RES, f63::sub(f.next(NONCE_COPY), f.cur(NONCE_COPY)));
+        a.flush(C, pv(TX_VALUE_COPY));
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int path = 0; path < 2; path++) merkle_auth_path(f, C, path == 0 ? SENDER_INITIAL : RECEIVER_INITIAL, tx_hash, hash_input, hashf);
+    merkle_roots(f, C, finish);
+
+    // message elements entering the Schnorr hash come from the carried key/delta/nonce registers (src/air.rs:542-565)
+    const fe k0 = pv(TX_INTERNAL), k1 = pv(TX_INTERNAL + 1), k2 = pv(TX_INTERNAL + 2), k3 = pv(TX_INTERNAL + 3);
+    auto cell = [&](int idx) -> fe {
+        if (idx < 2 * APW) return f.next(SENDER_KEY + idx);   // sender key then receiver key are adjacent columns
+        if (idx == 2 * APW) return f.next(DELTA_COPY);
+        if (idx == 2 * APW + 1) return f.next(NONCE_COPY);
+        return 0;
+    };
+    auto in = [&](int i) -> fe {
+        f63::acc128 t;
+        t.mac(k0, cell(i)); t.mac(k1, cell(HRW + i)); t.mac(k2, cell(2 * HRW + i)); t.mac(k3, cell(3 * HRW + i));
+        return t.reduce();
+    };
+    const fe digest[4] = {pv(TX_DIGEST), pv(TX_DIGEST + 1), pv(TX_DIGEST + 2), pv(TX_DIGEST + 3)};
+    schnorr_block(f, C, doubling, addition, digest, [&](int j) { return f.next(SENDER_KEY + j); }, final_add, copy_hash, in);
+
+    {   // range proofs of delta and sigma (src/air.rs:582-609); the sigma finish check compares the delta registers, as the reference does
+        FlagAcc a;
+        fe db = f.next(DELTA_BIT), sb = f.next(SIGMA_BIT);
+        a.add(C, DELTA_ACC, f63::sub(f.next(DELTA_ACC), f63::add(f63::dbl(f.cur(DELTA_ACC)), db)));
+        a.add(C, DELTA_BIT, f_bin(db));
+        a.add(C, SIGMA_ACC, f63::sub(f.next(SIGMA_ACC), f63::add(f63::dbl(f.cur(SIGMA_ACC)), sb)));
+        a.add(C, SIGMA_BIT, f_bin(sb));
+        a.flush(C, pv(TX_RANGE_STEP));
+        FlagAcc b;
+        fe v = f63::sub(f.next(DELTA_ACC), f.next(DELTA_COPY));
+        b.add(C, DELTA_RANGE_RES, v);
+        b.add(C, SIGMA_RANGE_RES, v);
+        b.flush(C, pv(TX_RANGE_FINISH));
+    }
+}
+
+// MerkleAir: periodic = setup, tx_hash, hash_input, finish, hash, ark[28] (src/merkle/update/air.rs:73-156, 182-212)
+template <class PV>
+CSG_HD void eval_merkle_update(const Frame &f, const PV &pv, Comb &C) {
+    const fe setup = pv(0), tx_hash = pv(1), hash_input = pv(2), finish = pv(3), hashf = pv(4);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = 0; s < 4; s++) {
+        const int col0 = 15 * s - (s >> 1);
+        rescue_state(f, pv, C, col0, 5, hashf, col0, false, 0, 0);
+    }
+    FlagAcc a;
+    value_block(f, C, a);
+    a.flush(C, setup);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int path = 0; path < 2; path++) merkle_auth_path(f, C, path == 0 ? SENDER_INITIAL : RECEIVER_INITIAL, tx_hash, hash_input, hashf);
+    merkle_roots(f, C, finish);
+}
+// PreMerkleAir: periodic = ark[28]; the flag is the constant one (src/merkle/init/air.rs:76-90)
+template <class PV>
+CSG_HD void eval_merkle_init(const Frame &f, const PV &pv, Comb &C) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = 0; s < 4; s++) rescue_state(f, pv, C, 15 * s - (s >> 1), 0, f63::ONE, 14 * s, false, 0, 0);
+}
+// SchnorrAir: periodic = global, scalar_mult, doubling, digest[4], pkey[12], hash flag, message chunk[7], ark[28] (src/schnorr/air.rs:75-113)
+template <class PV>
+CSG_HD void eval_schnorr(const Frame &f, const PV &pv, Comb &C) {
+    const fe global = pv(0), scalar_mult = pv(1), doubling = pv(2), hash_flag = pv(APW + 7);
+    const fe copy_hash = f63::mul(f_not(hash_flag), global), final_add = f63::mul(f_not(scalar_mult), global);
+    const fe addition = f63::mul(f_not(doubling), scalar_mult);
+    rescue_state(f, pv, C, SIG_HASH, APW + 15, hash_flag, SIG_HASH, false, 0, 0);
+    const fe digest[4] = {pv(3), pv(4), pv(5), pv(6)};
+    schnorr_block(f, C, doubling, addition, digest, [&](int j) { return pv(7 + j); }, final_add, copy_hash, [&](int i) { return pv(APW + 8 + i); });
+}
+// RangeProofAir (src/range/air.rs:69-105): column 0 = bit, column 1 = accumulator
+template <class PV>
+CSG_HD void eval_range(const Frame &f, const PV &, Comb &C) {
+    fe b = f.next(0);
+    C.add(1, f63::sub(f.next(1), f63::add(f63::dbl(f.cur(1)), b)));
+    C.add(0, f_bin(b));
+}
+// RescueAir of benches/rescue.rs:205-222: periodic = cycle mask, ark[28]
+template <class PV>
+CSG_HD void eval_rescue(const Frame &f, const PV &pv, Comb &C) {
+    const fe hash_flag = pv(0);
+    rescue_state(f, pv, C, 0, 1, hash_flag, 0, false, 0, 0);
+    FlagAcc a;
+    for (int i = 0; i < HRW; i++) {
+        a.add(C, i, f63::sub(f.cur(i), f.next(i)));
+        a.add(C, HRW + i, f.next(HRW + i));
+    }
+    a.flush(C, f_not(hash_flag));
+}
+
+template <int AIR, class PV>
+CSG_HD void eval_transition(const Frame &f, const PV &pv, Comb &C) {
+    if (AIR == TRANSACTION) eval_transaction(f, pv, C);
+    else if (AIR == MERKLE_UPDATE) eval_merkle_update(f, pv, C);
+    else if (AIR == MERKLE_INIT) eval_merkle_init(f, pv, C);
+    else if (AIR == SCHNORR) eval_schnorr(f, pv, C);
+    else if (AIR == RANGE) eval_range(f, pv, C);
+    else eval_rescue(f, pv, C);
+}
+
+}  // namespace airs

@@ -1,0 +1,21 @@
+// Vector commitments (K3/K4 of SURVEY.md section 2.2): leaf = H(row bytes), node = H(left || right), with the hash the
+// ProofOptions select -- what winterfell's `H::hash_elements(row)` + `MerkleTree::new(leaves)` do for the reference
+// (stage 2 and 4 of Prover::prove, entered at /root/reference/src/lib.rs:140).
+//
+// Layout: a tree over L leaves is one array of 2L digests of 8 u32 words; nodes[1] is the root, nodes[i] has children
+// nodes[2i], nodes[2i+1], leaf j sits at nodes[L + j] -- the row-hash kernel writes leaves straight into that slot.
+#pragma once
+#include "dev.cuh"
+
+namespace csg {
+
+// digest of row j = k + ncosets*i of a coset-major matrix: elements data[k*coset_stride + c*col_stride + i], c < width,
+// hashed as canonical little-endian bytes.  Writes 8 words to leaves + 8*j.
+void hash_rows(const fe *data, unsigned width, size_t n, unsigned ncosets, size_t coset_stride, size_t col_stride, int hash_fn,
+               uint32_t *leaves, Stream &st);
+// interior nodes of the tree whose leaves are already in nodes[8*L ..)
+void merkle_build(uint32_t *nodes, size_t nleaves, int hash_fn, Stream &st);
+// out[8*t ..] = nodes[8*idx[t] ..]
+void gather_digests(const uint32_t *nodes, const uint32_t *idx_dev, size_t count, uint32_t *out_dev, Stream &st);
+
+}  // namespace csg

@@ -1,0 +1,55 @@
+// Constraint evaluation over the constraint-evaluation domain and merging into one composition column per coset
+// (stage 3 of Prover::prove: winterfell ConstraintEvaluator::evaluate + the divisor step of
+// ConstraintEvaluationTable::into_poly, driven from /root/reference/src/lib.rs:140 with the AIRs of src/air.rs & co).
+//
+// For every row x = s_k * w_n^i of every ce coset the kernel produces
+//     C(x) = T(x) * (x - g^(n-1)) / (x^n - 1)  +  sum_groups  B_g(x) / (x^steps_g - offset_g)
+// with T the merged transition constraints (airs.cuh) and B_g the merged boundary constraints of one divisor group.
+// On a coset x^n is a constant, so the transition divisor costs one multiplication per row.
+#pragma once
+#include "dev.cuh"
+
+namespace csg {
+
+constexpr int CONS_MAX_CONSTRAINTS = 128, CONS_MAX_GROUPS = 8, CONS_MAX_PERIODIC = 64, CONS_MAX_ASSERTIONS = 64,
+              CONS_MAX_BGROUPS = 4, CONS_MAX_COSETS = 32;
+
+// everything the kernel needs besides the trace; lives in device memory, read warp-uniformly
+struct ConsArgs {
+    // domain
+    unsigned logn;                 // trace length n = 2^logn
+    unsigned ncosets;              // ce cosets evaluated
+    unsigned long long lde_coset_stride[CONS_MAX_COSETS];  // element offset of ce coset kc inside the LDE buffer
+    unsigned long long col_stride;
+    unsigned width;
+    fe shift[CONS_MAX_COSETS];     // s_k
+    fe zinv[CONS_MAX_COSETS];      // 1 / (s_k^n - 1)
+    fe g_last;                     // g^(n-1)
+    // transition combination
+    unsigned nconstraints, ngroups;
+    fe alpha[CONS_MAX_CONSTRAINTS], beta[CONS_MAX_CONSTRAINTS];
+    unsigned char group[CONS_MAX_CONSTRAINTS];
+    unsigned long long adj_mod[CONS_MAX_GROUPS];                 // adj_g mod n
+    fe shift_adj[CONS_MAX_COSETS][CONS_MAX_GROUPS];              // s_k^adj_g
+    // periodic columns: value of column c at row i of ce coset kc = ptab[kc * ptab_coset_stride + poff[c] + (i & pmask[c])]
+    unsigned nperiodic;
+    unsigned poff[CONS_MAX_PERIODIC], pmask[CONS_MAX_PERIODIC];
+    unsigned long long ptab_coset_stride;
+    // boundary constraints
+    unsigned nbgroups, nassertions;
+    unsigned long long b_adj_mod[CONS_MAX_BGROUPS], b_steps[CONS_MAX_BGROUPS];   // adj_g mod n, number of asserted steps
+    fe b_offset[CONS_MAX_BGROUPS];                                               // g^(steps * first_step)
+    fe b_shift_adj[CONS_MAX_COSETS][CONS_MAX_BGROUPS], b_shift_steps[CONS_MAX_COSETS][CONS_MAX_BGROUPS];  // s_k^adj, s_k^steps
+    unsigned a_col[CONS_MAX_ASSERTIONS], a_group[CONS_MAX_ASSERTIONS];
+    fe a_alpha[CONS_MAX_ASSERTIONS], a_beta[CONS_MAX_ASSERTIONS], a_value[CONS_MAX_ASSERTIONS];
+    unsigned a_poly_len[CONS_MAX_ASSERTIONS];            // > 1: value polynomial of that many coefficients at a_poly_off
+    unsigned long long a_poly_off[CONS_MAX_ASSERTIONS];
+    fe a_xoff[CONS_MAX_ASSERTIONS];                      // the polynomial is evaluated at x * a_xoff
+};
+
+// lde: coset-major extended trace; W: root table of size n; ptab / apoly: periodic tables and assertion value
+// polynomials; out[kc * n + i] receives C(x)
+void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &args_host, const fe *lde, const fe *W, const fe *ptab,
+                      const fe *apoly, fe *out, Stream &st);
+
+}  // namespace csg

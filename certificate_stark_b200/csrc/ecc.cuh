@@ -29,8 +29,13 @@ CSG_HD fp2 sqr(fp2 a) { return mul(a, a); }
 CSG_HD fp6 add(const fp6 &a, const fp6 &b) { fp6 r; for (int i = 0; i < 6; i++) r.c[i] = f63::add(a.c[i], b.c[i]); return r; }
 CSG_HD fp6 sub(const fp6 &a, const fp6 &b) { fp6 r; for (int i = 0; i < 6; i++) r.c[i] = f63::sub(a.c[i], b.c[i]); return r; }
 CSG_HD fp6 dbl(const fp6 &a) { fp6 r; for (int i = 0; i < 6; i++) r.c[i] = f63::dbl(a.c[i]); return r; }
-// (a + b v + c v^2)(d + e v + f v^2) with v^3 = -v - 1: six Fp2 products (ecc.rs:506-548)
-CSG_HD fp6 mul(const fp6 &x, const fp6 &y) {
+// (a + b v + c v^2)(d + e v + f v^2) with v^3 = -v - 1: six Fp2 products (ecc.rs:506-548).
+// Not inlined on the device: the curve formulas call it ~40 times per row and the body is ~700 instructions.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__ fp6 mul(const fp6 &x, const fp6 &y) {
+#else
+inline fp6 mul(const fp6 &x, const fp6 &y) {
+#endif
     fp2 a = {x.c[0], x.c[1]}, b = {x.c[2], x.c[3]}, c = {x.c[4], x.c[5]};
     fp2 d = {y.c[0], y.c[1]}, e = {y.c[2], y.c[3]}, f = {y.c[4], y.c[5]};
     fp2 ad = mul(a, d), be = mul(b, e), cf = mul(c, f);
@@ -42,7 +47,7 @@ CSG_HD fp6 mul(const fp6 &x, const fp6 &y) {
     return {{r0.c0, r0.c1, r1.c0, r1.c1, r2.c0, r2.c1}};
 }
 CSG_HD fp6 sqr(const fp6 &a) { return mul(a, a); }
-CSG_HD fp6 b3() { return {{CSG_B3_M[0], CSG_B3_M[1], CSG_B3_M[2], CSG_B3_M[3], CSG_B3_M[4], CSG_B3_M[5]}}; }
+CSG_HD fp6 b3() { const uint64_t *t = CSG_TABLE(CSG_B3); return {{t[0], t[1], t[2], t[3], t[4], t[5]}}; }
 CSG_HD fp6 load6(const fe *p) { return {{p[0], p[1], p[2], p[3], p[4], p[5]}}; }
 
 // RCB15 Alg. 3 (ecc.rs:186-246)
@@ -103,7 +108,6 @@ CSG_HD point add_full(const point &p, const point &q) {
     return {x3, y3, z3};
 }
 
-#if !defined(__CUDA_ARCH__)
 // host-only inversions for the final X/Z reduction of the witness (ecc.rs:441-446, 551-591)
 inline fp2 inv(fp2 a) {
     fe t = f63::inv(f63::sub(f63::add(f63::sqr(a.c0), f63::mul(f63::dbl(a.c0), a.c1)), f63::dbl(f63::sqr(a.c1))));
@@ -121,5 +125,4 @@ inline fp6 inv(const fp6 &x) {
     fp2 r2 = mul(add(sub(b2, mul(a, c)), c2), t);
     return {{r0.c0, r0.c1, r1.c0, r1.c1, r2.c0, r2.c1}};
 }
-#endif
 }  // namespace ecc

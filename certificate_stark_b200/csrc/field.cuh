@@ -9,6 +9,7 @@
 // p and -p^-1 = p - 2 are both sparse, so the Montgomery reduction needs no multiplier: on the device it is
 // shifts and adds on the ALU pipe, leaving the fma pipe for the 4 IMAD.WIDE of the 64x64 product.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 #if defined(__CUDACC__)
@@ -95,12 +96,34 @@ struct acc128 {
     }
 };
 
-#if !defined(__CUDA_ARCH__)
-inline fe root_of_unity(unsigned logn) {  // primitive 2^logn-th root (winterfell StarkField::get_root_of_unity)
+// ---- lazily reduced 192-bit accumulator for long sums of products (the random linear combination of constraints)
+struct acc192 {
+    uint64_t lo, mid, hi;
+    CSG_HD acc192() : lo(0), mid(0), hi(0) {}
+    CSG_HD void mac(fe a, fe b) {
+        u128 t = mul_wide(a, b);
+        lo += t.lo;
+        uint64_t c = lo < t.lo ? 1 : 0;
+        uint64_t m = mid + t.hi;       // t.hi < 2^61, so adding the carry below cannot wrap a second time
+        uint64_t c2 = m < mid ? 1 : 0;
+        m += c;
+        c2 += m < c ? 1 : 0;
+        mid = m;
+        hi += c2;
+    }
+    // (hi*2^128 + mid*2^64 + lo) * 2^-64 mod p  =  hi*2^64 + mid + lo*2^-64   (hi counts carries: far below p)
+    CSG_HD fe reduce() const {
+        uint64_t m = mid;
+        if (m >= 2 * P) m -= 2 * P;
+        if (m >= P) m -= P;
+        return add(add(m, redc(lo, 0)), mul(hi, R2));
+    }
+};
+
+CSG_HD fe root_of_unity(unsigned logn) {  // primitive 2^logn-th root (winterfell StarkField::get_root_of_unity)
     fe r = to_mont(TWO_ADIC_ROOT);
     for (unsigned i = logn; i < TWO_ADICITY; i++) r = sqr(r);
     return r;
 }
-#endif
 
 }  // namespace f63

@@ -1,0 +1,270 @@
+// See ntt.cuh for the design.  Hand-written for sm_100a: no library FFT exists for this field.
+#include <vector>
+
+#include "ntt.cuh"
+
+namespace csg {
+using namespace f63;
+
+namespace {
+
+constexpr unsigned TILE_LOG = 13;      // elements staged per CTA (64 KB of shared memory + padding)
+constexpr unsigned MAX_SUB_LOG = 11;   // largest single sub-transform
+constexpr unsigned NTT_THREADS = 256;
+
+struct PassArgs {
+    const fe *in; fe *out;
+    unsigned logS, logT;                           // sub-transform size, lanes per CTA
+    unsigned nlanes;                               // total lanes along grid.x
+    unsigned long long in_se, in_sl, out_se, out_sl;  // element / lane strides, in field elements
+    unsigned long long in_by, in_bz, out_by, out_bz;  // strides for blockIdx.y (column) and blockIdx.z (coset)
+    const fe *W; unsigned logW;                    // root table
+    int inverse;
+    const fe *preA, *preB; unsigned long long pre_bz;    // input (e, lane) *= preA[e] * preB[lane]
+    const fe *postA, *postB; unsigned long long post_bz;  // output (e, lane) *= postA[e] * postB[lane]
+    unsigned tw_logn;                              // != 0: output (e, lane) *= w_{2^tw_logn}^(+-e*lane)
+    int use_scalar; fe scalar;                     // output *= scalar
+};
+
+__device__ __forceinline__ fe root_pow(const fe *W, unsigned logW, unsigned logm, unsigned long long e, int inverse) {
+    // w_{2^logm}^(+-e), e < 2^logm <= 2^logW
+    unsigned long long idx = e << (logW - logm), N = 1ULL << logW;
+    if (inverse) idx = (N - idx) & (N - 1);
+    return W[idx];
+}
+
+// One pass: T lanes x S elements staged in shared memory, S-point natural-order NTT along each lane (bit-reversed on
+// the way in, radix-2 decimation-in-time stages in place), optional scalings on the way in and out.
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
+    extern __shared__ fe sm[];
+    const unsigned S = 1u << a.logS, T = 1u << a.logT, SP = S + 1;  // +1 element of padding per lane: lanes land in different banks
+    fe *tw = sm + (size_t)T * SP;                                  // S/2 twiddles of the sub-transform
+    const unsigned tid = threadIdx.x, nth = blockDim.x;
+    const unsigned lane0 = blockIdx.x << a.logT;
+    const fe *in = a.in + blockIdx.y * a.in_by + blockIdx.z * a.in_bz;
+    fe *out = a.out + blockIdx.y * a.out_by + blockIdx.z * a.out_bz;
+
+    for (unsigned j = tid; j < S / 2; j += nth) tw[j] = root_pow(a.W, a.logW, a.logS, j, a.inverse);
+
+    const fe *preA = a.preA ? a.preA + blockIdx.z * a.pre_bz : nullptr;
+    const fe *preB = a.preB ? a.preB + blockIdx.z * a.pre_bz : nullptr;
+    const bool lane_fast_in = a.in_sl == 1 && T > 1;
+    for (unsigned idx = tid; idx < S * T; idx += nth) {
+        unsigned e, l;
+        if (lane_fast_in) { l = idx & (T - 1); e = idx >> a.logT; } else { e = idx & (S - 1); l = idx >> a.logS; }
+        fe v = 0;
+        if (lane0 + l < a.nlanes) {
+            v = in[e * a.in_se + (lane0 + l) * a.in_sl];
+            if (preA) v = mul(v, preA[e]);
+            if (preB) v = mul(v, preB[lane0 + l]);
+        }
+        unsigned r = a.logS ? (__brev(e) >> (32 - a.logS)) : 0;
+        sm[l * SP + r] = v;
+    }
+    __syncthreads();
+
+    const unsigned half = S >> 1;
+    for (unsigned s = 0; s < a.logS; s++) {
+        const unsigned h = 1u << s;
+        for (unsigned b = tid; b < half * T; b += nth) {
+            unsigned l = b >> (a.logS - 1), bb = b & (half - 1);
+            unsigned k = bb & (h - 1);
+            unsigned i0 = l * SP + ((bb >> s) << (s + 1)) + k, i1 = i0 + h;
+            fe u = sm[i0], v = mul(sm[i1], tw[k << (a.logS - 1 - s)]);
+            sm[i0] = add(u, v);
+            sm[i1] = sub(u, v);
+        }
+        __syncthreads();
+    }
+
+    const fe *postA = a.postA ? a.postA + blockIdx.z * a.post_bz : nullptr;
+    const fe *postB = a.postB ? a.postB + blockIdx.z * a.post_bz : nullptr;
+    const bool lane_fast_out = a.out_sl == 1 && T > 1;
+    for (unsigned idx = tid; idx < S * T; idx += nth) {
+        unsigned e, l;
+        if (lane_fast_out) { l = idx & (T - 1); e = idx >> a.logT; } else { e = idx & (S - 1); l = idx >> a.logS; }
+        if (lane0 + l >= a.nlanes) continue;
+        fe v = sm[l * SP + e];
+        if (a.tw_logn) v = mul(v, root_pow(a.W, a.logW, a.tw_logn, (unsigned long long)e * (lane0 + l), a.inverse));
+        if (postA) v = mul(v, postA[e]);
+        if (postB) v = mul(v, postB[lane0 + l]);
+        if (a.use_scalar) v = mul(v, a.scalar);
+        out[e * a.out_se + (lane0 + l) * a.out_sl] = v;
+    }
+}
+
+void launch_pass(const PassArgs &a, unsigned ncols, unsigned ncosets, Stream &st) {
+    const unsigned S = 1u << a.logS, T = 1u << a.logT;
+    size_t smem = ((size_t)T * (S + 1) + S / 2 + 1) * sizeof(fe);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CSG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    unsigned threads = NTT_THREADS;
+    while (threads > 32 && threads > (S * T) / 2) threads >>= 1;
+    dim3 grid((a.nlanes + T - 1) / T, ncols, ncosets);
+    CSG_LAUNCH(st, ntt_pass_kernel, grid, threads, smem, a);
+}
+
+// W[j] = base_hi[j >> 10] * base_lo[j & 1023]
+__global__ void roots_kernel(fe *W, const fe *lo, const fe *hi, unsigned long long n) {
+    unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (j < n) W[j] = mul(hi[j >> 10], lo[j & 1023]);
+}
+
+// scale tables for a coset shift s and a split n = n1*n2 (element m = i1*n2 + i2):  A[i1] = s^(i1*n2),  B[i2] = s^i2
+__global__ void scale_tables_kernel(const fe *shifts, unsigned n1, unsigned n2, fe *tables) {
+    const fe s = shifts[blockIdx.y];
+    fe *A = tables + (size_t)blockIdx.y * (n1 + n2), *B = A + n1;
+    unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n1) A[j] = f63::pow(s, (unsigned long long)j * n2);
+    else if (j < n1 + n2) B[j - n1] = f63::pow(s, j - n1);
+}
+
+struct Split { unsigned l1, l2; };
+Split split_of(unsigned logn) {
+    if (logn <= MAX_SUB_LOG) return {logn, 0};
+    unsigned l1 = (logn + 1) / 2;
+    if (l1 > MAX_SUB_LOG || logn - l1 > MAX_SUB_LOG) throw std::runtime_error("NTT size above 2^22 is not supported");
+    return {l1, logn - l1};
+}
+unsigned lanes_log(unsigned logS, unsigned nlanes_log) {
+    unsigned t = TILE_LOG > logS ? TILE_LOG - logS : 0;
+    return t < nlanes_log ? t : nlanes_log;
+}
+void upload_shifts(NttScratch &sc, const fe *host, size_t n, Stream &st) {
+    sc.shifts.reserve(n < 64 ? 64 : n);
+    CSG_CUDA(cudaMemcpyAsync(sc.shifts.p, host, n * sizeof(fe), cudaMemcpyHostToDevice, st.s));
+}
+void build_scale_tables(NttScratch &sc, unsigned n1, unsigned n2, size_t ncosets, Stream &st) {
+    sc.scale.reserve((size_t)(n1 + n2) * ncosets);
+    dim3 grid((n1 + n2 + 127) / 128, (unsigned)ncosets);
+    CSG_LAUNCH(st, scale_tables_kernel, grid, 128, 0, sc.shifts.p, n1, n2, sc.scale.p);
+}
+
+}  // namespace
+
+void RootTable::build(unsigned logn_, Stream &st) {
+    if (logn_ == logn && W.p) return;
+    logn = logn_;
+    const size_t n = (size_t)1 << logn;
+    W.reserve(n);
+    std::vector<fe> lo(1024), hi(((n + 1023) >> 10));
+    fe w = root_of_unity(logn), acc = ONE;
+    for (size_t i = 0; i < 1024; i++) { lo[i] = acc; acc = mul(acc, w); }
+    fe step = acc;  // w^1024
+    acc = ONE;
+    for (size_t i = 0; i < hi.size(); i++) { hi[i] = acc; acc = mul(acc, step); }
+    DBuf<fe> dlo, dhi;
+    dlo.reserve(1024); dhi.reserve(hi.size());
+    CSG_CUDA(cudaMemcpyAsync(dlo.p, lo.data(), 1024 * sizeof(fe), cudaMemcpyHostToDevice, st.s));
+    CSG_CUDA(cudaMemcpyAsync(dhi.p, hi.data(), hi.size() * sizeof(fe), cudaMemcpyHostToDevice, st.s));
+    CSG_LAUNCH(st, roots_kernel, (unsigned)((n + 255) / 256), 256, 0, W.p, dlo.p, dhi.p, (unsigned long long)n);
+    CSG_CUDA(cudaStreamSynchronize(st.s));  // dlo/dhi/lo/hi go out of scope
+}
+
+void intt_columns(const RootTable &rt, NttScratch &sc, const fe *in, size_t in_stride, fe *out, size_t out_stride, size_t ncols,
+                  unsigned logn, Stream &st) {
+    if (logn > rt.logn) throw std::runtime_error("root table too small");
+    const size_t n = (size_t)1 << logn;
+    const fe ninv = inv(to_mont(n % P));
+    Split sp = split_of(logn);
+    PassArgs a{};
+    a.W = rt.W.p; a.logW = rt.logn; a.inverse = 1;
+    if (sp.l2 == 0) {  // single pass: lanes are columns
+        a.in = in; a.out = out; a.logS = logn; a.logT = lanes_log(logn, 31); a.nlanes = (unsigned)ncols;
+        a.in_se = 1; a.in_sl = in_stride; a.out_se = 1; a.out_sl = out_stride;
+        a.use_scalar = 1; a.scalar = ninv;
+        launch_pass(a, 1, 1, st);
+        return;
+    }
+    const size_t n1 = (size_t)1 << sp.l1, n2 = (size_t)1 << sp.l2;
+    sc.tmp.reserve(ncols * n);
+    // pass A: sub-transforms over i1 (stride n2) for T adjacent i2, twiddle w_n^-(k1*i2), tmp[k1*n2 + i2]
+    a.in = in; a.out = sc.tmp.p; a.logS = sp.l1; a.logT = lanes_log(sp.l1, sp.l2); a.nlanes = (unsigned)n2;
+    a.in_se = n2; a.in_sl = 1; a.out_se = n2; a.out_sl = 1; a.in_by = in_stride; a.out_by = n; a.tw_logn = logn;
+    launch_pass(a, (unsigned)ncols, 1, st);
+    // pass B: sub-transforms over i2 (contiguous) for T adjacent k1, out[k2*n1 + k1]
+    PassArgs b{};
+    b.W = rt.W.p; b.logW = rt.logn; b.inverse = 1;
+    b.in = sc.tmp.p; b.out = out; b.logS = sp.l2; b.logT = lanes_log(sp.l2, sp.l1); b.nlanes = (unsigned)n1;
+    b.in_se = 1; b.in_sl = n2; b.out_se = n1; b.out_sl = 1; b.in_by = n; b.out_by = out_stride;
+    b.use_scalar = 1; b.scalar = ninv;
+    launch_pass(b, (unsigned)ncols, 1, st);
+}
+
+void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
+                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *shifts_host, size_t ncosets, Stream &st) {
+    if (logn > rt.logn) throw std::runtime_error("root table too small");
+    const size_t n = (size_t)1 << logn;
+    Split sp = split_of(logn);
+    const unsigned n1 = 1u << sp.l1, n2 = 1u << sp.l2;
+    upload_shifts(sc, shifts_host, ncosets, st);
+    build_scale_tables(sc, n1, n2, ncosets, st);
+    PassArgs a{};
+    a.W = rt.W.p; a.logW = rt.logn; a.inverse = 0;
+    a.preA = sc.scale.p; a.pre_bz = n1 + n2;
+    if (sp.l2 == 0) {
+        a.in = coeffs; a.out = out; a.logS = logn; a.logT = lanes_log(logn, 31); a.nlanes = (unsigned)ncols;
+        a.in_se = 1; a.in_sl = in_stride; a.out_se = 1; a.out_sl = out_col_stride; a.out_bz = out_coset_stride;
+        launch_pass(a, 1, (unsigned)ncosets, st);
+        return;
+    }
+    // cosets are processed in groups so that the pass-A scratch stays bounded (4 GB of elements at most)
+    size_t group = ncosets;
+    const size_t budget = (size_t)1 << 29;
+    while (group > 1 && group * ncols * n > budget) group = (group + 1) / 2;
+    sc.tmp.reserve(group * ncols * n);
+    for (size_t z0 = 0; z0 < ncosets; z0 += group) {
+        const size_t g = z0 + group <= ncosets ? group : ncosets - z0;
+        a.preA = sc.scale.p + z0 * (n1 + n2); a.preB = a.preA + n1;
+        a.in = coeffs; a.out = sc.tmp.p; a.logS = sp.l1; a.logT = lanes_log(sp.l1, sp.l2); a.nlanes = n2;
+        a.in_se = n2; a.in_sl = 1; a.out_se = n2; a.out_sl = 1; a.in_by = in_stride; a.in_bz = 0; a.out_by = n; a.out_bz = ncols * n;
+        a.tw_logn = logn;
+        launch_pass(a, (unsigned)ncols, (unsigned)g, st);
+        PassArgs b{};
+        b.W = rt.W.p; b.logW = rt.logn; b.inverse = 0;
+        b.in = sc.tmp.p; b.out = out + z0 * out_coset_stride; b.logS = sp.l2; b.logT = lanes_log(sp.l2, sp.l1); b.nlanes = n1;
+        b.in_se = 1; b.in_sl = n2; b.out_se = n1; b.out_sl = 1; b.in_by = n; b.in_bz = ncols * n; b.out_by = out_col_stride; b.out_bz = out_coset_stride;
+        launch_pass(b, (unsigned)ncols, (unsigned)g, st);
+    }
+}
+
+void coset_intt_columns(const RootTable &rt, NttScratch &sc, const fe *in, size_t in_stride, fe *out, size_t out_stride,
+                        unsigned logn, const fe *shift_inv_host, size_t ncosets, Stream &st) {
+    if (logn > rt.logn) throw std::runtime_error("root table too small");
+    const size_t n = (size_t)1 << logn;
+    const fe ninv = inv(to_mont(n % P));
+    Split sp = split_of(logn);
+    const unsigned n1 = 1u << sp.l1, n2 = 1u << sp.l2;
+    upload_shifts(sc, shift_inv_host, ncosets, st);
+    PassArgs a{};
+    a.W = rt.W.p; a.logW = rt.logn; a.inverse = 1;
+    if (sp.l2 == 0) {
+        // output element m *= shift_inv^m: tables A[m] (n1 = n entries), B unused
+        build_scale_tables(sc, n1, 1, ncosets, st);
+        a.in = in; a.out = out; a.logS = logn; a.logT = 0; a.nlanes = 1;
+        a.in_se = 1; a.in_sl = 0; a.out_se = 1; a.out_sl = 0; a.in_bz = in_stride; a.out_bz = out_stride;
+        a.postA = sc.scale.p; a.post_bz = n1 + 1;
+        a.use_scalar = 1; a.scalar = ninv;
+        launch_pass(a, 1, (unsigned)ncosets, st);
+        return;
+    }
+    // output index m = k1 + n1*k2: pass B has e = k2, lane = k1, so it needs  postA[k2] = s^(n1*k2), postB[k1] = s^k1:
+    // the tables of the split (n2, n1)
+    build_scale_tables(sc, n2, n1, ncosets, st);
+    sc.tmp.reserve(ncosets * n);
+    a.in = in; a.out = sc.tmp.p; a.logS = sp.l1; a.logT = lanes_log(sp.l1, sp.l2); a.nlanes = n2;
+    a.in_se = n2; a.in_sl = 1; a.out_se = n2; a.out_sl = 1; a.in_bz = in_stride; a.out_bz = n; a.tw_logn = logn;
+    launch_pass(a, 1, (unsigned)ncosets, st);
+    PassArgs b{};
+    b.W = rt.W.p; b.logW = rt.logn; b.inverse = 1;
+    b.in = sc.tmp.p; b.out = out; b.logS = sp.l2; b.logT = lanes_log(sp.l2, sp.l1); b.nlanes = n1;
+    b.in_se = 1; b.in_sl = n2; b.out_se = n1; b.out_sl = 1; b.in_bz = n; b.out_bz = out_stride;
+    b.postA = sc.scale.p; b.postB = sc.scale.p + n2; b.post_bz = n1 + n2;
+    b.use_scalar = 1; b.scalar = ninv;
+    launch_pass(b, 1, (unsigned)ncosets, st);
+}
+
+}  // namespace csg

@@ -1,0 +1,794 @@
+// libcsg: the proving context and the C ABI of include/csg.h.
+//
+// Replaces winterfell's `Prover::prove(trace)` as the reference calls it (/root/reference/src/lib.rs:140 and the five
+// sub-AIR examples): trace LDE -> commitment -> constraint evaluation -> composition commitment -> out-of-domain frame
+// -> DEEP composition -> FRI -> queries, with every bulk stage on the GPU and only the Fiat-Shamir transcript, proof
+// serialisation and a few hundred field operations per proof on the host.  Device data stays in Montgomery form and in
+// coset-major order (ntt.cuh) from the moment the trace is loaded until rows are opened.
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/csg.h"
+#include "commit.cuh"
+#include "constraints.cuh"
+#include "hash.cuh"
+#include "host/air_desc.hpp"
+#include "host/transcript.hpp"
+#include "ntt.cuh"
+#include "stages.cuh"
+
+namespace csg {
+using namespace f63;
+
+namespace {
+
+struct StateError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct FriLayer {
+    DBuf<fe> owned;           // evaluations of this layer (layer 0 aliases the DEEP evaluations)
+    const fe *evals = nullptr;
+    size_t m = 0;             // domain size of the layer
+    DBuf<uint32_t> nodes;     // tree over m/4 transposed rows
+    bool committed = false;
+};
+
+enum Stage { S_NONE, S_AIR, S_TRACE, S_COMMITTED, S_EVALUATED, S_COMPOSED, S_OOD, S_DEEP };
+
+class Timer {   // device time of a stage, CUDA events on the proving stream
+  public:
+    explicit Timer(Stream &st) : st_(st) { CSG_CUDA(cudaEventCreate(&a_)); CSG_CUDA(cudaEventCreate(&b_)); }
+    ~Timer() { cudaEventDestroy(a_); cudaEventDestroy(b_); }
+    void start() { CSG_CUDA(cudaEventRecord(a_, st_.s)); }
+    float stop() { CSG_CUDA(cudaEventRecord(b_, st_.s)); CSG_CUDA(cudaEventSynchronize(b_)); float ms = 0; CSG_CUDA(cudaEventElapsedTime(&ms, a_, b_)); return ms; }
+  private:
+    Stream &st_;
+    cudaEvent_t a_, b_;
+};
+
+}  // namespace
+}  // namespace csg
+
+using namespace csg;
+
+struct csg_ctx {
+    int device = 0;
+    Stream st;
+    std::string err;
+    RootTable roots;
+    NttScratch ntt;
+    DBuf<fe> scratch, scratch2;
+    Stage stage = S_NONE;
+
+    AirDesc air;
+    csg_options opt{};
+    TransitionGroups tg;
+    BoundaryGroups bg;
+    size_t n = 0, b = 0, ce = 0, lde_n = 0;
+    unsigned logn = 0;
+    std::vector<fe> lde_shift, ce_shift;   // s_k = offset * w_lde^k ; ce cosets are the LDE cosets k = kc * (b / ce)
+
+    DBuf<uint64_t> d_io;
+    DBuf<uint32_t> d_idx, d_dig;
+    DBuf<fe> d_polys, d_lde, d_comb, d_e, d_cpolys, d_clde, d_abc, d_abc_lde, d_deep, d_ptab, d_apoly;
+    DBuf<uint32_t> d_tnodes, d_cnodes;
+    DBuf<ConsArgs> d_cargs;
+    std::unique_ptr<ConsArgs> h_cargs;
+    std::vector<std::unique_ptr<FriLayer>> fri;
+
+    fe z = 0;
+    std::vector<fe> ood_cur, ood_next, ood_comp;
+    csg_timings tm{};
+
+    // ------------------------------------------------------------------------------------------ setup
+    void set_air(int air_id, size_t trace_len, const csg_options *o, const uint64_t *pub, size_t npub) {
+        if (!o) throw ArgError("options missing");
+        if (o->field_extension != CSG_FIELD_EXT_NONE) throw ArgError("only FieldExtension::None is implemented");
+        if (o->fri_folding_factor != 4) throw ArgError("only FRI folding factor 4 is implemented");
+        if (o->hash_fn != CSG_HASH_BLAKE3_256 && o->hash_fn != CSG_HASH_SHA3_256) throw ArgError("hash function must be Blake3_256 or Sha3_256");
+        if (o->num_queries == 0 || o->num_queries > 255 || o->grinding_factor >= 32) throw ArgError("num_queries in 1..255, grinding factor below 32");
+        if (o->blowup_factor < 2 || o->blowup_factor > 32 || (o->blowup_factor & (o->blowup_factor - 1))) throw ArgError("blowup factor must be a power of two in 2..32");
+        if (o->fri_max_remainder_size < 4 || (o->fri_max_remainder_size & (o->fri_max_remainder_size - 1))) throw ArgError("FRI remainder size must be a power of two");
+        try { air = make_air(air_id, trace_len, pub, npub); } catch (const std::invalid_argument &e) { throw ArgError(e.what()); }
+        opt = *o;
+        n = trace_len; logn = ilog2(n); b = o->blowup_factor; ce = air.ce_blowup(); lde_n = n * b;
+        if (ce > b) throw ArgError("blowup factor is smaller than the constraint evaluation blowup of this AIR");
+        if (logn > 22) throw ArgError("trace length above 2^22 is not supported");
+        if (air.num_constraints() > (size_t)CONS_MAX_CONSTRAINTS || air.periodic.size() > (size_t)CONS_MAX_PERIODIC ||
+            air.assertions.size() > (size_t)CONS_MAX_ASSERTIONS)
+            throw ArgError("AIR exceeds the compiled table sizes");
+        tg = transition_groups(air);
+        bg = boundary_groups(air);
+        if (tg.adj.size() > (size_t)CONS_MAX_GROUPS || bg.groups.size() > (size_t)CONS_MAX_BGROUPS) throw ArgError("too many constraint groups");
+        roots.build(logn, st);
+        const fe offset = to_mont(GENERATOR), w_lde = root_of_unity(ilog2(lde_n));
+        lde_shift.resize(b);
+        fe acc = offset;
+        for (size_t k = 0; k < b; k++) { lde_shift[k] = acc; acc = mul(acc, w_lde); }
+        ce_shift.resize(ce);
+        for (size_t kc = 0; kc < ce; kc++) ce_shift[kc] = lde_shift[kc * (b / ce)];
+        build_periodic_tables();
+        fri.clear();
+        stage = S_AIR;
+    }
+
+    // periodic column of period P on ce coset kc: values at y = (s_kc * w_n^i)^(n/P) = s_kc^(n/P) * w_P^i, i < P --
+    // a coset LDE of the length-P column with shifts s_kc^(n/P); columns of equal period go through the NTT together
+    void build_periodic_tables() {
+        h_cargs.reset(new ConsArgs());
+        ConsArgs &A = *h_cargs;
+        memset(&A, 0, sizeof A);
+        const size_t np = air.periodic.size();
+        A.nperiodic = (unsigned)np;
+        size_t total = 0;
+        for (size_t c = 0; c < np; c++) {
+            const size_t P = air.periodic[c].values.size();
+            if (P == 0 || (P & (P - 1)) || P > n) throw ArgError("periodic column length must be a power of two dividing the trace length");
+            A.poff[c] = (unsigned)total; A.pmask[c] = (unsigned)(P - 1);
+            total += P;
+        }
+        A.ptab_coset_stride = total;
+        d_ptab.reserve((total ? total : 1) * ce);
+        std::vector<bool> done(np, false);
+        DBuf<fe> vals, coef;
+        for (size_t c0 = 0; c0 < np; c0++) {
+            if (done[c0]) continue;
+            const size_t P = air.periodic[c0].values.size();
+            // columns of this period that are contiguous in the table starting at c0
+            size_t c1 = c0;
+            while (c1 < np && air.periodic[c1].values.size() == P) { done[c1] = true; c1++; }
+            const size_t nc = c1 - c0;
+            std::vector<fe> host(nc * P);
+            for (size_t c = c0; c < c1; c++) memcpy(&host[(c - c0) * P], air.periodic[c].values.data(), P * sizeof(fe));
+            vals.reserve(nc * P); coef.reserve(nc * P);
+            CSG_CUDA(cudaMemcpyAsync(vals.p, host.data(), nc * P * sizeof(fe), cudaMemcpyHostToDevice, st.s));
+            intt_columns(roots, ntt, vals.p, P, coef.p, P, nc, ilog2(P), st);
+            std::vector<fe> shifts(ce);
+            for (size_t kc = 0; kc < ce; kc++) shifts[kc] = f63::pow(ce_shift[kc], n / P);
+            coset_ntt_columns(roots, ntt, coef.p, P, d_ptab.p + A.poff[c0], P, total, nc, ilog2(P), shifts.data(), ce, st);
+            CSG_CUDA(cudaStreamSynchronize(st.s));   // host staging vector goes out of scope
+        }
+    }
+
+    void load_trace(const uint64_t *trace) {
+        need(S_AIR, "csg_set_air must be called first");
+        const size_t count = (size_t)air.width * n;
+        Timer t(st);
+        t.start();
+        d_io.reserve(count); d_polys.reserve(count);
+        CSG_CUDA(cudaMemcpyAsync(d_io.p, trace, count * sizeof(uint64_t), cudaMemcpyHostToDevice, st.s));
+        to_montgomery(d_io.p, d_polys.p, count, st);   // d_polys holds the trace until it is interpolated in place of it
+        tm.h2d = t.stop();
+        fri.clear();
+        stage = S_TRACE;
+    }
+    // for benchmarking with inputs already resident: the trace as left on the device by the last load_trace
+    void reload_resident() {
+        need(S_TRACE, "no trace has been loaded");
+        const size_t count = (size_t)air.width * n;
+        to_montgomery(d_io.p, d_polys.p, count, st);
+        fri.clear();
+        stage = S_TRACE;
+        tm.h2d = 0;
+    }
+
+    void need(Stage s, const char *msg) const { if (stage < s) throw StateError(msg); }
+    void download_root(const DBuf<uint32_t> &nodes, uint8_t root[32]) {
+        CSG_CUDA(cudaMemcpyAsync(root, nodes.p + 8, 32, cudaMemcpyDeviceToHost, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+    }
+
+    // ------------------------------------------------------------------------------------------ stage 1 + 2
+    void extend_and_commit_trace(uint8_t root[32]) {
+        need(S_TRACE, "csg_load_trace must be called first");
+        const size_t w = air.width;
+        Timer t(st);
+        t.start();
+        scratch.reserve(w * n);
+        intt_columns(roots, ntt, d_polys.p, n, scratch.p, n, w, logn, st);
+        std::swap(d_polys.p, scratch.p); std::swap(d_polys.n, scratch.n);   // d_polys = coefficients
+        d_lde.reserve(w * lde_n);
+        coset_ntt_columns(roots, ntt, d_polys.p, n, d_lde.p, n, w * n, w, logn, lde_shift.data(), b, st);
+        tm.lde = t.stop();
+        t.start();
+        d_tnodes.reserve(16 * lde_n);
+        hash_rows(d_lde.p, (unsigned)w, n, (unsigned)b, w * n, n, (int)opt.hash_fn, d_tnodes.p + 8 * lde_n, st);
+        merkle_build(d_tnodes.p, lde_n, (int)opt.hash_fn, st);
+        download_root(d_tnodes, root);
+        tm.commit_trace = t.stop();
+        stage = S_COMMITTED;
+    }
+
+    // ------------------------------------------------------------------------------------------ stage 3
+    void eval_constraints(const fe *t_ab, const fe *b_ab) {
+        need(S_COMMITTED, "the trace must be committed first");
+        Timer t(st);
+        t.start();
+        ConsArgs &A = *h_cargs;
+        const fe g = root_of_unity(logn);
+        A.logn = logn; A.ncosets = (unsigned)ce; A.col_stride = n; A.width = air.width;
+        A.g_last = f63::pow(g, n - 1);
+        A.nconstraints = (unsigned)air.num_constraints(); A.ngroups = (unsigned)tg.adj.size();
+        for (size_t i = 0; i < air.num_constraints(); i++) { A.alpha[i] = t_ab[2 * i]; A.beta[i] = t_ab[2 * i + 1]; A.group[i] = tg.group_of[i]; }
+        for (size_t gi = 0; gi < tg.adj.size(); gi++) A.adj_mod[gi] = tg.adj[gi] % n;
+        A.nbgroups = (unsigned)bg.groups.size(); A.nassertions = (unsigned)air.assertions.size();
+        for (size_t gi = 0; gi < bg.groups.size(); gi++) {
+            A.b_adj_mod[gi] = bg.groups[gi].adj % n; A.b_steps[gi] = bg.groups[gi].num_steps; A.b_offset[gi] = bg.groups[gi].offset;
+        }
+        for (size_t kc = 0; kc < ce; kc++) {
+            const fe s = ce_shift[kc];
+            A.lde_coset_stride[kc] = (unsigned long long)(kc * (b / ce)) * air.width * n;
+            A.shift[kc] = s;
+            A.zinv[kc] = inv(sub(f63::pow(s, n), ONE));
+            for (size_t gi = 0; gi < tg.adj.size(); gi++) A.shift_adj[kc][gi] = f63::pow(s, tg.adj[gi]);
+            for (size_t gi = 0; gi < bg.groups.size(); gi++) {
+                A.b_shift_adj[kc][gi] = f63::pow(s, bg.groups[gi].adj);
+                A.b_shift_steps[kc][gi] = f63::pow(s, bg.groups[gi].num_steps);
+            }
+        }
+        // assertion values; a sequence becomes its interpolating polynomial, evaluated in-kernel at x * g^-first_step
+        std::vector<fe> polys;
+        const fe g_inv = inv(g);
+        for (size_t i = 0; i < air.assertions.size(); i++) {
+            const Assertion &s = air.assertions[i];
+            A.a_col[i] = s.column; A.a_group[i] = bg.group_of[i];
+            A.a_alpha[i] = b_ab[2 * i]; A.a_beta[i] = b_ab[2 * i + 1];
+            A.a_value[i] = s.values[0]; A.a_poly_len[i] = (unsigned)s.values.size(); A.a_poly_off[i] = polys.size();
+            A.a_xoff[i] = s.first_step ? f63::pow(g_inv, s.first_step) : ONE;
+            if (s.values.size() > 1) {
+                std::vector<fe> c = host_interpolate(s.values);
+                polys.insert(polys.end(), c.begin(), c.end());
+            }
+        }
+        d_apoly.reserve(polys.size() ? polys.size() : 1);
+        if (!polys.empty()) CSG_CUDA(cudaMemcpyAsync(d_apoly.p, polys.data(), polys.size() * sizeof(fe), cudaMemcpyHostToDevice, st.s));
+        d_cargs.reserve(1);
+        CSG_CUDA(cudaMemcpyAsync(d_cargs.p, &A, sizeof A, cudaMemcpyHostToDevice, st.s));
+        d_comb.reserve(ce * n);
+        csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_comb.p, st);
+        tm.constraints = t.stop();   // also keeps `polys` alive until the copy has completed
+        stage = S_EVALUATED;
+    }
+    // coefficients of the polynomial taking the given values on <w_len> (host, tiny: one value per signature)
+    static std::vector<fe> host_interpolate(const std::vector<fe> &vals) {
+        const size_t len = vals.size();
+        const fe w_inv = inv(root_of_unity(ilog2(len))), len_inv = inv(to_mont(len));
+        std::vector<fe> c(len);
+        for (size_t m = 0; m < len; m++) {
+            fe s = 0, wm = f63::pow(w_inv, m), x = ONE;
+            for (size_t i = 0; i < len; i++) { s = add(s, mul(vals[i], x)); x = mul(x, wm); }
+            c[m] = mul(s, len_inv);
+        }
+        return c;
+    }
+
+    // ------------------------------------------------------------------------------------------ stage 4
+    void commit_composition(uint8_t root[32]) {
+        need(S_EVALUATED, "constraints must be evaluated first");
+        Timer t(st);
+        t.start();
+        // per-coset interpolants, divided by s_kc^m; then the cross-coset step yields the ce column polynomials
+        std::vector<fe> sinv(ce);
+        for (size_t kc = 0; kc < ce; kc++) sinv[kc] = inv(ce_shift[kc]);
+        d_e.reserve(ce * n); d_cpolys.reserve(ce * n);
+        coset_intt_columns(roots, ntt, d_comb.p, n, d_e.p, n, logn, sinv.data(), ce, st);
+        std::vector<fe> mat(ce * ce);
+        const fe off_n_inv = inv(f63::pow(to_mont(GENERATOR), n)), ce_inv = inv(to_mont(ce)), w_ce_inv = inv(root_of_unity(ilog2(ce)));
+        for (size_t tt = 0; tt < ce; tt++)
+            for (size_t k = 0; k < ce; k++)
+                mat[tt * ce + k] = mul(mul(f63::pow(off_n_inv, tt), ce_inv), f63::pow(w_ce_inv, (k * tt) % ce));
+        composition_columns(d_e.p, d_cpolys.p, n, (unsigned)ce, mat.data(), st);
+        d_clde.reserve(ce * lde_n);
+        coset_ntt_columns(roots, ntt, d_cpolys.p, n, d_clde.p, n, ce * n, ce, logn, lde_shift.data(), b, st);
+        d_cnodes.reserve(16 * lde_n);
+        hash_rows(d_clde.p, (unsigned)ce, n, (unsigned)b, ce * n, n, (int)opt.hash_fn, d_cnodes.p + 8 * lde_n, st);
+        merkle_build(d_cnodes.p, lde_n, (int)opt.hash_fn, st);
+        download_root(d_cnodes, root);
+        tm.composition = t.stop();
+        stage = S_COMPOSED;
+    }
+
+    // ------------------------------------------------------------------------------------------ stage 5 + 6
+    void ood(fe z_) {
+        need(S_COMPOSED, "the composition polynomial must be committed first");
+        Timer t(st);
+        t.start();
+        z = z_;
+        const size_t w = air.width;
+        const fe pts[2] = {z, mul(z, root_of_unity(logn))};
+        std::vector<fe> vals(2 * w);
+        eval_polys_at(d_polys.p, n, w, n, pts, 2, vals.data(), scratch2, st);
+        ood_cur.assign(vals.begin(), vals.begin() + w);
+        ood_next.assign(vals.begin() + w, vals.end());
+        const fe zm = f63::pow(z, ce);
+        ood_comp.resize(ce);
+        eval_polys_at(d_cpolys.p, n, ce, n, &zm, 1, ood_comp.data(), scratch2, st);
+        tm.ood_deep = t.stop();
+        stage = S_OOD;
+    }
+    void deep(const fe *trace_ab, const fe *comp_d, fe lambda, fe mu) {
+        need(S_OOD, "the out-of-domain frame must be computed first");
+        Timer t(st);
+        t.start();
+        const size_t w = air.width;
+        std::vector<fe> coef(2 * w);
+        DeepArgs a{};
+        a.z = z; a.zg = mul(z, root_of_unity(logn)); a.zm = f63::pow(z, ce);
+        for (size_t c = 0; c < w; c++) {
+            coef[c] = trace_ab[2 * c]; coef[w + c] = trace_ab[2 * c + 1];
+            a.az = add(a.az, mul(coef[c], ood_cur[c]));
+            a.bzg = add(a.bzg, mul(coef[w + c], ood_next[c]));
+        }
+        for (size_t r = 0; r < ce; r++) a.czm = add(a.czm, mul(comp_d[r], ood_comp[r]));
+        a.lambda = lambda; a.mu = mu; a.ncosets = (unsigned)b;
+        for (size_t k = 0; k < b; k++) a.shift[k] = lde_shift[k];
+        d_abc.reserve(3 * n); d_abc_lde.reserve(3 * lde_n); d_deep.reserve(lde_n);
+        combine_polys(d_polys.p, n, w, n, coef.data(), 2, d_abc.p, n, scratch2, st);
+        combine_polys(d_cpolys.p, n, ce, n, comp_d, 1, d_abc.p + 2 * n, n, scratch, st);
+        coset_ntt_columns(roots, ntt, d_abc.p, n, d_abc_lde.p, n, 3 * n, 3, logn, lde_shift.data(), b, st);
+        deep_quotients(d_abc_lde.p, roots.W.p, n, a, d_deep.p, st);
+        fri.clear();
+        fri.emplace_back(new FriLayer());
+        fri.back()->evals = d_deep.p; fri.back()->m = lde_n;
+        tm.ood_deep += t.stop();   // also keeps coef alive until the copies have completed
+        tm.fri = 0;
+        stage = S_DEEP;
+    }
+
+    // ------------------------------------------------------------------------------------------ stage 7
+    void fri_commit_layer(uint8_t root[32]) {
+        need(S_DEEP, "the DEEP composition must be computed first");
+        FriLayer &L = *fri.back();
+        Timer t(st);
+        t.start();
+        const size_t q = L.m / 4;
+        L.nodes.reserve(16 * q);
+        hash_rows(L.evals, 4, q, 1, 0, q, (int)opt.hash_fn, L.nodes.p + 8 * q, st);
+        merkle_build(L.nodes.p, q, (int)opt.hash_fn, st);
+        download_root(L.nodes, root);
+        L.committed = true;
+        tm.fri += t.stop();
+    }
+    void fri_fold(fe alpha) {
+        need(S_DEEP, "the DEEP composition must be computed first");
+        FriLayer &L = *fri.back();
+        if (!L.committed) throw StateError("the current FRI layer must be committed before it is folded");
+        Timer t(st);
+        t.start();
+        const size_t m = L.m, q = m / 4;
+        const unsigned logm = ilog2(m);
+        FoldArgs a{};
+        a.alpha = alpha; a.offset_inv = inv(to_mont(GENERATOR));
+        const fe w_inv = inv(root_of_unity(logm));
+        a.zeta_inv = f63::pow(w_inv, q); a.quarter = inv(to_mont(4));
+        a.logm = logm; a.logW = roots.logn;
+        if (logm > roots.logn) {
+            if (logm - roots.logn > 5) throw StateError("FRI layer too large for the root table");
+            for (unsigned i = 0; i < (1u << (logm - roots.logn)); i++) a.small[i] = f63::pow(w_inv, i);
+        }
+        std::unique_ptr<FriLayer> N(new FriLayer());
+        N->owned.reserve(q);
+        csg::fri_fold4(L.evals, m, roots.W.p, a, N->owned.p, st);
+        N->evals = N->owned.p; N->m = q;
+        fri.push_back(std::move(N));
+        tm.fri += t.stop();
+    }
+    size_t num_fri_folds() const { size_t r = 0, d = lde_n; while (d > opt.fri_max_remainder_size) { d /= 4; r++; } return r; }
+
+    // ------------------------------------------------------------------------------------------ stage 9
+    void upload_positions(const std::vector<size_t> &pos) {
+        std::vector<uint32_t> p32(pos.begin(), pos.end());
+        d_idx.reserve(std::max<size_t>(p32.size(), 4096));
+        CSG_CUDA(cudaMemcpyAsync(d_idx.p, p32.data(), p32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+    }
+    // rows (canonical, row-major) of a coset-major matrix at the given natural positions
+    std::vector<uint64_t> open_rows(const fe *data, unsigned width, unsigned ncosets, size_t coset_stride, size_t col_stride, const std::vector<size_t> &pos) {
+        upload_positions(pos);
+        std::vector<uint64_t> rows(pos.size() * width);
+        // d_io still holds the resident trace for re-proving; rows go through a separate small buffer
+        DBuf<uint64_t> out;
+        out.reserve(rows.size());
+        gather_rows(data, width, ncosets, coset_stride, col_stride, d_idx.p, pos.size(), out.p, st);
+        CSG_CUDA(cudaMemcpyAsync(rows.data(), out.p, rows.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+        return rows;
+    }
+    // BatchMerkleProof::serialize_nodes() of the opening of `pos` in the tree `nodes` over nleaves leaves
+    std::vector<uint8_t> open_paths(const DBuf<uint32_t> &nodes, size_t nleaves, const std::vector<size_t> &pos) {
+        std::vector<std::vector<uint32_t>> slots = batch_opening_nodes(nleaves, pos);
+        std::vector<uint32_t> flat;
+        for (auto &s : slots) flat.insert(flat.end(), s.begin(), s.end());
+        std::vector<uint8_t> dig(flat.size() * 32);
+        if (!flat.empty()) {
+            d_idx.reserve(std::max<size_t>(flat.size(), 4096));
+            d_dig.reserve(std::max<size_t>(flat.size() * 8, 8 * 4096));
+            CSG_CUDA(cudaMemcpyAsync(d_idx.p, flat.data(), flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st.s));
+            gather_digests(nodes.p, d_idx.p, flat.size(), d_dig.p, st);
+            CSG_CUDA(cudaMemcpyAsync(dig.data(), d_dig.p, dig.size(), cudaMemcpyDeviceToHost, st.s));
+            CSG_CUDA(cudaStreamSynchronize(st.s));
+        }
+        std::vector<uint8_t> out;
+        out.push_back((uint8_t)slots.size());
+        size_t o = 0;
+        for (auto &s : slots) {
+            out.push_back((uint8_t)s.size());
+            out.insert(out.end(), dig.begin() + o * 32, dig.begin() + (o + s.size()) * 32);
+            o += s.size();
+        }
+        return out;
+    }
+    static std::vector<size_t> fold_positions(const std::vector<size_t> &pos, size_t domain) {
+        std::vector<size_t> out;
+        for (size_t p : pos) { size_t f = p % (domain / 4); if (std::find(out.begin(), out.end(), f) == out.end()) out.push_back(f); }
+        return out;
+    }
+
+    // ------------------------------------------------------------------------------------------ the whole of Prover::prove
+    void write_context(Bytes &w) const {
+        w.u8((uint8_t)air.width); w.u8((uint8_t)logn); w.u16(0);
+        w.u8(8); w.u64(P);
+        w.u8((uint8_t)opt.num_queries); w.u8((uint8_t)ilog2(opt.blowup_factor)); w.u8((uint8_t)opt.grinding_factor);
+        w.u8((uint8_t)opt.hash_fn); w.u8((uint8_t)opt.field_extension);
+        w.u8((uint8_t)ilog2(opt.fri_folding_factor)); w.u8((uint8_t)ilog2(opt.fri_max_remainder_size));
+    }
+    void prove_loaded(uint8_t **proof, size_t *proof_len) {
+        need(S_TRACE, "csg_load_trace must be called first");
+        auto t0 = std::chrono::steady_clock::now();
+        const unsigned long long launches0 = st.launches;
+        const int hf = (int)opt.hash_fn;
+        const size_t w = air.width, nc = air.num_constraints(), na = air.assertions.size();
+        Bytes seed;
+        for (uint64_t v : air.pub_inputs) seed.u64(v);
+        write_context(seed);
+        Coin coin(hf, seed.v.data(), seed.v.size());
+
+        uint8_t trace_root[32], comp_root[32];
+        extend_and_commit_trace(trace_root);
+        coin.reseed(trace_root);
+        std::vector<fe> t_ab(2 * nc), b_ab(2 * na + 2);
+        for (size_t i = 0; i < 2 * nc; i++) t_ab[i] = coin.draw();
+        for (size_t i = 0; i < 2 * na; i++) b_ab[i] = coin.draw();
+        eval_constraints(t_ab.data(), b_ab.data());
+        commit_composition(comp_root);
+        coin.reseed(comp_root);
+
+        ood(coin.draw());
+        uint8_t d[32];
+        hash_elements_host(hf, ood_cur.data(), w, d); coin.reseed(d);
+        hash_elements_host(hf, ood_next.data(), w, d); coin.reseed(d);
+        hash_elements_host(hf, ood_comp.data(), ce, d); coin.reseed(d);
+
+        std::vector<fe> dab(2 * w), dd(ce);
+        for (size_t c = 0; c < w; c++) { dab[2 * c] = coin.draw(); dab[2 * c + 1] = coin.draw(); (void)coin.draw(); }
+        for (size_t r = 0; r < ce; r++) dd[r] = coin.draw();
+        const fe lambda = coin.draw(), mu = coin.draw();
+        deep(dab.data(), dd.data(), lambda, mu);
+
+        const size_t nlayers = num_fri_folds() + 1;
+        std::vector<std::vector<uint8_t>> fri_roots(nlayers, std::vector<uint8_t>(32));
+        for (size_t l = 0; l < nlayers; l++) {
+            fri_commit_layer(fri_roots[l].data());
+            coin.reseed(fri_roots[l].data());
+            const fe alpha = coin.draw();
+            if (l + 1 < nlayers) fri_fold(alpha);
+        }
+
+        Timer tq(st);
+        tq.start();
+        uint64_t nonce = 1;
+        while (coin.check_leading_zeros(nonce) < opt.grinding_factor) nonce++;
+        coin.reseed_with_int(nonce);
+        std::vector<size_t> pos = coin.draw_integers(opt.num_queries, lde_n);
+
+        Bytes pf;
+        write_context(pf);
+        pf.u16((uint16_t)((2 + nlayers) * 32));
+        pf.put(trace_root, 32); pf.put(comp_root, 32);
+        for (auto &r : fri_roots) pf.put(r.data(), 32);
+        {
+            std::vector<uint64_t> rows = open_rows(d_lde.p, (unsigned)w, (unsigned)b, w * n, n, pos);
+            pf.u32((uint32_t)(rows.size() * 8));
+            for (uint64_t v : rows) pf.u64(v);
+            std::vector<uint8_t> paths = open_paths(d_tnodes, lde_n, pos);
+            pf.u32((uint32_t)paths.size()); pf.put(paths.data(), paths.size());
+        }
+        {
+            std::vector<uint64_t> rows = open_rows(d_clde.p, (unsigned)ce, (unsigned)b, ce * n, n, pos);
+            pf.u32((uint32_t)(rows.size() * 8));
+            for (uint64_t v : rows) pf.u64(v);
+            std::vector<uint8_t> paths = open_paths(d_cnodes, lde_n, pos);
+            pf.u32((uint32_t)paths.size()); pf.put(paths.data(), paths.size());
+        }
+        pf.u16((uint16_t)(w * 8));
+        for (fe v : ood_cur) pf.element(v);
+        for (fe v : ood_next) pf.element(v);
+        pf.u16((uint16_t)(ce * 8));
+        for (fe v : ood_comp) pf.element(v);
+        {
+            pf.u8((uint8_t)(nlayers - 1));
+            std::vector<size_t> fp = pos;
+            size_t domain = lde_n;
+            for (size_t l = 0; l + 1 < nlayers; l++) {
+                fp = fold_positions(fp, domain);
+                const size_t q = domain / 4;
+                std::vector<uint64_t> rows = open_rows(fri[l]->evals, 4, 1, 0, q, fp);
+                pf.u32((uint32_t)(rows.size() * 8));
+                for (uint64_t v : rows) pf.u64(v);
+                std::vector<uint8_t> paths = open_paths(fri[l]->nodes, q, fp);
+                pf.u32((uint32_t)paths.size()); pf.put(paths.data(), paths.size());
+                domain = q;
+            }
+            const FriLayer &last = *fri[nlayers - 1];
+            std::vector<uint64_t> rem(last.m);
+            DBuf<uint64_t> tmp;
+            tmp.reserve(last.m);
+            from_montgomery(last.evals, tmp.p, last.m, st);
+            CSG_CUDA(cudaMemcpyAsync(rem.data(), tmp.p, last.m * 8, cudaMemcpyDeviceToHost, st.s));
+            CSG_CUDA(cudaStreamSynchronize(st.s));
+            pf.u16((uint16_t)(last.m * 8));
+            for (uint64_t v : rem) pf.u64(v);
+            pf.u8(1);
+        }
+        pf.u64(nonce);
+        tm.queries = tq.stop();
+        tm.kernel_launches = st.launches - launches0;
+        tm.total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+        *proof = (uint8_t *)malloc(pf.v.size());
+        if (!*proof) throw std::bad_alloc();
+        memcpy(*proof, pf.v.data(), pf.v.size());
+        *proof_len = pf.v.size();
+        stage = S_TRACE;   // the resident trace (d_io) can be proved again
+    }
+};
+
+// ================================================================================================ C ABI
+namespace {
+template <class F>
+int guarded(csg_ctx *ctx, F f) {
+    if (!ctx) return CSG_ERR_ARG;
+    try {
+        CSG_CUDA(cudaSetDevice(ctx->device));
+        f();
+        return CSG_OK;
+    } catch (const ArgError &e) { ctx->err = e.what(); return CSG_ERR_ARG; }
+    catch (const StateError &e) { ctx->err = e.what(); return CSG_ERR_STATE; }
+    catch (const CudaError &e) { ctx->err = e.what(); return CSG_ERR_CUDA; }
+    catch (const std::exception &e) { ctx->err = e.what(); return CSG_ERR_UNSUPPORTED; }
+}
+std::vector<fe> mont_vec(const uint64_t *v, size_t n) { std::vector<fe> r(n); for (size_t i = 0; i < n; i++) r[i] = to_mont(v[i] % P); return r; }
+}  // namespace
+
+extern "C" {
+
+csg_ctx *csg_create(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    csg_ctx *ctx = new csg_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->st.s, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
+    return ctx;
+}
+void csg_destroy(csg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st.s);
+    cudaStream_t s = ctx->st.s;
+    delete ctx;
+    cudaStreamDestroy(s);
+}
+const char *csg_last_error(const csg_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context (CUDA device unavailable)"; }
+void csg_free(void *p) { free(p); }
+
+int csg_set_air(csg_ctx *ctx, int air_id, size_t trace_len, const csg_options *opt, const uint64_t *pub, size_t npub) {
+    return guarded(ctx, [&] { ctx->set_air(air_id, trace_len, opt, pub, npub); });
+}
+int csg_load_trace(csg_ctx *ctx, const uint64_t *trace) { return guarded(ctx, [&] { if (!trace) throw ArgError("null trace"); ctx->load_trace(trace); }); }
+int csg_reload_resident_trace(csg_ctx *ctx) { return guarded(ctx, [&] { ctx->reload_resident(); }); }
+int csg_prove_loaded(csg_ctx *ctx, uint8_t **proof, size_t *proof_len) {
+    return guarded(ctx, [&] { if (!proof || !proof_len) throw ArgError("null output"); ctx->prove_loaded(proof, proof_len); });
+}
+int csg_prove(csg_ctx *ctx, int air_id, const uint64_t *trace, size_t trace_len, const uint64_t *pub, size_t npub, const csg_options *opt,
+              uint8_t **proof, size_t *proof_len) {
+    return guarded(ctx, [&] {
+        if (!trace || !proof || !proof_len) throw ArgError("null argument");
+        ctx->set_air(air_id, trace_len, opt, pub, npub);
+        ctx->load_trace(trace);
+        ctx->prove_loaded(proof, proof_len);
+    });
+}
+int csg_extend_and_commit_trace(csg_ctx *ctx, uint8_t root[32]) { return guarded(ctx, [&] { ctx->extend_and_commit_trace(root); }); }
+int csg_eval_constraints(csg_ctx *ctx, const uint64_t *t_coeffs, const uint64_t *b_coeffs) {
+    return guarded(ctx, [&] {
+        ctx->need(S_AIR, "csg_set_air must be called first");
+        std::vector<fe> t = mont_vec(t_coeffs, 2 * ctx->air.num_constraints()), bb = mont_vec(b_coeffs, 2 * ctx->air.assertions.size());
+        bb.push_back(0);
+        ctx->eval_constraints(t.data(), bb.data());
+    });
+}
+int csg_commit_composition(csg_ctx *ctx, uint8_t root[32]) { return guarded(ctx, [&] { ctx->commit_composition(root); }); }
+int csg_ood(csg_ctx *ctx, uint64_t z, uint64_t *frame_cur, uint64_t *frame_next, uint64_t *comp) {
+    return guarded(ctx, [&] {
+        ctx->ood(to_mont(z % P));
+        for (size_t c = 0; c < ctx->air.width; c++) { frame_cur[c] = from_mont(ctx->ood_cur[c]); frame_next[c] = from_mont(ctx->ood_next[c]); }
+        for (size_t r = 0; r < ctx->ce; r++) comp[r] = from_mont(ctx->ood_comp[r]);
+    });
+}
+int csg_deep(csg_ctx *ctx, const uint64_t *trace_ab, const uint64_t *comp_d, const uint64_t lambda_mu[2]) {
+    return guarded(ctx, [&] {
+        ctx->need(S_AIR, "csg_set_air must be called first");
+        std::vector<fe> ab = mont_vec(trace_ab, 2 * ctx->air.width), d = mont_vec(comp_d, ctx->ce);
+        ctx->deep(ab.data(), d.data(), to_mont(lambda_mu[0] % P), to_mont(lambda_mu[1] % P));
+    });
+}
+int csg_fri_commit_layer(csg_ctx *ctx, uint8_t root[32]) { return guarded(ctx, [&] { ctx->fri_commit_layer(root); }); }
+int csg_fri_fold(csg_ctx *ctx, uint64_t alpha) { return guarded(ctx, [&] { ctx->fri_fold(to_mont(alpha % P)); }); }
+int csg_fri_remainder(csg_ctx *ctx, uint64_t *out, size_t cap, size_t *len) {
+    return guarded(ctx, [&] {
+        ctx->need(S_DEEP, "the DEEP composition must be computed first");
+        const FriLayer &L = *ctx->fri.back();
+        if (cap < L.m) throw ArgError("remainder buffer too small");
+        DBuf<uint64_t> tmp;
+        tmp.reserve(L.m);
+        from_montgomery(L.evals, tmp.p, L.m, ctx->st);
+        CSG_CUDA(cudaMemcpyAsync(out, tmp.p, L.m * 8, cudaMemcpyDeviceToHost, ctx->st.s));
+        CSG_CUDA(cudaStreamSynchronize(ctx->st.s));
+        *len = L.m;
+    });
+}
+static void copy_opening(const std::vector<uint64_t> &r, const std::vector<uint8_t> &p, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
+    if (p.size() > cap) throw ArgError("path buffer too small");
+    memcpy(rows, r.data(), r.size() * 8);
+    memcpy(paths, p.data(), p.size());
+    *paths_len = p.size();
+}
+int csg_open_trace(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
+    return guarded(ctx, [&] {
+        ctx->need(S_COMMITTED, "the trace must be committed first");
+        std::vector<size_t> pos(positions, positions + npos);
+        const size_t w = ctx->air.width;
+        copy_opening(ctx->open_rows(ctx->d_lde.p, (unsigned)w, (unsigned)ctx->b, w * ctx->n, ctx->n, pos), ctx->open_paths(ctx->d_tnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
+    });
+}
+int csg_open_composition(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
+    return guarded(ctx, [&] {
+        ctx->need(S_COMPOSED, "the composition polynomial must be committed first");
+        std::vector<size_t> pos(positions, positions + npos);
+        copy_opening(ctx->open_rows(ctx->d_clde.p, (unsigned)ctx->ce, (unsigned)ctx->b, ctx->ce * ctx->n, ctx->n, pos), ctx->open_paths(ctx->d_cnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
+    });
+}
+int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
+    return guarded(ctx, [&] {
+        ctx->need(S_DEEP, "the DEEP composition must be computed first");
+        if (layer >= ctx->fri.size() || !ctx->fri[layer]->committed) throw ArgError("no such committed FRI layer");
+        std::vector<size_t> pos(positions, positions + npos);
+        const FriLayer &L = *ctx->fri[layer];
+        copy_opening(ctx->open_rows(L.evals, 4, 1, 0, L.m / 4, pos), ctx->open_paths(L.nodes, L.m / 4, pos), rows, paths, cap, paths_len);
+    });
+}
+int csg_get_timings(const csg_ctx *ctx, csg_timings *out) { if (!ctx || !out) return CSG_ERR_ARG; *out = ctx->tm; return CSG_OK; }
+
+// ---------------------------------------------------------------------------------------------- kernel-level entry points
+int csg_k_lde(csg_ctx *ctx, const uint64_t *cols, size_t width, size_t n, size_t blowup, uint64_t *lde) {
+    return guarded(ctx, [&] {
+        if (!cols || !lde || n < 2 || (n & (n - 1)) || blowup < 1 || (blowup & (blowup - 1)) || blowup > 32) throw ArgError("bad LDE shape");
+        Stream &st = ctx->st;
+        RootTable rt; NttScratch sc;
+        const unsigned logn = ilog2(n);
+        rt.build(logn, st);
+        DBuf<uint64_t> io; DBuf<fe> a, c, e;
+        io.reserve(width * n * blowup); a.reserve(width * n); c.reserve(width * n); e.reserve(width * n * blowup);
+        CSG_CUDA(cudaMemcpyAsync(io.p, cols, width * n * 8, cudaMemcpyHostToDevice, st.s));
+        to_montgomery(io.p, a.p, width * n, st);
+        intt_columns(rt, sc, a.p, n, c.p, n, width, logn, st);
+        std::vector<fe> shifts(blowup);
+        fe acc = to_mont(GENERATOR), w = root_of_unity(ilog2(n * blowup));
+        for (size_t k = 0; k < blowup; k++) { shifts[k] = acc; acc = mul(acc, w); }
+        coset_ntt_columns(rt, sc, c.p, n, e.p, n, width * n, width, logn, shifts.data(), blowup, st);
+        coset_major_to_natural(e.p, (unsigned)width, (unsigned)blowup, n, io.p, st);
+        CSG_CUDA(cudaMemcpyAsync(lde, io.p, width * n * blowup * 8, cudaMemcpyDeviceToHost, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+    });
+}
+int csg_k_hash_rows(csg_ctx *ctx, int hash_fn, const uint64_t *cols, size_t width, size_t rows, uint8_t *digests) {
+    return guarded(ctx, [&] {
+        if (!cols || !digests || !rows || !width || width > 128) throw ArgError("bad matrix shape");
+        Stream &st = ctx->st;
+        DBuf<uint64_t> io; DBuf<fe> a; DBuf<uint32_t> d;
+        io.reserve(width * rows); a.reserve(width * rows); d.reserve(8 * rows);
+        CSG_CUDA(cudaMemcpyAsync(io.p, cols, width * rows * 8, cudaMemcpyHostToDevice, st.s));
+        to_montgomery(io.p, a.p, width * rows, st);
+        hash_rows(a.p, (unsigned)width, rows, 1, 0, rows, hash_fn, d.p, st);
+        CSG_CUDA(cudaMemcpyAsync(digests, d.p, 32 * rows, cudaMemcpyDeviceToHost, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+    });
+}
+int csg_k_merkle(csg_ctx *ctx, int hash_fn, const uint8_t *leaves, size_t nleaves, uint8_t *nodes) {
+    return guarded(ctx, [&] {
+        if (!leaves || !nodes || nleaves < 2 || (nleaves & (nleaves - 1))) throw ArgError("leaf count must be a power of two, at least 2");
+        Stream &st = ctx->st;
+        DBuf<uint32_t> d;
+        d.reserve(16 * nleaves);
+        CSG_CUDA(cudaMemcpyAsync(d.p + 8 * nleaves, leaves, 32 * nleaves, cudaMemcpyHostToDevice, st.s));
+        merkle_build(d.p, nleaves, hash_fn, st);
+        CSG_CUDA(cudaMemcpyAsync(nodes, d.p, 64 * nleaves, cudaMemcpyDeviceToHost, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+    });
+}
+int csg_k_fri_fold4(csg_ctx *ctx, const uint64_t *evals, size_t n, uint64_t alpha, uint64_t *out) {
+    return guarded(ctx, [&] {
+        if (!evals || !out || n < 8 || (n & (n - 1))) throw ArgError("bad FRI layer size");
+        Stream &st = ctx->st;
+        RootTable rt;
+        const unsigned logn = ilog2(n);
+        rt.build(logn, st);
+        DBuf<uint64_t> io; DBuf<fe> a, r;
+        io.reserve(n); a.reserve(n); r.reserve(n / 4);
+        CSG_CUDA(cudaMemcpyAsync(io.p, evals, n * 8, cudaMemcpyHostToDevice, st.s));
+        to_montgomery(io.p, a.p, n, st);
+        FoldArgs fa{};
+        fa.alpha = to_mont(alpha % P); fa.offset_inv = inv(to_mont(GENERATOR));
+        fa.zeta_inv = f63::pow(inv(root_of_unity(logn)), n / 4); fa.quarter = inv(to_mont(4));
+        fa.logm = logn; fa.logW = logn;
+        csg::fri_fold4(a.p, n, rt.W.p, fa, r.p, st);
+        from_montgomery(r.p, io.p, n / 4, st);
+        CSG_CUDA(cudaMemcpyAsync(out, io.p, (n / 4) * 8, cudaMemcpyDeviceToHost, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+    });
+}
+// kernel sweep on synthetic device-resident columns: ms_out = {LDE, row hashing, Merkle tree, one FRI fold of an
+// LDE-sized layer}, each the mean over `iters` runs after one warm-up
+int csg_k_sweep(csg_ctx *ctx, size_t width, size_t n, size_t blowup, int hash_fn, int iters, float ms_out[4]) {
+    return guarded(ctx, [&] {
+        if (n < 8 || (n & (n - 1)) || blowup < 2 || (blowup & (blowup - 1)) || blowup > 32 || !width || width > 128 || iters < 1) throw ArgError("bad sweep shape");
+        Stream &st = ctx->st;
+        RootTable rt; NttScratch sc;
+        const unsigned logn = ilog2(n);
+        const size_t lde_n = n * blowup;
+        rt.build(logn, st);
+        DBuf<uint64_t> io; DBuf<fe> a, c, e, f; DBuf<uint32_t> nodes;
+        io.reserve(width * n); a.reserve(width * n); c.reserve(width * n); e.reserve(width * lde_n); f.reserve(lde_n / 4); nodes.reserve(16 * lde_n);
+        std::vector<uint64_t> host(width * n);
+        uint64_t s = 0x9e3779b97f4a7c15ULL;
+        for (auto &v : host) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v = s % P; }
+        CSG_CUDA(cudaMemcpyAsync(io.p, host.data(), host.size() * 8, cudaMemcpyHostToDevice, st.s));
+        to_montgomery(io.p, a.p, width * n, st);
+        std::vector<fe> shifts(blowup);
+        fe acc = to_mont(GENERATOR), w = root_of_unity(ilog2(lde_n));
+        for (size_t k = 0; k < blowup; k++) { shifts[k] = acc; acc = mul(acc, w); }
+        FoldArgs fa{};
+        const unsigned logm = ilog2(lde_n);
+        const fe w_inv = inv(w);
+        fa.alpha = to_mont(12345); fa.offset_inv = inv(to_mont(GENERATOR)); fa.zeta_inv = f63::pow(w_inv, lde_n / 4); fa.quarter = inv(to_mont(4));
+        fa.logm = logm; fa.logW = logn;
+        for (unsigned i = 0; i < (1u << (logm - logn)); i++) fa.small[i] = f63::pow(w_inv, i);
+        Timer t(st);
+        float acc_ms[4] = {0, 0, 0, 0};
+        for (int it = -1; it < iters; it++) {
+            float ms[4];
+            t.start();
+            intt_columns(rt, sc, a.p, n, c.p, n, width, logn, st);
+            coset_ntt_columns(rt, sc, c.p, n, e.p, n, width * n, width, logn, shifts.data(), blowup, st);
+            ms[0] = t.stop();
+            t.start();
+            hash_rows(e.p, (unsigned)width, n, (unsigned)blowup, width * n, n, hash_fn, nodes.p + 8 * lde_n, st);
+            ms[1] = t.stop();
+            t.start();
+            merkle_build(nodes.p, lde_n, hash_fn, st);
+            ms[2] = t.stop();
+            t.start();
+            csg::fri_fold4(e.p, lde_n, rt.W.p, fa, f.p, st);
+            ms[3] = t.stop();
+            if (it >= 0) for (int k = 0; k < 4; k++) acc_ms[k] += ms[k];
+        }
+        for (int k = 0; k < 4; k++) ms_out[k] = acc_ms[k] / iters;
+    });
+}
+
+}  // extern "C"

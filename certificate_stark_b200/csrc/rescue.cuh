@@ -12,18 +12,20 @@ using f63::fe;
 
 constexpr int STATE_WIDTH = 14, RATE_WIDTH = 7, NUM_ROUNDS = 7, CYCLE = 8;
 
-// out = M * in, M one of CSG_MDS_M / CSG_INV_MDS_M (row-major, Montgomery form)
+// out = M * in, M = MDS or INV_MDS (row-major, Montgomery form).  On the device the tables live in __constant__ memory
+// and the row loop is kept rolled: the 14-term dot product is the unit the instruction cache sees.
 template <bool INVERSE>
 CSG_HD void mat_mul(const fe (&in)[14], fe (&out)[14]) {
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#pragma unroll 1
 #endif
     for (int i = 0; i < 14; i++) {
+        const uint64_t *row = (INVERSE ? CSG_TABLE(CSG_INV_MDS) : CSG_TABLE(CSG_MDS)) + i * 14;
         f63::acc128 acc;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j < 14; j++) acc.mac(INVERSE ? CSG_INV_MDS_M[i * 14 + j] : CSG_MDS_M[i * 14 + j], in[j]);
+        for (int j = 0; j < 14; j++) acc.mac(row[j], in[j]);
         out[i] = acc.reduce();
     }
 }
@@ -66,10 +68,9 @@ CSG_HD void round_residual(const fe (&cur)[14], const fe (&next)[14], const fe *
     for (int i = 0; i < 14; i++) d[i] = f63::sub(b[i], a[i]);
 }
 
-#if !defined(__CUDA_ARCH__)
 // ---- host-only: the permutation itself, for witness generation (rescue.rs:239-263, 108-152)
 inline void apply_round(fe *state, size_t step) {
-    const uint64_t *ark = CSG_ARK_M + (step % CYCLE) * 28;
+    const uint64_t *ark = CSG_TABLE(CSG_ARK) + (step % CYCLE) * 28;
     fe s[14], t[14];
     for (int i = 0; i < 14; i++) s[i] = state[i];
     forward_half(s, ark, t);
@@ -94,5 +95,4 @@ inline void digest(const fe *data, size_t n, fe *out) {
     if (i > 0) apply_permutation(st);
     for (int k = 0; k < 7; k++) out[k] = st[k];
 }
-#endif
 }  // namespace rescue

@@ -1,0 +1,203 @@
+// See stages.cuh.
+#include <vector>
+
+#include "stages.cuh"
+
+namespace csg {
+using namespace f63;
+
+namespace {
+
+__global__ void to_mont_kernel(const uint64_t *__restrict__ in, fe *__restrict__ out, unsigned long long count) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x, step = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < count; i += step) out[i] = mul(in[i], R2);
+}
+__global__ void from_mont_kernel(const fe *__restrict__ in, uint64_t *__restrict__ out, unsigned long long count) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x, step = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < count; i += step) out[i] = from_mont(in[i]);
+}
+unsigned grid_for(size_t count, unsigned threads) {
+    size_t g = (count + threads - 1) / threads;
+    const size_t cap = 148 * 16;   // grid-stride kernels: a few waves of the 148 SMs
+    return (unsigned)(g < cap ? (g ? g : 1) : cap);
+}
+
+struct CrossMat { fe m[16 * 16]; };
+__global__ void composition_columns_kernel(const fe *__restrict__ e, fe *__restrict__ cols, unsigned long long n, unsigned ce, CrossMat M) {
+    unsigned long long m = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    fe v[16];
+    for (unsigned k = 0; k < ce; k++) v[k] = e[k * n + m];
+    const unsigned long long r = m % ce, q0 = m / ce, qs = n / ce;
+    for (unsigned t = 0; t < ce; t++) {
+        acc192 s;
+        for (unsigned k = 0; k < ce; k++) s.mac(M.m[t * ce + k], v[k]);
+        cols[r * n + q0 + qs * t] = s.reduce();
+    }
+}
+
+constexpr unsigned EVAL_THREADS = 256, EVAL_CHUNK = 32;
+struct EvalPoints { fe z[4], z_stride[4]; };   // z_stride = z^EVAL_THREADS
+__global__ void __launch_bounds__(EVAL_THREADS) eval_polys_kernel(const fe *__restrict__ polys, unsigned long long stride, unsigned long long n,
+                                                                 EvalPoints pts, fe *__restrict__ partial) {
+    __shared__ fe red[EVAL_THREADS];
+    const unsigned t = threadIdx.x, c = blockIdx.y, p = blockIdx.z;
+    const unsigned long long base = blockIdx.x * (unsigned long long)(EVAL_THREADS * EVAL_CHUNK);
+    const fe *poly = polys + c * stride;
+    const fe zs = pts.z_stride[p];
+    fe v = 0;
+    // coefficients base + t + j*THREADS, Horner in z^THREADS from the top
+    for (int j = EVAL_CHUNK - 1; j >= 0; j--) {
+        unsigned long long m = base + t + (unsigned long long)j * EVAL_THREADS;
+        fe cm = m < n ? poly[m] : 0;
+        v = add(mul(v, zs), cm);
+    }
+    red[t] = mul(v, f63::pow(pts.z[p], base + t));
+    __syncthreads();
+    for (unsigned s = EVAL_THREADS / 2; s > 0; s >>= 1) {
+        if (t < s) red[t] = add(red[t], red[t + s]);
+        __syncthreads();
+    }
+    if (t == 0) partial[((unsigned long long)p * gridDim.y + c) * gridDim.x + blockIdx.x] = red[0];
+}
+
+template <int NCOMB>
+__global__ void combine_polys_kernel(const fe *__restrict__ polys, unsigned long long stride, unsigned ncols, unsigned long long n,
+                                     const fe *__restrict__ coef, fe *__restrict__ out, unsigned long long out_stride) {
+    unsigned long long m = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    acc192 s[NCOMB];
+    for (unsigned c = 0; c < ncols; c++) {
+        fe v = polys[c * stride + m];
+#pragma unroll
+        for (int t = 0; t < NCOMB; t++) s[t].mac(coef[t * ncols + c], v);
+    }
+#pragma unroll
+    for (int t = 0; t < NCOMB; t++) out[t * out_stride + m] = s[t].reduce();
+}
+
+__global__ void deep_quotients_kernel(const fe *__restrict__ abc, const fe *__restrict__ W, unsigned long long n, DeepArgs a, fe *__restrict__ deep) {
+    unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (j >= n * a.ncosets) return;
+    const unsigned k = (unsigned)(j % a.ncosets);
+    const unsigned long long i = j / a.ncosets;
+    const fe x = mul(a.shift[k], W[i]);
+    const fe *src = abc + (unsigned long long)k * 3 * n + i;
+    const fe na = sub(src[0], a.az), nb = sub(src[n], a.bzg), nc = sub(src[2 * n], a.czm);
+    const fe d1 = sub(x, a.z), d2 = sub(x, a.zg), d3 = sub(x, a.zm);
+    const fe d12 = mul(d1, d2), pinv = inv(mul(d12, d3));
+    const fe i3 = mul(pinv, d12), i12 = mul(pinv, d3);   // 1/d3, 1/(d1 d2)
+    const fe i1 = mul(i12, d2), i2 = mul(i12, d1);
+    fe s = add(add(mul(na, i1), mul(nb, i2)), mul(nc, i3));
+    deep[j] = mul(s, add(a.lambda, mul(a.mu, x)));
+}
+
+__global__ void fri_fold4_kernel(const fe *__restrict__ e, unsigned long long q, const fe *__restrict__ W, FoldArgs a, fe *__restrict__ out) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    const unsigned long long N = 1ULL << a.logW;
+    fe wi;   // w_m^-i
+    if (a.logm <= a.logW) wi = W[(N - (i << (a.logW - a.logm))) & (N - 1)];
+    else {
+        const unsigned extra = a.logm - a.logW;
+        wi = mul(a.small[i & ((1u << extra) - 1)], W[(N - (i >> extra)) & (N - 1)]);
+    }
+    const fe xinv = mul(a.offset_inv, wi);
+    const fe v0 = e[i], v1 = e[i + q], v2 = e[i + 2 * q], v3 = e[i + 3 * q];
+    const fe s02 = add(v0, v2), d02 = sub(v0, v2), s13 = add(v1, v3), d13 = mul(sub(v1, v3), a.zeta_inv);
+    const fe c0 = add(s02, s13), c1 = add(d02, d13), c2 = sub(s02, s13), c3 = sub(d02, d13);
+    const fe y = mul(a.alpha, xinv);
+    fe r = c3;
+    r = add(mul(r, y), c2);
+    r = add(mul(r, y), c1);
+    r = add(mul(r, y), c0);
+    out[i] = mul(r, a.quarter);
+}
+
+__global__ void gather_rows_kernel(const fe *__restrict__ data, unsigned width, unsigned ncosets, unsigned long long coset_stride,
+                                   unsigned long long col_stride, const uint32_t *__restrict__ pos, unsigned npos, uint64_t *__restrict__ rows) {
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npos * width) return;
+    unsigned r = t / width, c = t % width;
+    unsigned long long j = pos[r], k = j % ncosets, i = j / ncosets;
+    rows[t] = from_mont(data[k * coset_stride + c * col_stride + i]);
+}
+
+__global__ void coset_to_natural_kernel(const fe *__restrict__ lde, unsigned width, unsigned ncosets, unsigned long long n, uint64_t *__restrict__ out) {
+    unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned c = blockIdx.y;
+    if (j >= n * ncosets) return;
+    unsigned long long k = j % ncosets, i = j / ncosets;
+    out[c * n * ncosets + j] = from_mont(lde[(k * width + c) * n + i]);
+}
+
+}  // namespace
+
+void coset_major_to_natural(const fe *lde, unsigned width, unsigned ncosets, size_t n, uint64_t *out, Stream &st) {
+    dim3 grid((unsigned)((n * ncosets + 255) / 256), width);
+    CSG_LAUNCH(st, coset_to_natural_kernel, grid, 256, 0, lde, width, ncosets, (unsigned long long)n, out);
+}
+
+void to_montgomery(const uint64_t *in, fe *out, size_t count, Stream &st) {
+    CSG_LAUNCH(st, to_mont_kernel, grid_for(count, 256), 256, 0, in, out, (unsigned long long)count);
+}
+void from_montgomery(const fe *in, uint64_t *out, size_t count, Stream &st) {
+    CSG_LAUNCH(st, from_mont_kernel, grid_for(count, 256), 256, 0, in, out, (unsigned long long)count);
+}
+
+void composition_columns(const fe *e, fe *cols, size_t n, unsigned ce, const fe *mat_host, Stream &st) {
+    if (ce > 16) throw std::runtime_error("constraint blowup above 16 is not supported");
+    CrossMat M;
+    for (unsigned i = 0; i < ce * ce; i++) M.m[i] = mat_host[i];
+    CSG_LAUNCH(st, composition_columns_kernel, (unsigned)((n + 255) / 256), 256, 0, e, cols, (unsigned long long)n, ce, M);
+}
+
+void eval_polys_at(const fe *polys, size_t stride, size_t ncols, size_t n, const fe *points_host, size_t npoints, fe *values_host,
+                   DBuf<fe> &scratch, Stream &st) {
+    if (npoints > 4) throw std::runtime_error("at most 4 evaluation points per call");
+    const unsigned nblk = (unsigned)((n + EVAL_THREADS * EVAL_CHUNK - 1) / (EVAL_THREADS * EVAL_CHUNK));
+    const size_t total = (size_t)nblk * ncols * npoints;
+    scratch.reserve(total);
+    EvalPoints pts{};
+    for (size_t p = 0; p < npoints; p++) { pts.z[p] = points_host[p]; pts.z_stride[p] = f63::pow(points_host[p], EVAL_THREADS); }
+    dim3 grid(nblk, (unsigned)ncols, (unsigned)npoints);
+    CSG_LAUNCH(st, eval_polys_kernel, grid, EVAL_THREADS, 0, polys, (unsigned long long)stride, (unsigned long long)n, pts, scratch.p);
+    std::vector<fe> part(total);
+    CSG_CUDA(cudaMemcpyAsync(part.data(), scratch.p, total * sizeof(fe), cudaMemcpyDeviceToHost, st.s));
+    CSG_CUDA(cudaStreamSynchronize(st.s));
+    for (size_t pc = 0; pc < npoints * ncols; pc++) {
+        fe s = 0;
+        for (unsigned b = 0; b < nblk; b++) s = add(s, part[pc * nblk + b]);
+        values_host[pc] = s;
+    }
+}
+
+void combine_polys(const fe *polys, size_t stride, size_t ncols, size_t n, const fe *coef_host, size_t ncomb, fe *out, size_t out_stride,
+                   DBuf<fe> &scratch, Stream &st) {
+    scratch.reserve(ncomb * ncols);
+    CSG_CUDA(cudaMemcpyAsync(scratch.p, coef_host, ncomb * ncols * sizeof(fe), cudaMemcpyHostToDevice, st.s));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (ncomb == 1) CSG_LAUNCH(st, combine_polys_kernel<1>, grid, 256, 0, polys, (unsigned long long)stride, (unsigned)ncols, (unsigned long long)n, scratch.p, out, (unsigned long long)out_stride);
+    else if (ncomb == 2) CSG_LAUNCH(st, combine_polys_kernel<2>, grid, 256, 0, polys, (unsigned long long)stride, (unsigned)ncols, (unsigned long long)n, scratch.p, out, (unsigned long long)out_stride);
+    else throw std::runtime_error("combine_polys: 1 or 2 combinations per call");
+}
+
+void deep_quotients(const fe *abc, const fe *W, size_t n, const DeepArgs &a, fe *deep, Stream &st) {
+    const size_t total = n * a.ncosets;
+    CSG_LAUNCH(st, deep_quotients_kernel, (unsigned)((total + 255) / 256), 256, 0, abc, W, (unsigned long long)n, a, deep);
+}
+
+void fri_fold4(const fe *evals, size_t m, const fe *W, const FoldArgs &a, fe *out, Stream &st) {
+    const size_t q = m / 4;
+    CSG_LAUNCH(st, fri_fold4_kernel, (unsigned)((q + 255) / 256), 256, 0, evals, (unsigned long long)q, W, a, out);
+}
+
+void gather_rows(const fe *data, unsigned width, unsigned ncosets, size_t coset_stride, size_t col_stride, const uint32_t *pos_dev,
+                 size_t npos, uint64_t *rows_dev, Stream &st) {
+    if (!npos) return;
+    const size_t total = npos * width;
+    CSG_LAUNCH(st, gather_rows_kernel, (unsigned)((total + 255) / 256), 256, 0, data, width, ncosets, (unsigned long long)coset_stride,
+               (unsigned long long)col_stride, pos_dev, (unsigned)npos, rows_dev);
+}
+
+}  // namespace csg

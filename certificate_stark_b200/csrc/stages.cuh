@@ -1,0 +1,54 @@
+// The streaming kernels between the big transforms of Prover::prove (K6-K10 of SURVEY.md section 2.2): representation
+// change of the incoming trace, the cross-coset step that turns per-coset interpolants into composition columns, the
+// out-of-domain evaluations, the DEEP composition and the FRI degree-respecting projection.  All restate the published
+// winterfell v0.3 protocol (the fork at Cargo.toml:20 of the reference is not vendored) as flat data-parallel kernels.
+#pragma once
+#include "dev.cuh"
+
+namespace csg {
+
+// canonical u64 -> Montgomery (BaseElement::new) and back
+void to_montgomery(const uint64_t *in, fe *out, size_t count, Stream &st);
+
+// e[k][m] (k < ce): coefficient m of the size-n interpolant of C on ce coset k, already divided by s_k^m.
+// cols[r][q] = coefficient q*ce + r of the degree < ce*n composition polynomial (CompositionPoly::new's transposition).
+// mat[t*ce + k] = offset^(-n t) / ce * w_ce^(-k t)
+void composition_columns(const fe *e, fe *cols, size_t n, unsigned ce, const fe *mat_host, Stream &st);
+
+// values[p * ncols + c] = poly_c(points[p]) for ncols polynomials of n coefficients at polys[c * stride ..]; the final
+// reduction over per-CTA partial sums runs on the host (a few hundred KB)
+void eval_polys_at(const fe *polys, size_t stride, size_t ncols, size_t n, const fe *points_host, size_t npoints, fe *values_host,
+                   DBuf<fe> &scratch, Stream &st);
+
+// out[t][m] = sum_c coef[t][c] * polys[c][m], t < ncomb (linear combinations of coefficient vectors); coef on the host
+void combine_polys(const fe *polys, size_t stride, size_t ncols, size_t n, const fe *coef_host, size_t ncomb, fe *out, size_t out_stride,
+                   DBuf<fe> &scratch, Stream &st);
+
+struct DeepArgs {
+    fe z, zg, zm;         // the three out-of-domain points
+    fe az, bzg, czm;      // sum alpha_c T_c(z), sum beta_c T_c(zg), sum delta_r H_r(z^m)
+    fe lambda, mu;        // degree adjustment (lambda + mu x)
+    fe shift[32];         // coset shifts s_k of the LDE domain
+    unsigned ncosets;     // blowup
+};
+// abc: coset-major LDE of the three combined polynomials, abc[(k*3 + t)*n + i]; W = root table of size n.
+// deep[j] for natural LDE index j = k + ncosets*i:
+//   ((A - az)/(x - z) + (B - bzg)/(x - zg) + (C - czm)/(x - zm)) * (lambda + mu x)
+void deep_quotients(const fe *abc, const fe *W, size_t n, const DeepArgs &a, fe *deep, Stream &st);
+
+struct FoldArgs {
+    fe alpha, offset_inv, zeta_inv, quarter;
+    fe small[32];       // w_m^-(i_lo), i_lo < 2^extra, where m = 2^logm may exceed the root table size 2^logW
+    unsigned logm, logW;
+};
+// FRI folding factor 4: out[i] = interpolant of {e[i], e[i+q], e[i+2q], e[i+3q]} on x_i*{1, zeta, zeta^2, zeta^3} at alpha
+void fri_fold4(const fe *evals, size_t m, const fe *W, const FoldArgs &a, fe *out, Stream &st);
+
+// rows[t][c] (canonical) = element (c, position[t]) of a coset-major matrix; position j = k + ncosets*i
+void gather_rows(const fe *data, unsigned width, unsigned ncosets, size_t coset_stride, size_t col_stride, const uint32_t *pos_dev,
+                 size_t npos, uint64_t *rows_dev, Stream &st);
+void from_montgomery(const fe *in, uint64_t *out, size_t count, Stream &st);
+// coset-major lde[(k*width + c)*n + i] -> canonical natural-order columns out[c*(n*ncosets) + k + ncosets*i]
+void coset_major_to_natural(const fe *lde, unsigned width, unsigned ncosets, size_t n, uint64_t *out, Stream &st);
+
+}  // namespace csg

@@ -70,6 +70,8 @@ def lib():
         L.air_eval_row.argtypes = [C.c_void_p, C.c_size_t, u64p, u64p, u64p]
         L.air_ce_blowup.argtypes = [C.c_void_p]
         L.air_ce_blowup.restype = C.c_size_t
+        L.fe_array_to_mont.argtypes = [u64p, u64p, C.c_size_t]
+        L.fe_array_from_mont.argtypes = [u64p, u64p, C.c_size_t]
         L.rescue_init_tables()
         L.ecc_init_tables()
     return _lib
@@ -94,6 +96,21 @@ def to_mont(a):
 
 def from_mont(a):
     return np.array([(int(v) * RINV) % P for v in np.asarray(a, dtype=np.uint64).ravel()], dtype=np.uint64).reshape(np.shape(a))
+
+
+def to_mont_fast(a):
+    """canonical -> Montgomery through the C oracle (any shape)"""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty_like(a)
+    lib().fe_array_to_mont(_p64(a), _p64(out), a.size)
+    return out
+
+
+def from_mont_fast(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty_like(a)
+    lib().fe_array_from_mont(_p64(a), _p64(out), a.size)
+    return out
 
 
 def options(num_queries=42, blowup=8, grinding=0, hash_fn=HASH_BLAKE3_256, field_extension=1, folding=4, max_remainder=256):

@@ -10,6 +10,9 @@
 
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 void stark_free(void *p) { free(p); }
+/* representation changes for test drivers: canonical <-> Montgomery over arrays */
+void fe_array_to_mont(const uint64_t *in, fe *out, size_t n) { for (size_t i = 0; i < n; i++) out[i] = fe_from_u64(in[i]); }
+void fe_array_from_mont(const fe *in, uint64_t *out, size_t n) { for (size_t i = 0; i < n; i++) out[i] = fe_to_u64(in[i]); }
 
 /* ------------------------------------------------------------------ byte buffers (winterfell ByteWriter: little endian) */
 typedef struct { uint8_t *p; size_t len, cap; } buf_t;

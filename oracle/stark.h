@@ -55,4 +55,6 @@ void hash_elements(int hash_fn, const fe *elems, size_t n, uint8_t out[32]); /* 
 void merkle_build(int hash_fn, const uint8_t *leaves, size_t nleaves, uint8_t *nodes /* 2*nleaves*32 */);
 size_t merkle_prove_batch(const uint8_t *nodes, size_t nleaves, const size_t *positions, size_t npos, uint8_t *out /* cap */);
 void fri_fold4(const fe *evals, size_t n, fe alpha, fe *out); /* one degree-respecting projection, folding factor 4 */
+void fe_array_to_mont(const uint64_t *in, fe *out, size_t n);
+void fe_array_from_mont(const fe *in, uint64_t *out, size_t n);
 #endif

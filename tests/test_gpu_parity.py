@@ -1,0 +1,190 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI of include/csg.h, against the CPU oracle on the same
+seeded inputs.  Integer arithmetic throughout: every comparison is bit-exact."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+P = 0x4180000000000001
+
+
+def rand_field(rng, shape):
+    return (rng.integers(0, 2**63, size=shape, dtype=np.uint64) % np.uint64(P)).astype(np.uint64)
+
+
+# ---------------------------------------------------------------------------------------------- kernels
+@pytest.mark.parametrize("logn,width,blowup", [(1, 3, 2), (3, 5, 4), (6, 2, 8), (10, 14, 4), (11, 3, 8), (12, 7, 8), (13, 2, 2), (16, 3, 8), (20, 1, 2)])
+def test_lde_matches_oracle(ctx, oracle, logn, width, blowup):
+    rng = np.random.default_rng(logn * 100 + width)
+    n = 1 << logn
+    cols = rand_field(rng, (width, n))
+    got = ctx.lde(cols, blowup)
+    for c in range(width):
+        want = oracle.from_mont_fast(oracle.lde_column(oracle.to_mont_fast(cols[c]), blowup))
+        assert np.array_equal(got[c], want), f"column {c}"
+
+
+def test_lde_of_low_degree_column_is_the_polynomial(ctx):
+    # size-independent property at a large size: LDE of evaluations of x -> x^3 + 5 over the trace domain equals that
+    # polynomial on the coset 3*<w>
+    logn, blowup = 18, 8
+    n = 1 << logn
+    g = pow(pow(3, 131, P), 1 << (55 - logn), P)
+    x = np.empty(n, dtype=object)
+    acc = 1
+    for i in range(n):
+        x[i] = acc
+        acc = acc * g % P
+    col = np.array([(int(v) ** 3 + 5) % P for v in x], dtype=np.uint64).reshape(1, n)
+    got = ctx.lde(col, blowup)[0]
+    gl = pow(pow(3, 131, P), 1 << (55 - logn - 3), P)
+    for j in [0, 1, 7, 8, 9, 12345, n * blowup - 1]:
+        xj = 3 * pow(gl, j, P) % P
+        assert int(got[j]) == (xj ** 3 + 5) % P
+
+
+@pytest.mark.parametrize("hash_fn", [2, 3])
+@pytest.mark.parametrize("width,rows", [(1, 4), (4, 300), (8, 64), (14, 1000), (17, 33), (56, 128), (94, 513), (128, 16)])
+def test_row_hashes_match_oracle_and_hashlib(ctx, oracle, hash_fn, width, rows):
+    rng = np.random.default_rng(width * 7 + rows)
+    cols = rand_field(rng, (width, rows))
+    got = ctx.hash_rows(cols, hash_fn)
+    for r in [0, 1, rows // 2, rows - 1]:
+        data = cols[:, r].astype("<u8").tobytes()
+        want = oracle.blake3(data) if hash_fn == 2 else hashlib.sha3_256(data).digest()
+        assert got[r].tobytes() == want
+    mont = oracle.to_mont_fast(cols)
+    for r in range(0, rows, max(1, rows // 16)):
+        assert got[r].tobytes() == oracle.hash_elements(np.ascontiguousarray(mont[:, r]), hash_fn)
+
+
+@pytest.mark.parametrize("hash_fn", [2, 3])
+@pytest.mark.parametrize("logl", [1, 2, 9, 10, 11, 15])
+def test_merkle_tree_matches_oracle(ctx, oracle, hash_fn, logl):
+    rng = np.random.default_rng(logl)
+    leaves = rng.integers(0, 256, size=(1 << logl, 32), dtype=np.uint8)
+    got = ctx.merkle(leaves, hash_fn)
+    want = oracle.merkle_nodes(leaves, hash_fn)
+    assert np.array_equal(got[1:], want[1:])
+
+
+@pytest.mark.parametrize("logm", [3, 6, 10, 16, 21])
+def test_fri_fold_matches_oracle(ctx, oracle, logm):
+    rng = np.random.default_rng(logm)
+    evals = rand_field(rng, 1 << logm)
+    alpha = int(rand_field(rng, 1)[0])
+    got = ctx.fri_fold4(evals, alpha)
+    want = oracle.from_mont_fast(oracle.fri_fold4(oracle.to_mont_fast(evals), int(oracle.to_mont_fast(np.array([alpha], dtype=np.uint64))[0])))
+    assert np.array_equal(got, want)
+
+
+def test_fri_fold_of_a_cubic_is_constant(ctx):
+    # folding by 4 maps a polynomial of degree < 4 to a constant: sum_d c_d alpha^d
+    m, alpha, c = 1 << 12, 987654321, [11, 22, 33, 44]
+    gl = pow(pow(3, 131, P), 1 << (55 - 12), P)
+    ev = np.array([sum(cd * pow(3 * pow(gl, j, P) % P, d, P) for d, cd in enumerate(c)) % P for j in range(m)], dtype=np.uint64)
+    out = ctx.fri_fold4(ev, alpha)
+    want = sum(cd * pow(alpha, d, P) for d, cd in enumerate(c)) % P
+    assert np.all(out == np.uint64(want))
+
+
+# ---------------------------------------------------------------------------------------------- whole proofs
+def prove_both(ctx, oracle, csg, air_id, trace, pub, blowup=8, hash_fn=2):
+    want = oracle.prove(air_id, trace, pub, oracle.options(blowup=blowup, hash_fn=hash_fn))
+    got = ctx.prove(air_id, trace, pub, csg.ProofOptions(blowup_factor=blowup, hash_fn=hash_fn))
+    return got, want
+
+
+def assert_same_proof(got, want):
+    if got != want:
+        first = next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), min(len(got), len(want)))
+        raise AssertionError(f"proof bytes differ: len {len(got)} vs {len(want)}, first difference at byte {first}")
+
+
+@pytest.mark.parametrize("chain", [2, 8, 128, 1024])
+@pytest.mark.parametrize("hash_fn", [2, 3])
+def test_rescue_proof_identical_to_oracle(ctx, oracle, csg, chain, hash_fn):
+    # config 2: benches/rescue.rs, seed [42..48], blowup 4
+    trace, pub = csg.build_rescue_trace(np.arange(42, 49, dtype=np.uint64), chain)
+    got, want = prove_both(ctx, oracle, csg, csg.AIR_RESCUE, trace, pub, blowup=4, hash_fn=hash_fn)
+    assert_same_proof(got, want)
+    assert oracle.verify(oracle.AIR_RESCUE, pub, got) == 0
+
+
+@pytest.mark.parametrize("blowup", [4, 8, 16])
+def test_range_proof_identical_to_oracle(ctx, oracle, csg, blowup):
+    for number in [0, 1, 123456789012345, 2**63 - 1]:
+        trace, pub = csg.build_range_trace(number)
+        got, want = prove_both(ctx, oracle, csg, csg.AIR_RANGE, trace, pub, blowup=blowup)
+        assert_same_proof(got, want)
+        assert oracle.verify(oracle.AIR_RANGE, pub, got) == 0
+
+
+def test_merkle_init_proof_identical_to_oracle(ctx, oracle, csg):
+    z = np.zeros(14, dtype=np.uint64)
+    trace, pub = csg.build_merkle_init_trace(z, z, 1)   # PreMerkleExample::new (src/merkle/init/mod.rs:66-79)
+    for blowup in (4, 8):
+        got, want = prove_both(ctx, oracle, csg, csg.AIR_MERKLE_INIT, trace, pub, blowup=blowup)
+        assert_same_proof(got, want)
+        assert oracle.verify(oracle.AIR_MERKLE_INIT, pub, got) == 0
+
+
+@pytest.mark.parametrize("num_tx", [1, 2, 16])
+def test_merkle_update_proof_identical_to_oracle(ctx, oracle, csg, num_tx):
+    batch = csg.TransactionBatch(seed=3, num_tx=num_tx)
+    trace, pub = batch.merkle_update_trace()
+    got, want = prove_both(ctx, oracle, csg, csg.AIR_MERKLE_UPDATE, trace, pub, blowup=8)
+    assert_same_proof(got, want)
+    assert oracle.verify(oracle.AIR_MERKLE_UPDATE, pub, got) == 0
+
+
+@pytest.mark.parametrize("num_sig", [1, 2, 8])
+def test_schnorr_proof_identical_to_oracle(ctx, oracle, csg, num_sig):
+    batch = csg.SignatureBatch(seed=5, num_sig=num_sig)
+    trace, pub = batch.schnorr_trace()
+    got, want = prove_both(ctx, oracle, csg, csg.AIR_SCHNORR, trace, pub, blowup=8)
+    assert_same_proof(got, want)
+    assert oracle.verify(oracle.AIR_SCHNORR, pub, got) == 0
+
+
+@pytest.mark.parametrize("num_tx,hash_fn", [(1, 2), (4, 2), (2, 3), (16, 2)])
+def test_transaction_proof_identical_to_oracle(ctx, oracle, csg, num_tx, hash_fn):
+    # config 1: the state-transition example at its smallest batches, default options (src/lib.rs:78-86)
+    batch = csg.TransactionBatch(seed=1, num_tx=num_tx)
+    trace, pub = batch.transaction_trace()
+    got, want = prove_both(ctx, oracle, csg, csg.AIR_TRANSACTION, trace, pub, blowup=8, hash_fn=hash_fn)
+    assert_same_proof(got, want)
+    assert oracle.verify(oracle.AIR_TRANSACTION, pub, got) == 0
+    wrong = pub.copy()
+    wrong[8] = (int(wrong[8]) + 1) % P
+    assert oracle.verify(oracle.AIR_TRANSACTION, wrong, got) != 0      # src/tests.rs:32-37
+
+
+def test_reproving_a_resident_trace_gives_the_same_bytes(ctx, csg):
+    batch = csg.TransactionBatch(seed=9, num_tx=2)
+    trace, pub = batch.transaction_trace()
+    opt = csg.ProofOptions()
+    first = ctx.prove(csg.AIR_TRANSACTION, trace, pub, opt)
+    ctx.reload_resident_trace()
+    assert ctx.prove_loaded() == first
+    t = ctx.timings()
+    assert t["kernel_launches"] > 0 and t["total"] > 0
+
+
+def test_example_facade(csg, oracle):
+    ex = csg.get_example(2, seed=4)
+    proof = ex.prove()
+    assert oracle.verify(oracle.AIR_TRANSACTION, ex.pub_inputs, proof) == 0
+
+
+def test_errors_are_reported_not_swallowed(ctx, csg):
+    trace, pub = csg.build_range_trace(5)
+    with pytest.raises(csg.CsgError):
+        ctx.prove(csg.AIR_RANGE, trace, pub, csg.ProofOptions(fri_folding_factor=8))
+    with pytest.raises(csg.CsgError):
+        ctx.prove(csg.AIR_RANGE, trace, pub[:0], csg.ProofOptions())
+    with pytest.raises(csg.CsgError):   # blowup below the AIR's constraint-evaluation blowup
+        batch = csg.TransactionBatch(seed=1, num_tx=1)
+        t, p = batch.transaction_trace()
+        ctx.prove(csg.AIR_TRANSACTION, t, p, csg.ProofOptions(blowup_factor=4))
