@@ -1,0 +1,253 @@
+#!/usr/bin/env python3
+"""bench.py -- proving throughput of the state-transition AIR (BASELINE.json: "prove ms & tx/s, state-transition AIR").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--num-tx T] [--impl reference]
+
+A "step" is one complete proof (Prover::prove, /root/reference/src/lib.rs:140) of one synthetic batch of T transactions
+(default 1024: trace 2^20 rows x 94 columns, blowup 8 -> 2^23 LDE rows; BASELINE.json configs[3]).  With N > 1 (launched
+by torchrun, one rank per GPU) every rank proves its own batch: the path shards by independent proofs, there is no
+data-path collective, scaling is weak.
+
+  value     tx/s with the trace already resident in HBM when the timed region starts (device-event time, max over ranks)
+  e2e       the same through csg_prove() with the trace in pinned HOST memory: H2D copy and proof D2H inside the region
+  roofline  the dominant kernel (constraint evaluation), algorithmic bytes / its CUDA-event time, against the measured HBM peak
+  cpu_baseline  the CPU oracle (a port: the Rust reference cannot be built here) on a bounded sample, N=1 rank 0 only
+--impl reference times that CPU port alone, with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC, UNIT = "state_transition_prove_throughput", "tx/s"
+TRACE_WIDTH, ROWS_PER_TX, BLOWUP = 94, 1024, 8
+CONSTRAINT_BYTES_PER_ROW = 8 * TRACE_WIDTH + 8      # every LDE row read once, one combined value written
+MODMUL_PER_ROW = 5922                               # instrumented count of src/air.rs:383-610
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_port_run(num_tx, steps, warmup, seed=1):
+    """the CPU oracle's prover (OpenMP, all host threads) on num_tx transactions; returns mean seconds per proof"""
+    import certificate_stark_b200 as csg
+    from oracle import pyoracle as O
+    batch = csg.TransactionBatch(seed=seed, num_tx=num_tx)
+    trace, pub = batch.transaction_trace()
+    opt = O.options()
+    for _ in range(warmup):
+        O.prove(O.AIR_TRANSACTION, trace, pub, opt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.prove(O.AIR_TRANSACTION, trace, pub, opt)
+    return (time.perf_counter() - t0) / max(steps, 1)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference path's CPU implementation.  The reference is Rust over an un-vendored winterfell fork
+    and no Rust toolchain exists in this image, so what runs is the C/OpenMP port of that path (oracle/), on a bounded sample."""
+    if rank != 0:
+        return
+    sample_tx = min(args.num_tx, 64)
+    sec = cpu_port_run(sample_tx, args.steps, min(args.warmup, 1))
+    value = sample_tx / sec
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (f63 modular)",
+            "data": "synthetic", "config": workload_config(args.num_tx, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample_tx}-transaction batch (trace {sample_tx * ROWS_PER_TX} x 94, blowup 8) per step; C/OpenMP port of the path, the Rust reference cannot be built here"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(num_tx, world):
+    return {"workload": f"benches/state_transition.rs shape at {num_tx} transactions per proof: trace {num_tx * ROWS_PER_TX} x {TRACE_WIDTH}, blowup {BLOWUP}, "
+                        f"42 queries, Blake3_256, FRI folding 4 (BASELINE.json configs[3]); one proof per GPU per step",
+            "num_transactions": num_tx, "trace_rows": num_tx * ROWS_PER_TX, "lde_rows": num_tx * ROWS_PER_TX * BLOWUP, "proofs_per_step": world,
+            "l2_policy": f"inputs larger than L2: {num_tx * ROWS_PER_TX * TRACE_WIDTH * 8 / 2**20:.0f} MiB trace, {num_tx * ROWS_PER_TX * BLOWUP * TRACE_WIDTH * 8 / 2**30:.2f} GiB LDE"
+                         if num_tx >= 256 else "small batch: working set may fit L2",
+            "parallelism": f"independent proofs x{world}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--num-tx", type=int, default=1024)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up, no e2e leg, no CPU baseline (not a bench number)")
+    args = ap.parse_args()
+    rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import certificate_stark_b200 as csg
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA path is the product, there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    num_tx = args.num_tx
+    n = num_tx * ROWS_PER_TX
+    opt = csg.ProofOptions()
+    # synthetic batch (seeded per rank), witness built on the host straight into pinned memory
+    pinned = torch.empty((TRACE_WIDTH, n), dtype=torch.int64, pin_memory=True)
+    trace = pinned.numpy().view(np.uint64)
+    batch = csg.TransactionBatch(seed=1000 + rank, num_tx=num_tx)
+    _, pub = batch.transaction_trace(out=trace)
+    ctx = csg.Context(local_rank)
+    ctx.set_air(csg.AIR_TRANSACTION, n, pub, opt)
+
+    def prove_resident():
+        ctx.reload_resident_trace()
+        return ctx.prove_loaded()
+
+    def prove_e2e():
+        ctx.load_trace_ptr(pinned.data_ptr())
+        return ctx.prove_loaded()
+
+    ctx.load_trace_ptr(pinned.data_ptr())
+    proof = None
+    warmup = 1 if args.profile else max(args.warmup, 3)
+    for _ in range(warmup):
+        proof = prove_resident()
+
+    # ---- timed region 1: trace resident in HBM
+    stage_sum, launches = {}, 0
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ctx.timer_start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            p = prove_resident()
+            t = ctx.timings()
+            launches += int(t["kernel_launches"])
+            for k, v in t.items():
+                if k not in ("total", "kernel_launches"):
+                    stage_sum[k] = stage_sum.get(k, 0.0) + v
+            assert p == proof, "non-deterministic proof"
+        dev_ms = ctx.timer_stop()     # CUDA events on the proving stream around the K steps
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    clock_summary = clocks.summary()
+
+    # ---- timed region 2: end to end through the C ABI with host buffers
+    e2e_ms, e2e_h2d_ms = 0.0, 0.0
+    if not args.profile:
+        prove_e2e()
+        barrier()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            p = prove_e2e()
+            e2e_h2d_ms += ctx.timings()["h2d"]
+        e2e_ms = ctx.timer_stop()
+        barrier()
+
+    times = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, e2e_ms = [float(x) for x in times.cpu()]
+
+    if rank == 0:
+        steps = max(args.steps, 1)
+        ms_per_step = dev_ms / steps
+        value = world * num_tx / (ms_per_step / 1e3)
+        hbm_peak, peak_src, sm_max = measured_peaks()
+        cons_ms = stage_sum.get("constraints", 0.0) / steps
+        rows = n * BLOWUP
+        alg_bytes = rows * CONSTRAINT_BYTES_PER_ROW
+        achieved = alg_bytes / (cons_ms / 1e3) / 1e9 if cons_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (f63 modular)",
+            "data": "synthetic", "config": workload_config(num_tx, world),
+            "proofs_per_s": world / (ms_per_step / 1e3), "wall_ms_per_step": wall_ms / steps, "proof_bytes": len(proof),
+            "stage_ms": {k: v / steps for k, v in stage_sum.items()},
+            "e2e": {"value": (world * num_tx / (e2e_ms / steps / 1e3)) if e2e_ms else None, "unit": UNIT, "ms_per_step": e2e_ms / steps,
+                    "h2d_ms_per_step": e2e_h2d_ms / steps, "h2d_bytes_per_step": int(TRACE_WIDTH * n * 8), "d2h_bytes_per_step": int(len(proof))},
+            "gpu_launches": launches,
+            "clocks": clock_summary,
+            "roofline": {"kernel": "cons_kernel<TRANSACTION> (constraint evaluation + merge, 1 launch per proof)", "bound": "hbm",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+                         "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": cons_ms,
+                         "int_pipe": {"modmul_per_s": rows * MODMUL_PER_ROW / (cons_ms / 1e3) if cons_ms > 0 else None,
+                                      "note": "64-bit modular multiply has no native instruction; this kernel is integer-pipe-bound, not HBM-bound (DESIGN.md)"}},
+        }
+        if world == 1 and not args.no_cpu_baseline and not args.profile:
+            sample_tx = min(num_tx, 64)
+            sec = cpu_port_run(sample_tx, 1, 0)
+            line["cpu_baseline"] = {"value": sample_tx / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": f"one proof of a {sample_tx}-transaction batch (trace {sample_tx * ROWS_PER_TX} x 94, blowup 8): {sec:.2f} s; "
+                                              "C/OpenMP port of the path (oracle/), the Rust reference cannot be built here"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

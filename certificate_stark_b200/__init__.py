@@ -16,7 +16,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
-LIB_PATH = ROOT / "lib" / "libcsg.so"
+LIB_PATH = Path(os.environ.get("CSG_LIB", ROOT / "lib" / "libcsg.so"))
 P = 0x4180000000000001  # f63 modulus (/root/reference/src/range/tests.rs:59)
 
 AIR_TRANSACTION, AIR_MERKLE_UPDATE, AIR_MERKLE_INIT, AIR_SCHNORR, AIR_RANGE, AIR_RESCUE = range(6)
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
         "csg_open_composition": (C.c_int, [vp, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
         "csg_open_fri_layer": (C.c_int, [vp, C.c_size_t, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
         "csg_get_timings": (C.c_int, [vp, C.POINTER(Timings)]),
+        "csg_timer_start": (C.c_int, [vp]), "csg_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "csg_tx_batch_new": (vp, [C.c_uint64, C.c_size_t, C.c_uint]), "csg_tx_batch_free": (None, [vp]), "csg_tx_batch_size": (C.c_size_t, [vp]),
         "csg_tx_batch_roots": (None, [vp, _u64p, _u64p]),
         "csg_build_trace_transaction": (C.c_int, [vp, _u64p, _u64p]), "csg_build_trace_merkle_update": (C.c_int, [vp, _u64p, _u64p]),
@@ -174,6 +175,16 @@ class Context:
         out, n = _u8p(), C.c_size_t()
         self._check(lib().csg_prove_loaded(self._h, C.byref(out), C.byref(n)))
         return self._take_proof(out, n)
+
+    def timer_start(self):
+        """CUDA event on the proving stream"""
+        self._check(lib().csg_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        """milliseconds of device time since timer_start (CUDA events on the proving stream)"""
+        ms = C.c_float()
+        self._check(lib().csg_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def timings(self) -> dict:
         t = Timings()

@@ -54,6 +54,17 @@ void launch(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe
 }
 }  // namespace
 
+#if defined(CSG_REDC_CHECK)
+unsigned long long redc_violations() {
+    unsigned long long v = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&v, f63::csg_redc_violations, sizeof v);
+    return v;
+}
+#else
+unsigned long long redc_violations() { return 0; }
+#endif
+
 void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab,
                       const fe *apoly, fe *out, Stream &st) {
     switch (air_id) {

@@ -52,4 +52,6 @@ struct ConsArgs {
 void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &args_host, const fe *lde, const fe *W, const fe *ptab,
                       const fe *apoly, fe *out, Stream &st);
 
+unsigned long long redc_violations();   // debug builds (-DCSG_REDC_CHECK): reductions entered with an out-of-range operand
+
 }  // namespace csg

@@ -33,6 +33,9 @@ constexpr uint64_t TWO_ADIC_ROOT = 0x0141727b75b35c50ULL;  // 3^131 mod p, canon
 constexpr fe ZERO = 0, ONE = R;
 
 struct u128 { uint64_t lo, hi; };
+#if defined(CSG_REDC_CHECK) && defined(__CUDACC__)
+static __device__ unsigned long long csg_redc_violations = 0;
+#endif
 
 CSG_HD u128 mul_wide(uint64_t a, uint64_t b) {
 #if defined(__CUDA_ARCH__)
@@ -44,22 +47,60 @@ CSG_HD u128 mul_wide(uint64_t a, uint64_t b) {
 }
 
 // Montgomery reduction of t = hi * 2^64 + lo, t < p * 2^64.  Returns t * 2^-64 mod p in [0, p).
+// p = P_HI * 2^32 + 1, so -p^-1 mod 2^32 = 2^32 - 1 and a 32-bit reduction step is:  m = -t0 (mod 2^32);
+// t <- (t + m*p) / 2^32 = (t >> 32) + (t0 != 0) + m * P_HI.  Two steps take the 128-bit product down to < 2p with
+// two 32x32->64 multiply-adds (IMAD.WIDE.U32 on the device) and a handful of adds: no 64-bit multiplications at all.
+constexpr uint64_t P_HI = P >> 32;   // 0x41800000
+CSG_HD fe redc_reference(uint64_t lo, uint64_t hi);
 CSG_HD fe redc(uint64_t lo, uint64_t hi) {
-    // m = lo * (p - 2) mod 2^64 = ((lo * 131) << 55) - lo        (p - 2 = 131 * 2^55 - 1)
-    // (t + m * p) / 2^64 = hi + floor(m * p / 2^64) + (lo != 0)  with  m * p = m + ((m * 131) << 55)
-    uint64_t m = ((lo * 131ULL) << 55) - lo;
-    // floor(m * p / 2^64): m*131 is a 72-bit number (h8 : l64); (m*131) << 55 contributes (m*131) >> 9 to the high
-    // word, and its low word ((m*131) & 511) << 55 can carry once when added to m.
-#if defined(__CUDA_ARCH__)
-    uint64_t l64 = m * 131ULL, h8 = __umul64hi(m, 131ULL);
-#else
-    unsigned __int128 w = (unsigned __int128)m * 131ULL;
-    uint64_t l64 = (uint64_t)w, h8 = (uint64_t)(w >> 64);
+#if defined(CSG_REDC_REFERENCE)
+    return redc_reference(lo, hi);
 #endif
-    uint64_t mp_hi = (l64 >> 9) | (h8 << 55);
-    uint64_t low = (l64 << 55);
-    uint64_t s = low + m;  // == -lo mod 2^64: the low words of t and m*p cancel
-    uint64_t u = hi + mp_hi + (s < low ? 1 : 0) + (lo != 0 ? 1 : 0);
+#if defined(CSG_REDC_CHECK) && defined(__CUDA_ARCH__)
+    if (hi >= P) atomicAdd(&csg_redc_violations, 1ULL);
+#endif
+#if defined(__CUDA_ARCH__)
+    // One asm block: the carry flag links the steps (t0 + m1 carries exactly when t0 != 0), and the sequence stays
+    // opaque to the optimiser -- the plain C++ below was observed to be mis-optimised inside one large kernel
+    // (tests/test_gpu_parity.py::test_schnorr_proof_identical_to_oracle caught it).
+    uint64_t u;
+    asm("{\n\t"
+        ".reg .u32 t0, l1, m, pl, ph, t1, r0, r1, h0, h1, d;\n\t"
+        ".reg .u64 mp;\n\t"
+        "mov.b64 {t0, l1}, %1;\n\t"
+        "mov.b64 {h0, h1}, %2;\n\t"
+        "sub.u32 m, 0, t0;\n\t"
+        "mul.wide.u32 mp, m, 0x41800000;\n\t"
+        "mov.b64 {pl, ph}, mp;\n\t"
+        "add.cc.u32 d, t0, m;\n\t"          // carry = (t0 != 0)
+        "addc.cc.u32 t1, l1, pl;\n\t"       // word 1 of t + m*p
+        "addc.cc.u32 r0, h0, ph;\n\t"       // rest = hi + (m*P_HI >> 32) + carry
+        "addc.u32 r1, h1, 0;\n\t"
+        "sub.u32 m, 0, t1;\n\t"
+        "mul.wide.u32 mp, m, 0x41800000;\n\t"
+        "mov.b64 {pl, ph}, mp;\n\t"
+        "add.cc.u32 d, t1, m;\n\t"          // carry = (t1 != 0)
+        "addc.cc.u32 r0, r0, pl;\n\t"
+        "addc.u32 r1, r1, ph;\n\t"
+        "mov.b64 %0, {r0, r1};\n\t"
+        "}"
+        : "=l"(u) : "l"(lo), "l"(hi));
+    return u >= P ? u - P : u;
+#else
+    const uint32_t t0 = (uint32_t)lo, m1 = 0u - t0;
+    const uint64_t mp1 = (uint64_t)m1 * P_HI;                                   // < 2^63
+    const uint64_t s = (lo >> 32) + (uint64_t)(uint32_t)mp1 + (t0 != 0 ? 1 : 0);   // word 1 of t + m1*p, with its carry
+    const uint32_t t1 = (uint32_t)s, m2 = 0u - t1;
+    const uint64_t rest = hi + (mp1 >> 32) + (s >> 32);                         // (t + m1*p) >> 64, at most p
+    const uint64_t u = (uint64_t)m2 * P_HI + rest + (t1 != 0 ? 1 : 0);           // < 2p
+    return u >= P ? u - P : u;
+#endif
+}
+// the same value computed the long way (one 64-bit Montgomery step with -p^-1 = p - 2); kept for the unit tests
+CSG_HD fe redc_reference(uint64_t lo, uint64_t hi) {
+    uint64_t m = lo * NPRIME;
+    u128 mp = mul_wide(m, P);
+    uint64_t u = hi + mp.hi + (lo != 0 ? 1 : 0);
     return u >= P ? u - P : u;
 }
 

@@ -39,15 +39,16 @@ struct FriLayer {
 
 enum Stage { S_NONE, S_AIR, S_TRACE, S_COMMITTED, S_EVALUATED, S_COMPOSED, S_OOD, S_DEEP };
 
-class Timer {   // device time of a stage, CUDA events on the proving stream
+class Timer {   // device time of a stage, CUDA events on the proving stream; the events live as long as the context
   public:
-    explicit Timer(Stream &st) : st_(st) { CSG_CUDA(cudaEventCreate(&a_)); CSG_CUDA(cudaEventCreate(&b_)); }
-    ~Timer() { cudaEventDestroy(a_); cudaEventDestroy(b_); }
-    void start() { CSG_CUDA(cudaEventRecord(a_, st_.s)); }
-    float stop() { CSG_CUDA(cudaEventRecord(b_, st_.s)); CSG_CUDA(cudaEventSynchronize(b_)); float ms = 0; CSG_CUDA(cudaEventElapsedTime(&ms, a_, b_)); return ms; }
+    ~Timer() { if (a_) { cudaEventDestroy(a_); cudaEventDestroy(b_); } }
+    void start(Stream &st) {
+        if (!a_) { CSG_CUDA(cudaEventCreate(&a_)); CSG_CUDA(cudaEventCreate(&b_)); }
+        CSG_CUDA(cudaEventRecord(a_, st.s));
+    }
+    float stop(Stream &st) { CSG_CUDA(cudaEventRecord(b_, st.s)); CSG_CUDA(cudaEventSynchronize(b_)); float ms = 0; CSG_CUDA(cudaEventElapsedTime(&ms, a_, b_)); return ms; }
   private:
-    Stream &st_;
-    cudaEvent_t a_, b_;
+    cudaEvent_t a_ = nullptr, b_ = nullptr;
 };
 
 }  // namespace
@@ -78,11 +79,15 @@ struct csg_ctx {
     DBuf<uint32_t> d_tnodes, d_cnodes;
     DBuf<ConsArgs> d_cargs;
     std::unique_ptr<ConsArgs> h_cargs;
-    std::vector<std::unique_ptr<FriLayer>> fri;
+    std::vector<std::unique_ptr<FriLayer>> fri;   // pool: buffers survive from proof to proof; nfri layers are live
+    size_t nfri = 0;
+    DBuf<uint64_t> d_rows;
+    Timer stage_timer, query_timer;
 
     fe z = 0;
     std::vector<fe> ood_cur, ood_next, ood_comp;
     csg_timings tm{};
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // csg_timer_start / csg_timer_stop
 
     // ------------------------------------------------------------------------------------------ setup
     void set_air(int air_id, size_t trace_len, const csg_options *o, const uint64_t *pub, size_t npub) {
@@ -112,7 +117,7 @@ struct csg_ctx {
         ce_shift.resize(ce);
         for (size_t kc = 0; kc < ce; kc++) ce_shift[kc] = lde_shift[kc * (b / ce)];
         build_periodic_tables();
-        fri.clear();
+        nfri = 0;
         stage = S_AIR;
     }
 
@@ -157,13 +162,13 @@ struct csg_ctx {
     void load_trace(const uint64_t *trace) {
         need(S_AIR, "csg_set_air must be called first");
         const size_t count = (size_t)air.width * n;
-        Timer t(st);
-        t.start();
+        Timer &t = stage_timer;
+        t.start(st);
         d_io.reserve(count); d_polys.reserve(count);
         CSG_CUDA(cudaMemcpyAsync(d_io.p, trace, count * sizeof(uint64_t), cudaMemcpyHostToDevice, st.s));
         to_montgomery(d_io.p, d_polys.p, count, st);   // d_polys holds the trace until it is interpolated in place of it
-        tm.h2d = t.stop();
-        fri.clear();
+        tm.h2d = t.stop(st);
+        nfri = 0;
         stage = S_TRACE;
     }
     // for benchmarking with inputs already resident: the trace as left on the device by the last load_trace
@@ -171,7 +176,7 @@ struct csg_ctx {
         need(S_TRACE, "no trace has been loaded");
         const size_t count = (size_t)air.width * n;
         to_montgomery(d_io.p, d_polys.p, count, st);
-        fri.clear();
+        nfri = 0;
         stage = S_TRACE;
         tm.h2d = 0;
     }
@@ -186,28 +191,28 @@ struct csg_ctx {
     void extend_and_commit_trace(uint8_t root[32]) {
         need(S_TRACE, "csg_load_trace must be called first");
         const size_t w = air.width;
-        Timer t(st);
-        t.start();
+        Timer &t = stage_timer;
+        t.start(st);
         scratch.reserve(w * n);
         intt_columns(roots, ntt, d_polys.p, n, scratch.p, n, w, logn, st);
         std::swap(d_polys.p, scratch.p); std::swap(d_polys.n, scratch.n);   // d_polys = coefficients
         d_lde.reserve(w * lde_n);
         coset_ntt_columns(roots, ntt, d_polys.p, n, d_lde.p, n, w * n, w, logn, lde_shift.data(), b, st);
-        tm.lde = t.stop();
-        t.start();
+        tm.lde = t.stop(st);
+        t.start(st);
         d_tnodes.reserve(16 * lde_n);
         hash_rows(d_lde.p, (unsigned)w, n, (unsigned)b, w * n, n, (int)opt.hash_fn, d_tnodes.p + 8 * lde_n, st);
         merkle_build(d_tnodes.p, lde_n, (int)opt.hash_fn, st);
         download_root(d_tnodes, root);
-        tm.commit_trace = t.stop();
+        tm.commit_trace = t.stop(st);
         stage = S_COMMITTED;
     }
 
     // ------------------------------------------------------------------------------------------ stage 3
     void eval_constraints(const fe *t_ab, const fe *b_ab) {
         need(S_COMMITTED, "the trace must be committed first");
-        Timer t(st);
-        t.start();
+        Timer &t = stage_timer;
+        t.start(st);
         ConsArgs &A = *h_cargs;
         const fe g = root_of_unity(logn);
         A.logn = logn; A.ncosets = (unsigned)ce; A.col_stride = n; A.width = air.width;
@@ -250,7 +255,7 @@ struct csg_ctx {
         CSG_CUDA(cudaMemcpyAsync(d_cargs.p, &A, sizeof A, cudaMemcpyHostToDevice, st.s));
         d_comb.reserve(ce * n);
         csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_comb.p, st);
-        tm.constraints = t.stop();   // also keeps `polys` alive until the copy has completed
+        tm.constraints = t.stop(st);   // also keeps `polys` alive until the copy has completed
         stage = S_EVALUATED;
     }
     // coefficients of the polynomial taking the given values on <w_len> (host, tiny: one value per signature)
@@ -269,8 +274,8 @@ struct csg_ctx {
     // ------------------------------------------------------------------------------------------ stage 4
     void commit_composition(uint8_t root[32]) {
         need(S_EVALUATED, "constraints must be evaluated first");
-        Timer t(st);
-        t.start();
+        Timer &t = stage_timer;
+        t.start(st);
         // per-coset interpolants, divided by s_kc^m; then the cross-coset step yields the ce column polynomials
         std::vector<fe> sinv(ce);
         for (size_t kc = 0; kc < ce; kc++) sinv[kc] = inv(ce_shift[kc]);
@@ -288,15 +293,15 @@ struct csg_ctx {
         hash_rows(d_clde.p, (unsigned)ce, n, (unsigned)b, ce * n, n, (int)opt.hash_fn, d_cnodes.p + 8 * lde_n, st);
         merkle_build(d_cnodes.p, lde_n, (int)opt.hash_fn, st);
         download_root(d_cnodes, root);
-        tm.composition = t.stop();
+        tm.composition = t.stop(st);
         stage = S_COMPOSED;
     }
 
     // ------------------------------------------------------------------------------------------ stage 5 + 6
     void ood(fe z_) {
         need(S_COMPOSED, "the composition polynomial must be committed first");
-        Timer t(st);
-        t.start();
+        Timer &t = stage_timer;
+        t.start(st);
         z = z_;
         const size_t w = air.width;
         const fe pts[2] = {z, mul(z, root_of_unity(logn))};
@@ -307,13 +312,13 @@ struct csg_ctx {
         const fe zm = f63::pow(z, ce);
         ood_comp.resize(ce);
         eval_polys_at(d_cpolys.p, n, ce, n, &zm, 1, ood_comp.data(), scratch2, st);
-        tm.ood_deep = t.stop();
+        tm.ood_deep = t.stop(st);
         stage = S_OOD;
     }
     void deep(const fe *trace_ab, const fe *comp_d, fe lambda, fe mu) {
         need(S_OOD, "the out-of-domain frame must be computed first");
-        Timer t(st);
-        t.start();
+        Timer &t = stage_timer;
+        t.start(st);
         const size_t w = air.width;
         std::vector<fe> coef(2 * w);
         DeepArgs a{};
@@ -331,10 +336,10 @@ struct csg_ctx {
         combine_polys(d_cpolys.p, n, ce, n, comp_d, 1, d_abc.p + 2 * n, n, scratch, st);
         coset_ntt_columns(roots, ntt, d_abc.p, n, d_abc_lde.p, n, 3 * n, 3, logn, lde_shift.data(), b, st);
         deep_quotients(d_abc_lde.p, roots.W.p, n, a, d_deep.p, st);
-        fri.clear();
-        fri.emplace_back(new FriLayer());
-        fri.back()->evals = d_deep.p; fri.back()->m = lde_n;
-        tm.ood_deep += t.stop();   // also keeps coef alive until the copies have completed
+        if (fri.empty()) fri.emplace_back(new FriLayer());
+        nfri = 1;
+        fri[0]->evals = d_deep.p; fri[0]->m = lde_n; fri[0]->committed = false;
+        tm.ood_deep += t.stop(st);   // also keeps coef alive until the copies have completed
         tm.fri = 0;
         stage = S_DEEP;
     }
@@ -342,23 +347,23 @@ struct csg_ctx {
     // ------------------------------------------------------------------------------------------ stage 7
     void fri_commit_layer(uint8_t root[32]) {
         need(S_DEEP, "the DEEP composition must be computed first");
-        FriLayer &L = *fri.back();
-        Timer t(st);
-        t.start();
+        FriLayer &L = *fri[nfri - 1];
+        Timer &t = stage_timer;
+        t.start(st);
         const size_t q = L.m / 4;
         L.nodes.reserve(16 * q);
         hash_rows(L.evals, 4, q, 1, 0, q, (int)opt.hash_fn, L.nodes.p + 8 * q, st);
         merkle_build(L.nodes.p, q, (int)opt.hash_fn, st);
         download_root(L.nodes, root);
         L.committed = true;
-        tm.fri += t.stop();
+        tm.fri += t.stop(st);
     }
     void fri_fold(fe alpha) {
         need(S_DEEP, "the DEEP composition must be computed first");
-        FriLayer &L = *fri.back();
+        FriLayer &L = *fri[nfri - 1];
         if (!L.committed) throw StateError("the current FRI layer must be committed before it is folded");
-        Timer t(st);
-        t.start();
+        Timer &t = stage_timer;
+        t.start(st);
         const size_t m = L.m, q = m / 4;
         const unsigned logm = ilog2(m);
         FoldArgs a{};
@@ -370,12 +375,13 @@ struct csg_ctx {
             if (logm - roots.logn > 5) throw StateError("FRI layer too large for the root table");
             for (unsigned i = 0; i < (1u << (logm - roots.logn)); i++) a.small[i] = f63::pow(w_inv, i);
         }
-        std::unique_ptr<FriLayer> N(new FriLayer());
-        N->owned.reserve(q);
-        csg::fri_fold4(L.evals, m, roots.W.p, a, N->owned.p, st);
-        N->evals = N->owned.p; N->m = q;
-        fri.push_back(std::move(N));
-        tm.fri += t.stop();
+        if (fri.size() == nfri) fri.emplace_back(new FriLayer());
+        FriLayer &N = *fri[nfri];
+        N.owned.reserve(q);
+        csg::fri_fold4(L.evals, m, roots.W.p, a, N.owned.p, st);
+        N.evals = N.owned.p; N.m = q; N.committed = false;
+        nfri++;
+        tm.fri += t.stop(st);
     }
     size_t num_fri_folds() const { size_t r = 0, d = lde_n; while (d > opt.fri_max_remainder_size) { d /= 4; r++; } return r; }
 
@@ -391,10 +397,9 @@ struct csg_ctx {
         upload_positions(pos);
         std::vector<uint64_t> rows(pos.size() * width);
         // d_io still holds the resident trace for re-proving; rows go through a separate small buffer
-        DBuf<uint64_t> out;
-        out.reserve(rows.size());
-        gather_rows(data, width, ncosets, coset_stride, col_stride, d_idx.p, pos.size(), out.p, st);
-        CSG_CUDA(cudaMemcpyAsync(rows.data(), out.p, rows.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st.s));
+        d_rows.reserve(std::max<size_t>(rows.size(), 1 << 16));
+        gather_rows(data, width, ncosets, coset_stride, col_stride, d_idx.p, pos.size(), d_rows.p, st);
+        CSG_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, rows.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st.s));
         CSG_CUDA(cudaStreamSynchronize(st.s));
         return rows;
     }
@@ -478,8 +483,8 @@ struct csg_ctx {
             if (l + 1 < nlayers) fri_fold(alpha);
         }
 
-        Timer tq(st);
-        tq.start();
+        Timer &tq = query_timer;
+        tq.start(st);
         uint64_t nonce = 1;
         while (coin.check_leading_zeros(nonce) < opt.grinding_factor) nonce++;
         coin.reseed_with_int(nonce);
@@ -525,17 +530,16 @@ struct csg_ctx {
             }
             const FriLayer &last = *fri[nlayers - 1];
             std::vector<uint64_t> rem(last.m);
-            DBuf<uint64_t> tmp;
-            tmp.reserve(last.m);
-            from_montgomery(last.evals, tmp.p, last.m, st);
-            CSG_CUDA(cudaMemcpyAsync(rem.data(), tmp.p, last.m * 8, cudaMemcpyDeviceToHost, st.s));
+            d_rows.reserve(std::max<size_t>(last.m, 1 << 16));
+            from_montgomery(last.evals, d_rows.p, last.m, st);
+            CSG_CUDA(cudaMemcpyAsync(rem.data(), d_rows.p, last.m * 8, cudaMemcpyDeviceToHost, st.s));
             CSG_CUDA(cudaStreamSynchronize(st.s));
             pf.u16((uint16_t)(last.m * 8));
             for (uint64_t v : rem) pf.u64(v);
             pf.u8(1);
         }
         pf.u64(nonce);
-        tm.queries = tq.stop();
+        tm.queries = tq.stop(st);
         tm.kernel_launches = st.launches - launches0;
         tm.total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
@@ -580,6 +584,7 @@ void csg_destroy(csg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st.s);
     cudaStream_t s = ctx->st.s;
+    if (ctx->ev_a) { cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); }
     delete ctx;
     cudaStreamDestroy(s);
 }
@@ -632,7 +637,7 @@ int csg_fri_fold(csg_ctx *ctx, uint64_t alpha) { return guarded(ctx, [&] { ctx->
 int csg_fri_remainder(csg_ctx *ctx, uint64_t *out, size_t cap, size_t *len) {
     return guarded(ctx, [&] {
         ctx->need(S_DEEP, "the DEEP composition must be computed first");
-        const FriLayer &L = *ctx->fri.back();
+        const FriLayer &L = *ctx->fri[ctx->nfri - 1];
         if (cap < L.m) throw ArgError("remainder buffer too small");
         DBuf<uint64_t> tmp;
         tmp.reserve(L.m);
@@ -666,10 +671,45 @@ int csg_open_composition(csg_ctx *ctx, const uint64_t *positions, size_t npos, u
 int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
     return guarded(ctx, [&] {
         ctx->need(S_DEEP, "the DEEP composition must be computed first");
-        if (layer >= ctx->fri.size() || !ctx->fri[layer]->committed) throw ArgError("no such committed FRI layer");
+        if (layer >= ctx->nfri || !ctx->fri[layer]->committed) throw ArgError("no such committed FRI layer");
         std::vector<size_t> pos(positions, positions + npos);
         const FriLayer &L = *ctx->fri[layer];
         copy_opening(ctx->open_rows(L.evals, 4, 1, 0, L.m / 4, pos), ctx->open_paths(L.nodes, L.m / 4, pos), rows, paths, cap, paths_len);
+    });
+}
+// debugging aid: number of elements >= p in an internal device buffer (0 = trace polys, 1 = LDE, 2 = periodic tables,
+// 3 = merged constraint column, 4 = composition columns, 5 = composition LDE)
+long long csg_debug_redc_violations(csg_ctx *) { return (long long)redc_violations(); }
+long long csg_debug_redc_selftest(csg_ctx *ctx) {
+    long long bad = -1;
+    guarded(ctx, [&] { bad = redc_selftest(ctx->st); });
+    return bad;
+}
+long long csg_debug_count_unreduced(csg_ctx *ctx, int which) {
+    long long bad = -1;
+    guarded(ctx, [&] {
+        const DBuf<fe> *b = which == 0 ? &ctx->d_polys : which == 1 ? &ctx->d_lde : which == 2 ? &ctx->d_ptab : which == 3 ? &ctx->d_comb : which == 4 ? &ctx->d_cpolys : &ctx->d_clde;
+        size_t count = which == 0 ? ctx->air.width * ctx->n : which == 1 ? ctx->air.width * ctx->lde_n : which == 2 ? ctx->h_cargs->ptab_coset_stride * ctx->ce
+                       : which == 3 ? ctx->ce * ctx->n : which == 4 ? ctx->ce * ctx->n : ctx->ce * ctx->lde_n;
+        std::vector<fe> h(count);
+        CSG_CUDA(cudaMemcpy(h.data(), b->p, count * sizeof(fe), cudaMemcpyDeviceToHost));
+        bad = 0;
+        for (fe v : h) bad += v >= P;
+    });
+    return bad;
+}
+int csg_timer_start(csg_ctx *ctx) {
+    return guarded(ctx, [&] {
+        if (!ctx->ev_a) { CSG_CUDA(cudaEventCreate(&ctx->ev_a)); CSG_CUDA(cudaEventCreate(&ctx->ev_b)); }
+        CSG_CUDA(cudaEventRecord(ctx->ev_a, ctx->st.s));
+    });
+}
+int csg_timer_stop(csg_ctx *ctx, float *ms) {
+    return guarded(ctx, [&] {
+        if (!ctx->ev_a || !ms) throw StateError("csg_timer_start must be called first");
+        CSG_CUDA(cudaEventRecord(ctx->ev_b, ctx->st.s));
+        CSG_CUDA(cudaEventSynchronize(ctx->ev_b));
+        CSG_CUDA(cudaEventElapsedTime(ms, ctx->ev_a, ctx->ev_b));
     });
 }
 int csg_get_timings(const csg_ctx *ctx, csg_timings *out) { if (!ctx || !out) return CSG_ERR_ARG; *out = ctx->tm; return CSG_OK; }
@@ -768,23 +808,23 @@ int csg_k_sweep(csg_ctx *ctx, size_t width, size_t n, size_t blowup, int hash_fn
         fa.alpha = to_mont(12345); fa.offset_inv = inv(to_mont(GENERATOR)); fa.zeta_inv = f63::pow(w_inv, lde_n / 4); fa.quarter = inv(to_mont(4));
         fa.logm = logm; fa.logW = logn;
         for (unsigned i = 0; i < (1u << (logm - logn)); i++) fa.small[i] = f63::pow(w_inv, i);
-        Timer t(st);
+        Timer t;
         float acc_ms[4] = {0, 0, 0, 0};
         for (int it = -1; it < iters; it++) {
             float ms[4];
-            t.start();
+            t.start(st);
             intt_columns(rt, sc, a.p, n, c.p, n, width, logn, st);
             coset_ntt_columns(rt, sc, c.p, n, e.p, n, width * n, width, logn, shifts.data(), blowup, st);
-            ms[0] = t.stop();
-            t.start();
+            ms[0] = t.stop(st);
+            t.start(st);
             hash_rows(e.p, (unsigned)width, n, (unsigned)blowup, width * n, n, hash_fn, nodes.p + 8 * lde_n, st);
-            ms[1] = t.stop();
-            t.start();
+            ms[1] = t.stop(st);
+            t.start(st);
             merkle_build(nodes.p, lde_n, hash_fn, st);
-            ms[2] = t.stop();
-            t.start();
+            ms[2] = t.stop(st);
+            t.start(st);
             csg::fri_fold4(e.p, lde_n, rt.W.p, fa, f.p, st);
-            ms[3] = t.stop();
+            ms[3] = t.stop(st);
             if (it >= 0) for (int k = 0; k < 4; k++) acc_ms[k] += ms[k];
         }
         for (int k = 0; k < 4; k++) ms_out[k] = acc_ms[k] / iters;

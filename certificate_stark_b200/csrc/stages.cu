@@ -131,7 +131,37 @@ __global__ void coset_to_natural_kernel(const fe *__restrict__ lde, unsigned wid
     out[c * n * ncosets + j] = from_mont(lde[(k * width + c) * n + i]);
 }
 
+__global__ void redc_selftest_kernel(unsigned long long *bad, unsigned long long seed) {
+    unsigned long long x = seed + (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 0x9e3779b97f4a7c15ULL;
+    unsigned long long nb = 0;
+    for (int it = 0; it < 4096; it++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        unsigned long long lo = x;
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        unsigned long long hi = x % P;
+        if (it & 1) { lo = (it & 2) ? 0 : (lo << 32); }
+        if ((it & 12) == 4) hi = P - 1 - (hi & 0xffff);
+        if ((it & 12) == 8) hi = hi & 0xffff;
+        if (redc(lo, hi) != redc_reference(lo, hi)) nb++;
+        fe a = lo % P, b = hi;
+        u128 t = mul_wide(a, b);
+        if (redc(t.lo, t.hi) != redc_reference(t.lo, t.hi)) nb++;
+    }
+    if (nb) atomicAdd(bad, nb);
+}
+
 }  // namespace
+
+long long redc_selftest(Stream &st) {
+    unsigned long long *d, h = 0;
+    CSG_CUDA(cudaMalloc((void **)&d, 8));
+    CSG_CUDA(cudaMemsetAsync(d, 0, 8, st.s));
+    CSG_LAUNCH(st, redc_selftest_kernel, 1024, 256, 0, d, 12345ULL);
+    CSG_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, st.s));
+    CSG_CUDA(cudaStreamSynchronize(st.s));
+    cudaFree(d);
+    return (long long)h;
+}
 
 void coset_major_to_natural(const fe *lde, unsigned width, unsigned ncosets, size_t n, uint64_t *out, Stream &st) {
     dim3 grid((unsigned)((n * ncosets + 255) / 256), width);

@@ -51,4 +51,8 @@ void from_montgomery(const fe *in, uint64_t *out, size_t count, Stream &st);
 // coset-major lde[(k*width + c)*n + i] -> canonical natural-order columns out[c*(n*ncosets) + k + ncosets*i]
 void coset_major_to_natural(const fe *lde, unsigned width, unsigned ncosets, size_t n, uint64_t *out, Stream &st);
 
+// arithmetic self-test on the device: number of (random and edge-case) inputs on which the fast Montgomery reduction
+// disagrees with the textbook one; must be 0
+long long redc_selftest(Stream &st);
+
 }  // namespace csg

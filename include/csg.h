@@ -94,6 +94,9 @@ typedef struct {
     uint64_t kernel_launches; /* kernels launched by the last proof */
 } csg_timings;
 int csg_get_timings(const csg_ctx *ctx, csg_timings *out);
+/* CUDA events on the proving stream around an arbitrary sequence of calls (bench.py's timed region) */
+int csg_timer_start(csg_ctx *ctx);
+int csg_timer_stop(csg_ctx *ctx, float *ms);
 
 /* ---- witness builders: build_trace() of each prover -------------------------------------------------------------
  * Traces are column-major canonical; `pub` receives get_pub_inputs(). */

@@ -188,3 +188,11 @@ def test_errors_are_reported_not_swallowed(ctx, csg):
         batch = csg.TransactionBatch(seed=1, num_tx=1)
         t, p = batch.transaction_trace()
         ctx.prove(csg.AIR_TRANSACTION, t, p, csg.ProofOptions(blowup_factor=4))
+
+
+def test_device_montgomery_reduction_selftest(ctx, csg):
+    # the 32-bit word-serial reduction used by every kernel against the textbook 64-bit one, on random and edge operands
+    import ctypes as C
+    L = csg.lib()
+    L.csg_debug_redc_selftest.restype, L.csg_debug_redc_selftest.argtypes = C.c_longlong, [C.c_void_p]
+    assert L.csg_debug_redc_selftest(ctx._h) == 0
