@@ -199,82 +199,105 @@ CSG_HD void scalar_mult_bank(const Frame &f, Comb &C, int o, const fe (&q)[12], 
         a.flush(C, addition);
     }
 }
-// everything of schnorr::evaluate_constraints except the Rescue round of the message hash.
-// PK(j): limb j of the signer's affine public key; IN(i): message element injected into the hash at this row.
-template <class PK, class IN>
-CSG_HD void schnorr_block(const Frame &f, Comb &C, fe doubling, fe addition, const fe (&digest)[4], PK pk, fe final_add, fe copy_hash, IN in) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int bank = 0; bank < 2; bank++) {
-        fe q[12];
-        const uint64_t *gen = CSG_TABLE(CSG_GENERATOR);
-        for (int j = 0; j < 12; j++) q[j] = bank == 0 ? gen[j] : pk(j);
-        scalar_mult_bank(f, C, bank * (PPW + 1), q, doubling, addition);
+// last step of a signature: S + h.P, x reduced to affine, and h must equal the hash output
+// (src/schnorr/air.rs:506-530, src/utils/ecc.rs:146-172)
+CSG_HD void schnorr_final_addition(const Frame &f, Comb &C, fe final_add) {
+    ecc::point s, hp;
+    for (int i = 0; i < 6; i++) {
+        s.x.c[i] = f.cur(i); s.y.c[i] = f.cur(6 + i); s.z.c[i] = f.cur(12 + i);
+        hp.x.c[i] = f.cur(PPW + 1 + i); hp.y.c[i] = f.cur(PPW + 7 + i); hp.z.c[i] = f.cur(PPW + 13 + i);
     }
+    ecc::point r = ecc::add_full(s, hp);
+    ecc::fp6 nx;
+    for (int i = 0; i < 6; i++) nx.c[i] = f.next(i);
+    ecc::fp6 xz = ecc::mul(nx, r.z);
+    FlagAcc a;
+    for (int i = 0; i < 6; i++) {
+        a.add(C, i, f63::sub(xz.c[i], r.x.c[i]));
+        a.add(C, 6 + i, f63::sub(f.next(6 + i), r.y.c[i]));
+        a.add(C, 12 + i, f63::sub(f.next(12 + i), r.z.c[i]));
+    }
+    for (int i = 0; i < 4; i++) a.add(C, LIMBS + 1 + i, f63::sub(f.cur(LIMBS + 1 + i), f.cur(SIG_HASH + i)));
+    a.flush(C, final_add);
+}
+// the light part of schnorr::evaluate_constraints: limb reconstruction of h and the hash copy/injection constraints.
+// IN(i): message element injected into the hash at this row.
+template <class IN>
+CSG_HD void schnorr_light(const Frame &f, Comb &C, fe doubling, fe addition, const fe (&digest)[4], fe copy_hash, IN in) {
     // the four limbs of h are rebuilt from its bits while its scalar multiplication runs (src/schnorr/air.rs:454-486)
     const fe hbit_next = f.next(LIMBS);
-    {
-        FlagAcc hold;
-        for (int i = 0; i < 4; i++) {
-            const int c = LIMBS + 4 - i;
-            fe cv = f.cur(c), nv = f.next(c);
-            C.add(c, f63::mul(f63::mul(digest[i], doubling), f63::sub(nv, f63::add(f63::dbl(cv), hbit_next))));
-            C.add(c, f63::mul(f63::mul(f_not(digest[i]), doubling), f63::sub(cv, nv)));
-            hold.add(C, LIMBS + 1 + i, f63::sub(f.cur(LIMBS + 1 + i), f.next(LIMBS + 1 + i)));
-        }
-        hold.flush(C, addition);
+    FlagAcc hold;
+    for (int i = 0; i < 4; i++) {
+        const int c = LIMBS + 4 - i;
+        fe cv = f.cur(c), nv = f.next(c);
+        C.add(c, f63::mul(f63::mul(digest[i], doubling), f63::sub(nv, f63::add(f63::dbl(cv), hbit_next))));
+        C.add(c, f63::mul(f63::mul(f_not(digest[i]), doubling), f63::sub(cv, nv)));
+        hold.add(C, LIMBS + 1 + i, f63::sub(f.cur(LIMBS + 1 + i), f.next(LIMBS + 1 + i)));
     }
+    hold.flush(C, addition);
     // enforce_hash_copy (src/schnorr/air.rs:309-330)
-    {
-        FlagAcc a;
-        for (int i = 0; i < HRW; i++) {
-            a.add(C, SIG_HASH + i, f63::sub(f.cur(SIG_HASH + i), f.next(SIG_HASH + i)));
-            a.add(C, SIG_HASH + HRW + i, f63::sub(f.next(SIG_HASH + HRW + i), in(i)));
-        }
-        a.flush(C, copy_hash);
+    FlagAcc a;
+    for (int i = 0; i < HRW; i++) {
+        a.add(C, SIG_HASH + i, f63::sub(f.cur(SIG_HASH + i), f.next(SIG_HASH + i)));
+        a.add(C, SIG_HASH + HRW + i, f63::sub(f.next(SIG_HASH + HRW + i), in(i)));
     }
-    // last step: S + h.P, x reduced to affine, and h must equal the hash output (src/schnorr/air.rs:506-530, ecc.rs:146-172)
-    {
-        ecc::point s, hp;
-        for (int i = 0; i < 6; i++) {
-            s.x.c[i] = f.cur(i); s.y.c[i] = f.cur(6 + i); s.z.c[i] = f.cur(12 + i);
-            hp.x.c[i] = f.cur(PPW + 1 + i); hp.y.c[i] = f.cur(PPW + 7 + i); hp.z.c[i] = f.cur(PPW + 13 + i);
-        }
-        ecc::point r = ecc::add_full(s, hp);
-        ecc::fp6 nx;
-        for (int i = 0; i < 6; i++) nx.c[i] = f.next(i);
-        ecc::fp6 xz = ecc::mul(nx, r.z);
-        FlagAcc a;
-        for (int i = 0; i < 6; i++) {
-            a.add(C, i, f63::sub(xz.c[i], r.x.c[i]));
-            a.add(C, 6 + i, f63::sub(f.next(6 + i), r.y.c[i]));
-            a.add(C, 12 + i, f63::sub(f.next(12 + i), r.z.c[i]));
-        }
-        for (int i = 0; i < 4; i++) a.add(C, LIMBS + 1 + i, f63::sub(f.cur(LIMBS + 1 + i), f.cur(SIG_HASH + i)));
-        a.flush(C, final_add);
-    }
+    a.flush(C, copy_hash);
 }
 
 // ================================================================================================ the six AIRs
+// Each AIR's evaluate_transition is split into independent work items whose partial sums add up to T(x) (T is linear in
+// the result slots): `heavy` items -- one Rescue residual, one scalar-multiplication bank, or the final point addition,
+// each a few thousand modular multiplications -- and a `rest` of cheap linear constraints.  The CUDA driver gives every
+// heavy item its own thread (small code, moderate registers, 5-8x more parallelism); eval_transition below runs them
+// back to back and is what the host-side tests compare with the reference semantics.
+template <int AIR> struct Items;
+template <> struct Items<TRANSACTION> { static constexpr int rescue = 5, ecc = 3; };
+template <> struct Items<MERKLE_UPDATE> { static constexpr int rescue = 4, ecc = 0; };
+template <> struct Items<MERKLE_INIT> { static constexpr int rescue = 4, ecc = 0; };
+template <> struct Items<SCHNORR> { static constexpr int rescue = 1, ecc = 3; };
+template <> struct Items<RANGE> { static constexpr int rescue = 0, ecc = 0; };
+template <> struct Items<RESCUE> { static constexpr int rescue = 1, ecc = 0; };
+
+// ---- Rescue residual number s of the AIR
+template <int AIR, class PV>
+CSG_HD void eval_rescue_item(int s, const Frame &f, const PV &pv, Comb &C) {
+    if (AIR == TRANSACTION) {
+        // the four leaf/path hash states serve both the leaf-hash phase (setup flag, slots 0,14,28,42:
+        // src/merkle/init/air.rs:171-201) and the authentication paths (hash flag, slots = columns); the fifth state is the
+        // Schnorr message hash
+        const int col0 = s < 4 ? 15 * s - (s >> 1) : SIG_HASH;
+        const bool path = s < 4;
+        rescue_state(f, pv, C, col0, TX_ARK, path ? pv(TX_SETUP) : pv(TX_SCHNORR_HASH), path ? 14 * s : SIG_HASH, path, path ? pv(TX_HASH) : 0, col0);
+    } else if (AIR == MERKLE_UPDATE) {
+        const int col0 = 15 * s - (s >> 1);
+        rescue_state(f, pv, C, col0, 5, pv(4), col0, false, 0, 0);
+    } else if (AIR == MERKLE_INIT) {
+        rescue_state(f, pv, C, 15 * s - (s >> 1), 0, f63::ONE, 14 * s, false, 0, 0);
+    } else if (AIR == SCHNORR) {
+        rescue_state(f, pv, C, SIG_HASH, APW + 15, pv(APW + 7), SIG_HASH, false, 0, 0);
+    } else if (AIR == RESCUE) {
+        rescue_state(f, pv, C, 0, 1, pv(0), 0, false, 0, 0);
+    }
+}
+// ---- curve item: 0 = S bank (generator), 1 = h.P bank (public key), 2 = final addition
+template <int AIR, class PV>
+CSG_HD void eval_ecc_item(int item, const Frame &f, const PV &pv, Comb &C) {
+    if (AIR != TRANSACTION && AIR != SCHNORR) return;
+    const fe mask = pv(AIR == TRANSACTION ? TX_SCHNORR : 0), scalar_mult = pv(AIR == TRANSACTION ? TX_SCALAR_MULT : 1);
+    if (item == 2) { schnorr_final_addition(f, C, f63::mul(f_not(scalar_mult), mask)); return; }
+    const fe doubling = pv(AIR == TRANSACTION ? TX_DOUBLING : 2), addition = f63::mul(f_not(doubling), scalar_mult);
+    fe q[12];
+    const uint64_t *gen = CSG_TABLE(CSG_GENERATOR);
+    for (int j = 0; j < 12; j++) q[j] = item == 0 ? gen[j] : (AIR == TRANSACTION ? f.next(SENDER_KEY + j) : pv(7 + j));
+    scalar_mult_bank(f, C, item * (PPW + 1), q, doubling, addition);
+}
+
 template <class PV>
-CSG_HD void eval_transaction(const Frame &f, const PV &pv, Comb &C) {
+CSG_HD void rest_transaction(const Frame &f, const PV &pv, Comb &C) {
     const fe setup = pv(TX_SETUP), tx_hash = pv(TX_MERKLE), hash_input = pv(TX_HASH_INPUT), finish = pv(TX_FINISH), hashf = pv(TX_HASH);
     const fe schnorr_mask = pv(TX_SCHNORR), scalar_mult = pv(TX_SCALAR_MULT), doubling = pv(TX_DOUBLING), schnorr_hash = pv(TX_SCHNORR_HASH);
     const fe copy_hash = f63::mul(f_not(schnorr_hash), schnorr_mask);
-    const fe final_add = f63::mul(f_not(scalar_mult), schnorr_mask);
     const fe addition = f63::mul(f_not(doubling), scalar_mult);
-
-    // the four leaf/path hash states serve both the leaf-hash phase (setup flag, slots 0,14,28,42: src/merkle/init/air.rs:171-201)
-    // and the authentication paths (hash flag, slots = columns); the fifth state is the Schnorr message hash
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int s = 0; s < 5; s++) {
-        const int col0 = s < 4 ? 15 * s - (s >> 1) : SIG_HASH;
-        if (s < 4) rescue_state(f, pv, C, col0, TX_ARK, setup, 14 * s, true, hashf, col0);
-        else rescue_state(f, pv, C, col0, TX_ARK, schnorr_hash, SIG_HASH, false, 0, 0);
-    }
     {   // setup row of a transaction: leaf consistency and copies into the carried registers (src/air.rs:405-504)
         FlagAcc a;
         value_block(f, C, a);
@@ -318,7 +341,7 @@ CSG_HD void eval_transaction(const Frame &f, const PV &pv, Comb &C) {
         return t.reduce();
     };
     const fe digest[4] = {pv(TX_DIGEST), pv(TX_DIGEST + 1), pv(TX_DIGEST + 2), pv(TX_DIGEST + 3)};
-    schnorr_block(f, C, doubling, addition, digest, [&](int j) { return f.next(SENDER_KEY + j); }, final_add, copy_hash, in);
+    schnorr_light(f, C, doubling, addition, digest, copy_hash, in);
 
     {   // range proofs of delta and sigma (src/air.rs:582-609); the sigma finish check compares the delta registers, as the reference does
         FlagAcc a;
@@ -336,72 +359,44 @@ CSG_HD void eval_transaction(const Frame &f, const PV &pv, Comb &C) {
     }
 }
 
-// MerkleAir: periodic = setup, tx_hash, hash_input, finish, hash, ark[28] (src/merkle/update/air.rs:73-156, 182-212)
-template <class PV>
-CSG_HD void eval_merkle_update(const Frame &f, const PV &pv, Comb &C) {
-    const fe setup = pv(0), tx_hash = pv(1), hash_input = pv(2), finish = pv(3), hashf = pv(4);
+// ---- everything that is not a heavy item
+template <int AIR, class PV>
+CSG_HD void eval_rest(const Frame &f, const PV &pv, Comb &C) {
+    if (AIR == TRANSACTION) rest_transaction(f, pv, C);
+    else if (AIR == MERKLE_UPDATE) {   // periodic = setup, tx_hash, hash_input, finish, hash, ark[28] (src/merkle/update/air.rs:73-156, 182-212)
+        FlagAcc a;
+        value_block(f, C, a);
+        a.flush(C, pv(0));
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int s = 0; s < 4; s++) {
-        const int col0 = 15 * s - (s >> 1);
-        rescue_state(f, pv, C, col0, 5, hashf, col0, false, 0, 0);
+        for (int path = 0; path < 2; path++) merkle_auth_path(f, C, path == 0 ? SENDER_INITIAL : RECEIVER_INITIAL, pv(1), pv(2), pv(4));
+        merkle_roots(f, C, pv(3));
+    } else if (AIR == SCHNORR) {       // periodic = global, scalar_mult, doubling, digest[4], pkey[12], hash flag, chunk[7], ark[28] (src/schnorr/air.rs:75-113)
+        const fe global = pv(0), scalar_mult = pv(1), doubling = pv(2), hash_flag = pv(APW + 7);
+        const fe digest[4] = {pv(3), pv(4), pv(5), pv(6)};
+        schnorr_light(f, C, doubling, f63::mul(f_not(doubling), scalar_mult), digest, f63::mul(f_not(hash_flag), global), [&](int i) { return pv(APW + 8 + i); });
+    } else if (AIR == RANGE) {         // src/range/air.rs:69-105: column 0 = bit, column 1 = accumulator
+        fe b = f.next(0);
+        C.add(1, f63::sub(f.next(1), f63::add(f63::dbl(f.cur(1)), b)));
+        C.add(0, f_bin(b));
+    } else if (AIR == RESCUE) {        // benches/rescue.rs:205-222: periodic = cycle mask, ark[28]
+        FlagAcc a;
+        for (int i = 0; i < HRW; i++) {
+            a.add(C, i, f63::sub(f.cur(i), f.next(i)));
+            a.add(C, HRW + i, f.next(HRW + i));
+        }
+        a.flush(C, f_not(pv(0)));
     }
-    FlagAcc a;
-    value_block(f, C, a);
-    a.flush(C, setup);
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int path = 0; path < 2; path++) merkle_auth_path(f, C, path == 0 ? SENDER_INITIAL : RECEIVER_INITIAL, tx_hash, hash_input, hashf);
-    merkle_roots(f, C, finish);
-}
-// PreMerkleAir: periodic = ark[28]; the flag is the constant one (src/merkle/init/air.rs:76-90)
-template <class PV>
-CSG_HD void eval_merkle_init(const Frame &f, const PV &pv, Comb &C) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int s = 0; s < 4; s++) rescue_state(f, pv, C, 15 * s - (s >> 1), 0, f63::ONE, 14 * s, false, 0, 0);
-}
-// SchnorrAir: periodic = global, scalar_mult, doubling, digest[4], pkey[12], hash flag, message chunk[7], ark[28] (src/schnorr/air.rs:75-113)
-template <class PV>
-CSG_HD void eval_schnorr(const Frame &f, const PV &pv, Comb &C) {
-    const fe global = pv(0), scalar_mult = pv(1), doubling = pv(2), hash_flag = pv(APW + 7);
-    const fe copy_hash = f63::mul(f_not(hash_flag), global), final_add = f63::mul(f_not(scalar_mult), global);
-    const fe addition = f63::mul(f_not(doubling), scalar_mult);
-    rescue_state(f, pv, C, SIG_HASH, APW + 15, hash_flag, SIG_HASH, false, 0, 0);
-    const fe digest[4] = {pv(3), pv(4), pv(5), pv(6)};
-    schnorr_block(f, C, doubling, addition, digest, [&](int j) { return pv(7 + j); }, final_add, copy_hash, [&](int i) { return pv(APW + 8 + i); });
-}
-// RangeProofAir (src/range/air.rs:69-105): column 0 = bit, column 1 = accumulator
-template <class PV>
-CSG_HD void eval_range(const Frame &f, const PV &, Comb &C) {
-    fe b = f.next(0);
-    C.add(1, f63::sub(f.next(1), f63::add(f63::dbl(f.cur(1)), b)));
-    C.add(0, f_bin(b));
-}
-// RescueAir of benches/rescue.rs:205-222: periodic = cycle mask, ark[28]
-template <class PV>
-CSG_HD void eval_rescue(const Frame &f, const PV &pv, Comb &C) {
-    const fe hash_flag = pv(0);
-    rescue_state(f, pv, C, 0, 1, hash_flag, 0, false, 0, 0);
-    FlagAcc a;
-    for (int i = 0; i < HRW; i++) {
-        a.add(C, i, f63::sub(f.cur(i), f.next(i)));
-        a.add(C, HRW + i, f.next(HRW + i));
-    }
-    a.flush(C, f_not(hash_flag));
+    // MERKLE_INIT (src/merkle/init/air.rs:76-90) is its four Rescue rounds only
 }
 
+// the whole of Air::evaluate_transition, merged: what one row contributes to T(x)
 template <int AIR, class PV>
 CSG_HD void eval_transition(const Frame &f, const PV &pv, Comb &C) {
-    if (AIR == TRANSACTION) eval_transaction(f, pv, C);
-    else if (AIR == MERKLE_UPDATE) eval_merkle_update(f, pv, C);
-    else if (AIR == MERKLE_INIT) eval_merkle_init(f, pv, C);
-    else if (AIR == SCHNORR) eval_schnorr(f, pv, C);
-    else if (AIR == RANGE) eval_range(f, pv, C);
-    else eval_rescue(f, pv, C);
+    for (int s = 0; s < Items<AIR>::rescue; s++) eval_rescue_item<AIR>(s, f, pv, C);
+    for (int e = 0; e < Items<AIR>::ecc; e++) eval_ecc_item<AIR>(e, f, pv, C);
+    eval_rest<AIR>(f, pv, C);
 }
 
 }  // namespace airs

@@ -75,7 +75,7 @@ struct csg_ctx {
 
     DBuf<uint64_t> d_io;
     DBuf<uint32_t> d_idx, d_dig;
-    DBuf<fe> d_polys, d_lde, d_comb, d_e, d_cpolys, d_clde, d_abc, d_abc_lde, d_deep, d_ptab, d_apoly;
+    DBuf<fe> d_parts, d_polys, d_lde, d_comb, d_e, d_cpolys, d_clde, d_abc, d_abc_lde, d_deep, d_ptab, d_apoly;
     DBuf<uint32_t> d_tnodes, d_cnodes;
     DBuf<ConsArgs> d_cargs;
     std::unique_ptr<ConsArgs> h_cargs;
@@ -254,7 +254,8 @@ struct csg_ctx {
         d_cargs.reserve(1);
         CSG_CUDA(cudaMemcpyAsync(d_cargs.p, &A, sizeof A, cudaMemcpyHostToDevice, st.s));
         d_comb.reserve(ce * n);
-        csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_comb.p, st);
+        d_parts.reserve(constraint_scratch_elements(air.id, n, ce));
+        csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st);
         tm.constraints = t.stop(st);   // also keeps `polys` alive until the copy has completed
         stage = S_EVALUATED;
     }
