@@ -43,7 +43,7 @@ class ProofOptions(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d", "lde", "commit_trace", "constraints", "composition", "ood_deep", "fri", "queries", "total")] + \
-               [("kernel_launches", C.c_uint64)]
+               [("kernel_launches", C.c_uint64)] + [(n, C.c_float) for n in ("cons_rescue", "cons_ecc_banks", "cons_ecc_final", "cons_rest")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -60,6 +60,17 @@ struct Periodic {
     CSG_HD fe operator()(int c) const { return tab[off[c] + (i & mask[c])]; }
 };
 
+// alpha[s] + beta[s] * xp[group[s]].  A real call on the device: it is used at several hundred unrolled sites and inlining
+// it there made the instruction footprint of the kernels exceed the instruction cache.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+fe slot_coefficient(const fe *alpha, const fe *beta, const uint8_t *group, const fe *xp, size_t xp_stride, int slot) {
+    return f63::add(alpha[slot], f63::mul(beta[slot], xp[group[slot] * xp_stride]));
+}
+
 // the random linear combination: coefficient of result slot s at this row is alpha[s] + beta[s] * xp[group[s]]
 struct Comb {
     const fe *alpha, *beta;
@@ -67,7 +78,7 @@ struct Comb {
     const fe *xp;        // x^adj per degree group, element g at xp[g * xp_stride]
     size_t xp_stride;
     f63::acc192 sum;
-    CSG_HD fe coef(int slot) const { return f63::add(alpha[slot], f63::mul(beta[slot], xp[group[slot] * xp_stride])); }
+    CSG_HD fe coef(int slot) const { return slot_coefficient(alpha, beta, group, xp, xp_stride, slot); }
     CSG_HD void add(int slot, fe v) { sum.mac(coef(slot), v); }
 };
 // contributions that share one flag: sum_k coef(slot_k) * v_k, multiplied by the flag once at the end
@@ -164,36 +175,36 @@ CSG_HD void value_block(const Frame &f, const Comb &C, FlagAcc &a) {
 // ---- curve part of schnorr::evaluate_constraints: one scalar multiplication register bank (point at column o, its
 // bit at o+18) against the affine point q (src/schnorr/air.rs:415-452, src/utils/ecc.rs:73-144)
 CSG_HD void scalar_mult_bank(const Frame &f, Comb &C, int o, const fe (&q)[12], fe doubling, fe addition) {
-    ecc::point p;
-    fe nx[18];
+    // operands are (re)loaded where they are used instead of being held across the two formulas: the curve arithmetic
+    // alone needs ~100 64-bit temporaries, and the loads hit L1
+    auto load_point = [&]() {
+        ecc::point p;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 6; i++) { p.x.c[i] = f.cur(o + i); p.y.c[i] = f.cur(o + 6 + i); p.z.c[i] = f.cur(o + 12 + i); }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < 18; i++) nx[i] = f.next(o + i);
-    const fe bit = f.cur(o + PPW), nbit = f_not(bit);
+        for (int i = 0; i < 6; i++) { p.x.c[i] = f.cur(o + i); p.y.c[i] = f.cur(o + 6 + i); p.z.c[i] = f.cur(o + 12 + i); }
+        return p;
+    };
+    const fe bit = f.cur(o + PPW);
     {
-        ecc::point d = ecc::double_point(p);
+        ecc::point d = ecc::double_point(load_point());
         FlagAcc a;
         for (int i = 0; i < 6; i++) {
-            a.add(C, o + i, f63::sub(nx[i], d.x.c[i]));
-            a.add(C, o + 6 + i, f63::sub(nx[6 + i], d.y.c[i]));
-            a.add(C, o + 12 + i, f63::sub(nx[12 + i], d.z.c[i]));
+            a.add(C, o + i, f63::sub(f.next(o + i), d.x.c[i]));
+            a.add(C, o + 6 + i, f63::sub(f.next(o + 6 + i), d.y.c[i]));
+            a.add(C, o + 12 + i, f63::sub(f.next(o + 12 + i), d.z.c[i]));
         }
         a.add(C, o + PPW, f_bin(bit));
         a.flush(C, doubling);
     }
     {
-        ecc::fp6 qx = ecc::load6(q), qy = ecc::load6(q + 6);
-        ecc::point m = ecc::add_mixed(p, qx, qy);
+        ecc::point m = ecc::add_mixed(load_point(), ecc::load6(q), ecc::load6(q + 6));
+        const fe nbit = f_not(bit);
         FlagAcc a;
         for (int i = 0; i < 6; i++) {
-            a.add(C, o + i, f63::sub(nx[i], f63::add(f63::mul(bit, m.x.c[i]), f63::mul(nbit, p.x.c[i]))));
-            a.add(C, o + 6 + i, f63::sub(nx[6 + i], f63::add(f63::mul(bit, m.y.c[i]), f63::mul(nbit, p.y.c[i]))));
-            a.add(C, o + 12 + i, f63::sub(nx[12 + i], f63::add(f63::mul(bit, m.z.c[i]), f63::mul(nbit, p.z.c[i]))));
+            a.add(C, o + i, f63::sub(f.next(o + i), f63::add(f63::mul(bit, m.x.c[i]), f63::mul(nbit, f.cur(o + i)))));
+            a.add(C, o + 6 + i, f63::sub(f.next(o + 6 + i), f63::add(f63::mul(bit, m.y.c[i]), f63::mul(nbit, f.cur(o + 6 + i)))));
+            a.add(C, o + 12 + i, f63::sub(f.next(o + 12 + i), f63::add(f63::mul(bit, m.z.c[i]), f63::mul(nbit, f.cur(o + 12 + i)))));
         }
         a.add(C, o + PPW, f63::sub(bit, f.next(o + PPW)));
         a.flush(C, addition);
@@ -279,17 +290,22 @@ CSG_HD void eval_rescue_item(int s, const Frame &f, const PV &pv, Comb &C) {
         rescue_state(f, pv, C, 0, 1, pv(0), 0, false, 0, 0);
     }
 }
-// ---- curve item: 0 = S bank (generator), 1 = h.P bank (public key), 2 = final addition
+// ---- curve items: bank 0 = S (generator), bank 1 = h.P (public key); then the final addition
 template <int AIR, class PV>
-CSG_HD void eval_ecc_item(int item, const Frame &f, const PV &pv, Comb &C) {
+CSG_HD void eval_ecc_bank(int bank, const Frame &f, const PV &pv, Comb &C) {
     if (AIR != TRANSACTION && AIR != SCHNORR) return;
-    const fe mask = pv(AIR == TRANSACTION ? TX_SCHNORR : 0), scalar_mult = pv(AIR == TRANSACTION ? TX_SCALAR_MULT : 1);
-    if (item == 2) { schnorr_final_addition(f, C, f63::mul(f_not(scalar_mult), mask)); return; }
+    const fe scalar_mult = pv(AIR == TRANSACTION ? TX_SCALAR_MULT : 1);
     const fe doubling = pv(AIR == TRANSACTION ? TX_DOUBLING : 2), addition = f63::mul(f_not(doubling), scalar_mult);
     fe q[12];
     const uint64_t *gen = CSG_TABLE(CSG_GENERATOR);
-    for (int j = 0; j < 12; j++) q[j] = item == 0 ? gen[j] : (AIR == TRANSACTION ? f.next(SENDER_KEY + j) : pv(7 + j));
-    scalar_mult_bank(f, C, item * (PPW + 1), q, doubling, addition);
+    for (int j = 0; j < 12; j++) q[j] = bank == 0 ? gen[j] : (AIR == TRANSACTION ? f.next(SENDER_KEY + j) : pv(7 + j));
+    scalar_mult_bank(f, C, bank * (PPW + 1), q, doubling, addition);
+}
+template <int AIR, class PV>
+CSG_HD void eval_ecc_final(const Frame &f, const PV &pv, Comb &C) {
+    if (AIR != TRANSACTION && AIR != SCHNORR) return;
+    const fe mask = pv(AIR == TRANSACTION ? TX_SCHNORR : 0), scalar_mult = pv(AIR == TRANSACTION ? TX_SCALAR_MULT : 1);
+    schnorr_final_addition(f, C, f63::mul(f_not(scalar_mult), mask));
 }
 
 template <class PV>
@@ -395,7 +411,7 @@ CSG_HD void eval_rest(const Frame &f, const PV &pv, Comb &C) {
 template <int AIR, class PV>
 CSG_HD void eval_transition(const Frame &f, const PV &pv, Comb &C) {
     for (int s = 0; s < Items<AIR>::rescue; s++) eval_rescue_item<AIR>(s, f, pv, C);
-    for (int e = 0; e < Items<AIR>::ecc; e++) eval_ecc_item<AIR>(e, f, pv, C);
+    if (Items<AIR>::ecc) { eval_ecc_bank<AIR>(0, f, pv, C); eval_ecc_bank<AIR>(1, f, pv, C); eval_ecc_final<AIR>(f, pv, C); }
     eval_rest<AIR>(f, pv, C);
 }
 

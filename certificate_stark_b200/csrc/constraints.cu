@@ -30,26 +30,59 @@ __device__ __forceinline__ RowCtx row_setup(const ConsArgs *__restrict__ A, cons
     return r;
 }
 
-// KIND 0: Rescue residual number blockIdx.z; KIND 1: curve item number blockIdx.z
+// Inverse evaluations of the boundary divisors, 1 / (x^steps_g - offset_g) for every row of every ce coset, by batch
+// inversion (Montgomery's trick): a thread inverts INV_CHUNK values with one field inversion and 3 multiplications each,
+// instead of one ~90-multiplication inversion per row and divisor in the row kernel.
+constexpr int INV_CHUNK = 16, INV_THREADS = 128;
+__global__ void __launch_bounds__(INV_THREADS) boundary_inverse_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ W, fe *__restrict__ binv) {
+    const unsigned kc = blockIdx.y, g = blockIdx.z;
+    const unsigned long long n = 1ULL << A->logn;
+    // element c of this thread: row i = block_base + c * INV_THREADS + tid (coalesced across the warp)
+    const unsigned long long base = blockIdx.x * (unsigned long long)(INV_CHUNK * INV_THREADS) + threadIdx.x;
+    const fe shift = A->b_steps[g] == 1 ? A->shift[kc] : A->b_shift_steps[kc][g], off = A->b_offset[g];
+    fe d[INV_CHUNK], pre[INV_CHUNK];
+    fe acc = ONE;
+#pragma unroll
+    for (int c = 0; c < INV_CHUNK; c++) {
+        const unsigned long long i = base + (unsigned long long)c * INV_THREADS;
+        d[c] = i < n ? sub(mul(shift, W[(A->b_steps[g] * i) & (n - 1)]), off) : ONE;
+        pre[c] = acc;
+        acc = mul(acc, d[c]);
+    }
+    fe ainv = inv(acc);
+    fe *out = binv + ((unsigned long long)g * A->ncosets + kc) * n;
+#pragma unroll
+    for (int c = INV_CHUNK - 1; c >= 0; c--) {
+        const unsigned long long i = base + (unsigned long long)c * INV_THREADS;
+        if (i < n) out[i] = mul(ainv, pre[c]);
+        ainv = mul(ainv, d[c]);
+    }
+}
+
+#ifndef CSG_ECC_MINBLOCKS
+#define CSG_ECC_MINBLOCKS 3
+#endif
+// KIND 0: Rescue residual number blockIdx.z; KIND 1: scalar-multiplication bank blockIdx.z; KIND 2: final point addition
 template <int AIR, int KIND>
-__global__ void __launch_bounds__(CONS_THREADS, KIND == 0 ? 4 : 3)
+__global__ void __launch_bounds__(CONS_THREADS, KIND == 0 ? 4 : CSG_ECC_MINBLOCKS)
 cons_item_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W, const fe *__restrict__ ptab,
                  fe *__restrict__ part) {
     __shared__ fe xp_s[airs::MAX_GROUPS][CONS_THREADS];   // x^adj of each degree group, one column per thread
-    const unsigned kc = blockIdx.y, item = blockIdx.z;
+    const unsigned kc = blockIdx.y, item = KIND == 2 ? 2 : blockIdx.z;
     const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
     if (i >= n) return;
     RowCtx r = row_setup(A, lde, W, ptab, kc, i, xp_s);
     airs::Comb C{A->alpha, A->beta, A->group, &xp_s[0][threadIdx.x], (size_t)CONS_THREADS, acc192()};
     if (KIND == 0) airs::eval_rescue_item<AIR>((int)item, r.f, r.pv, C);
-    else airs::eval_ecc_item<AIR>((int)item, r.f, r.pv, C);
+    else if (KIND == 1) airs::eval_ecc_bank<AIR>((int)item, r.f, r.pv, C);
+    else airs::eval_ecc_final<AIR>(r.f, r.pv, C);
     part[((unsigned long long)item * A->ncosets + kc) * n + i] = C.sum.reduce();
 }
 
 template <int AIR>
 __global__ void __launch_bounds__(CONS_THREADS, 4)
 cons_rest_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W, const fe *__restrict__ ptab,
-                 const fe *__restrict__ apoly, const fe *__restrict__ part, unsigned nparts, fe *__restrict__ out) {
+                 const fe *__restrict__ apoly, const fe *__restrict__ part, unsigned nparts, const fe *__restrict__ binv, fe *__restrict__ out) {
     __shared__ fe xp_s[airs::MAX_GROUPS][CONS_THREADS];
     const unsigned kc = blockIdx.y;
     const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
@@ -76,20 +109,35 @@ cons_rest_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, con
             }
             s.mac(add(A->a_alpha[a], mul(A->a_beta[a], xpb)), sub(r.f.cur(A->a_col[a]), v));
         }
-        const fe xs = A->b_steps[g] == 1 ? x : mul(A->b_shift_steps[kc][g], W[(A->b_steps[g] * i) & (n - 1)]);
-        res = add(res, mul(s.reduce(), inv(sub(xs, A->b_offset[g]))));
+        res = add(res, mul(s.reduce(), binv[((unsigned long long)g * A->ncosets + kc) * n + i]));
     }
     out[kc * n + i] = res;
 }
 
 template <int AIR>
-void launch(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab, const fe *apoly, fe *part, fe *out, Stream &st) {
+void launch(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab, const fe *apoly, fe *part, fe *out, Stream &st,
+            cudaEvent_t *ev) {
+    // scratch layout: [items partial sums][boundary-divisor inverses], each ncosets * n elements per entry
     const unsigned long long n = 1ULL << h.logn;
     const unsigned gx = (unsigned)((n + CONS_THREADS - 1) / CONS_THREADS);
     constexpr int NR = airs::Items<AIR>::rescue, NE = airs::Items<AIR>::ecc;
+    auto mark = [&](int k) { if (ev) CSG_CUDA(cudaEventRecord(ev[k], st.s)); };
+    mark(0);
     if (NR > 0) CSG_LAUNCH(st, (cons_item_kernel<AIR, 0>), dim3(gx, h.ncosets, NR > 0 ? NR : 1), CONS_THREADS, 0, args_dev, lde, W, ptab, part);
-    if (NE > 0) CSG_LAUNCH(st, (cons_item_kernel<AIR, 1>), dim3(gx, h.ncosets, NE > 0 ? NE : 1), CONS_THREADS, 0, args_dev, lde, W, ptab, part + (size_t)NR * h.ncosets * n);
-    CSG_LAUNCH(st, cons_rest_kernel<AIR>, dim3(gx, h.ncosets), CONS_THREADS, 0, args_dev, lde, W, ptab, apoly, (const fe *)part, (unsigned)(NR + NE), out);
+    mark(1);
+    fe *ecc_part = part + (size_t)NR * h.ncosets * n;
+    // two scalar-multiplication banks, then the final addition (its own kernel: different code, fewer registers)
+    if (NE > 0) CSG_LAUNCH(st, (cons_item_kernel<AIR, 1>), dim3(gx, h.ncosets, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, ecc_part);
+    mark(2);
+    if (NE > 0) CSG_LAUNCH(st, (cons_item_kernel<AIR, 2>), dim3(gx, h.ncosets, 1), CONS_THREADS, 0, args_dev, lde, W, ptab, ecc_part);
+    mark(3);
+    fe *binv = part + (size_t)(NR + NE) * h.ncosets * n;
+    if (h.nbgroups > 0)
+        CSG_LAUNCH(st, boundary_inverse_kernel, dim3((unsigned)((n + INV_CHUNK * INV_THREADS - 1) / (INV_CHUNK * INV_THREADS)), h.ncosets, h.nbgroups),
+                   INV_THREADS, 0, args_dev, W, binv);
+    CSG_LAUNCH(st, cons_rest_kernel<AIR>, dim3(gx, h.ncosets), CONS_THREADS, 0, args_dev, lde, W, ptab, apoly, (const fe *)part, (unsigned)(NR + NE),
+               (const fe *)binv, out);
+    mark(4);
 }
 }  // namespace
 
@@ -114,18 +162,18 @@ size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets) {
     case airs::RESCUE: items = airs::Items<airs::RESCUE>::rescue; break;
     default: break;
     }
-    return (items ? items : 1) * n * ncosets;
+    return (items + CONS_MAX_BGROUPS) * n * ncosets;
 }
 
 void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab,
-                      const fe *apoly, fe *part, fe *out, Stream &st) {
+                      const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev) {
     switch (air_id) {
-    case airs::TRANSACTION: launch<airs::TRANSACTION>(args_dev, h, lde, W, ptab, apoly, part, out, st); break;
-    case airs::MERKLE_UPDATE: launch<airs::MERKLE_UPDATE>(args_dev, h, lde, W, ptab, apoly, part, out, st); break;
-    case airs::MERKLE_INIT: launch<airs::MERKLE_INIT>(args_dev, h, lde, W, ptab, apoly, part, out, st); break;
-    case airs::SCHNORR: launch<airs::SCHNORR>(args_dev, h, lde, W, ptab, apoly, part, out, st); break;
-    case airs::RANGE: launch<airs::RANGE>(args_dev, h, lde, W, ptab, apoly, part, out, st); break;
-    case airs::RESCUE: launch<airs::RESCUE>(args_dev, h, lde, W, ptab, apoly, part, out, st); break;
+    case airs::TRANSACTION: launch<airs::TRANSACTION>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;
+    case airs::MERKLE_UPDATE: launch<airs::MERKLE_UPDATE>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;
+    case airs::MERKLE_INIT: launch<airs::MERKLE_INIT>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;
+    case airs::SCHNORR: launch<airs::SCHNORR>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;
+    case airs::RANGE: launch<airs::RANGE>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;
+    case airs::RESCUE: launch<airs::RESCUE>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;
     default: throw std::runtime_error("unknown AIR id");
     }
 }

@@ -50,7 +50,7 @@ struct ConsArgs {
 // lde: coset-major extended trace; W: root table of size n; ptab / apoly: periodic tables and assertion value
 // polynomials; part: scratch of constraint_scratch_elements() for the per-item partial sums; out[kc * n + i] receives C(x)
 void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &args_host, const fe *lde, const fe *W, const fe *ptab,
-                      const fe *apoly, fe *part, fe *out, Stream &st);
+                      const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr);   // ev: 5 events bracketing the 4 kernels
 size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets);
 
 unsigned long long redc_violations();   // debug builds (-DCSG_REDC_CHECK): reductions entered with an out-of-range operand

@@ -32,7 +32,7 @@ CSG_HD fp6 dbl(const fp6 &a) { fp6 r; for (int i = 0; i < 6; i++) r.c[i] = f63::
 // (a + b v + c v^2)(d + e v + f v^2) with v^3 = -v - 1: six Fp2 products (ecc.rs:506-548).
 // Not inlined on the device: the curve formulas call it ~40 times per row and the body is ~700 instructions.
 #if defined(__CUDACC__)
-static __host__ __device__ __noinline__ fp6 mul(const fp6 &x, const fp6 &y) {
+static __host__ __device__ __noinline__ fp6 mul(fp6 x, fp6 y) {   // by value: operands travel in registers, not through local memory
 #else
 inline fp6 mul(const fp6 &x, const fp6 &y) {
 #endif

@@ -8,7 +8,10 @@ using namespace f63;
 
 namespace {
 
-constexpr unsigned TILE_LOG = 13;      // elements staged per CTA (64 KB of shared memory + padding)
+#ifndef CSG_NTT_TILE_LOG
+#define CSG_NTT_TILE_LOG 13
+#endif
+constexpr unsigned TILE_LOG = CSG_NTT_TILE_LOG;   // elements staged per CTA (2^13 = 64 KB of shared memory + padding)
 constexpr unsigned MAX_SUB_LOG = 11;   // largest single sub-transform
 constexpr unsigned NTT_THREADS = 256;
 
@@ -33,11 +36,47 @@ __device__ __forceinline__ fe root_pow(const fe *W, unsigned logW, unsigned logm
     return W[idx];
 }
 
+// shared-memory index of element i of a lane: one element of padding after every 16 keeps the strided accesses of the
+// register rounds (and most of the bit-reversed staging) on distinct banks
+__device__ __forceinline__ unsigned pad(unsigned i) { return i + (i >> 4); }
+__host__ __device__ inline unsigned lane_pitch(unsigned S) { return S + (S >> 4) + 1; }
+
+// radix-2^R decimation-in-time round: stages s .. s+R-1 of the S-point transform on 2^R elements held in registers.
+// Element j of a group sits at base + j*2^s; stage s+t pairs (j, j + 2^t) with twiddle w_S^((k0 + (j mod 2^t)*2^s) * S/2^(s+t+1)).
+template <int R>
+__device__ __forceinline__ void dit_round(fe *sm, const fe *tw, unsigned logS, unsigned logT, unsigned s, unsigned SP, unsigned tid, unsigned nth) {
+    constexpr unsigned E = 1u << R;
+    const unsigned groups = 1u << (logS - R + logT), per_lane_mask = (1u << (logS - R)) - 1;
+    for (unsigned g = tid; g < groups; g += nth) {
+        const unsigned lane = g >> (logS - R), gg = g & per_lane_mask;
+        const unsigned k0 = gg & ((1u << s) - 1), base = ((gg >> s) << (s + R)) + k0;
+        fe *L = sm + lane * SP;
+        fe v[E];
+#pragma unroll
+        for (unsigned j = 0; j < E; j++) v[j] = L[pad(base + (j << s))];
+#pragma unroll
+        for (unsigned t = 0; t < (unsigned)R; t++) {
+            const unsigned h = 1u << t;
+#pragma unroll
+            for (unsigned j = 0; j < E; j++) {
+                if (j & h) continue;
+                const unsigned k = k0 + ((j & (h - 1)) << s);
+                const fe w = tw[k << (logS - 1 - s - t)];
+                const fe x = v[j], y = mul(v[j + h], w);
+                v[j] = add(x, y);
+                v[j + h] = sub(x, y);
+            }
+        }
+#pragma unroll
+        for (unsigned j = 0; j < E; j++) L[pad(base + (j << s))] = v[j];
+    }
+}
+
 // One pass: T lanes x S elements staged in shared memory, S-point natural-order NTT along each lane (bit-reversed on
-// the way in, radix-2 decimation-in-time stages in place), optional scalings on the way in and out.
+// the way in, decimation-in-time rounds of three stages in registers), optional scalings on the way in and out.
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
     extern __shared__ fe sm[];
-    const unsigned S = 1u << a.logS, T = 1u << a.logT, SP = S + 1;  // +1 element of padding per lane: lanes land in different banks
+    const unsigned S = 1u << a.logS, T = 1u << a.logT, SP = lane_pitch(S);
     fe *tw = sm + (size_t)T * SP;                                  // S/2 twiddles of the sub-transform
     const unsigned tid = threadIdx.x, nth = blockDim.x;
     const unsigned lane0 = blockIdx.x << a.logT;
@@ -59,21 +98,17 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
             if (preB) v = mul(v, preB[lane0 + l]);
         }
         unsigned r = a.logS ? (__brev(e) >> (32 - a.logS)) : 0;
-        sm[l * SP + r] = v;
+        sm[l * SP + pad(r)] = v;
     }
     __syncthreads();
 
-    const unsigned half = S >> 1;
-    for (unsigned s = 0; s < a.logS; s++) {
-        const unsigned h = 1u << s;
-        for (unsigned b = tid; b < half * T; b += nth) {
-            unsigned l = b >> (a.logS - 1), bb = b & (half - 1);
-            unsigned k = bb & (h - 1);
-            unsigned i0 = l * SP + ((bb >> s) << (s + 1)) + k, i1 = i0 + h;
-            fe u = sm[i0], v = mul(sm[i1], tw[k << (a.logS - 1 - s)]);
-            sm[i0] = add(u, v);
-            sm[i1] = sub(u, v);
-        }
+    // logS = 3*q + rem: the rem (1 or 2) lowest stages go first as one small round, then q rounds of three stages
+    unsigned s = 0;
+    const unsigned rem = a.logS % 3;
+    if (rem == 1) { dit_round<1>(sm, tw, a.logS, a.logT, 0, SP, tid, nth); s = 1; __syncthreads(); }
+    else if (rem == 2) { dit_round<2>(sm, tw, a.logS, a.logT, 0, SP, tid, nth); s = 2; __syncthreads(); }
+    for (; s < a.logS; s += 3) {
+        dit_round<3>(sm, tw, a.logS, a.logT, s, SP, tid, nth);
         __syncthreads();
     }
 
@@ -84,7 +119,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
         unsigned e, l;
         if (lane_fast_out) { l = idx & (T - 1); e = idx >> a.logT; } else { e = idx & (S - 1); l = idx >> a.logS; }
         if (lane0 + l >= a.nlanes) continue;
-        fe v = sm[l * SP + e];
+        fe v = sm[l * SP + pad(e)];
         if (a.tw_logn) v = mul(v, root_pow(a.W, a.logW, a.tw_logn, (unsigned long long)e * (lane0 + l), a.inverse));
         if (postA) v = mul(v, postA[e]);
         if (postB) v = mul(v, postB[lane0 + l]);
@@ -95,14 +130,14 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
 
 void launch_pass(const PassArgs &a, unsigned ncols, unsigned ncosets, Stream &st) {
     const unsigned S = 1u << a.logS, T = 1u << a.logT;
-    size_t smem = ((size_t)T * (S + 1) + S / 2 + 1) * sizeof(fe);
+    size_t smem = ((size_t)T * lane_pitch(S) + S / 2 + 1) * sizeof(fe);
     static bool attr_set = false;
     if (!attr_set) {
         CSG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
     unsigned threads = NTT_THREADS;
-    while (threads > 32 && threads > (S * T) / 2) threads >>= 1;
+    while (threads > 32 && threads > (S * T) / 8) threads >>= 1;
     dim3 grid((a.nlanes + T - 1) / T, ncols, ncosets);
     CSG_LAUNCH(st, ntt_pass_kernel, grid, threads, smem, a);
 }

@@ -88,6 +88,7 @@ struct csg_ctx {
     std::vector<fe> ood_cur, ood_next, ood_comp;
     csg_timings tm{};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // csg_timer_start / csg_timer_stop
+    cudaEvent_t cons_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // ------------------------------------------------------------------------------------------ setup
     void set_air(int air_id, size_t trace_len, const csg_options *o, const uint64_t *pub, size_t npub) {
@@ -255,8 +256,11 @@ struct csg_ctx {
         CSG_CUDA(cudaMemcpyAsync(d_cargs.p, &A, sizeof A, cudaMemcpyHostToDevice, st.s));
         d_comb.reserve(ce * n);
         d_parts.reserve(constraint_scratch_elements(air.id, n, ce));
-        csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st);
+        if (!cons_ev[0]) for (auto &e : cons_ev) CSG_CUDA(cudaEventCreate(&e));
+        csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st, cons_ev);
         tm.constraints = t.stop(st);   // also keeps `polys` alive until the copy has completed
+        float *parts_ms[4] = {&tm.cons_rescue, &tm.cons_ecc_banks, &tm.cons_ecc_final, &tm.cons_rest};
+        for (int k = 0; k < 4; k++) CSG_CUDA(cudaEventElapsedTime(parts_ms[k], cons_ev[k], cons_ev[k + 1]));
         stage = S_EVALUATED;
     }
     // coefficients of the polynomial taking the given values on <w_len> (host, tiny: one value per signature)
@@ -586,6 +590,7 @@ void csg_destroy(csg_ctx *ctx) {
     cudaStreamSynchronize(ctx->st.s);
     cudaStream_t s = ctx->st.s;
     if (ctx->ev_a) { cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); }
+    for (auto e : ctx->cons_ev) if (e) cudaEventDestroy(e);
     delete ctx;
     cudaStreamDestroy(s);
 }

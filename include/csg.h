@@ -92,6 +92,9 @@ int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, si
 typedef struct {
     float h2d, lde, commit_trace, constraints, composition, ood_deep, fri, queries, total;
     uint64_t kernel_launches; /* kernels launched by the last proof */
+    /* the four kernels of the constraint stage: Rescue residuals, scalar-multiplication banks, final point addition,
+     * linear constraints + divisors + boundary terms (CUDA events between the launches) */
+    float cons_rescue, cons_ecc_banks, cons_ecc_final, cons_rest;
 } csg_timings;
 int csg_get_timings(const csg_ctx *ctx, csg_timings *out);
 /* CUDA events on the proving stream around an arbitrary sequence of calls (bench.py's timed region) */
