@@ -92,33 +92,39 @@ CSG_HD fe f_not(fe a) { return f63::sub(f63::ONE, a); }
 CSG_HD fe f_bin(fe a) { return f63::sub(f63::sqr(a), a); }
 
 // ---- Rescue round: backward_half(next) - forward_half(cur) of the 14-wide state at column col0, round constants from
-// periodic columns ark0..ark0+27; up to two (flag, first slot) users of the same residual
+// periodic columns ark0..ark0+27; up to two (flag, first slot) users of the same residual.
+//   forward_half(cur)[i]  = sum_j MDS[i][j] * cur[j]^3 + ark[i]                      (src/utils/rescue.rs:274-279)
+//   backward_half(next)[i] = (sum_j INV_MDS[i][j] * (next[j] - ark[14+j]))^3          (src/utils/rescue.rs:281-287)
+// Row i of both products is formed, cubed/offset and consumed inside one rolled loop, so no 14-element intermediate is
+// ever indexed dynamically (on the GPU that would put it in local memory: the first version of this kernel wrote 4x its
+// algorithmic bytes to DRAM that way).
 template <class PV>
 CSG_HD void rescue_state(const Frame &f, const PV &pv, Comb &C, int col0, int ark0, fe flag_a, int slot_a, bool second, fe flag_b, int slot_b) {
-    fe cur[14], next[14], ark[28], d[14];
+    fe tc[14], tn[14];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 14; i++) { cur[i] = f.cur(col0 + i); next[i] = f.next(col0 + i); }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < 28; i++) ark[i] = pv(ark0 + i);
-    rescue::round_residual(cur, next, ark, d);
-    FlagAcc a;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int i = 0; i < 14; i++) a.add(C, slot_a + i, d[i]);
-    a.flush(C, flag_a);
-    if (second) {
-        FlagAcc b;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int i = 0; i < 14; i++) b.add(C, slot_b + i, d[i]);
-        b.flush(C, flag_b);
+    for (int j = 0; j < 14; j++) {
+        tc[j] = rescue::cube(f.cur(col0 + j));
+        tn[j] = f63::sub(f.next(col0 + j), pv(ark0 + 14 + j));
     }
+    FlagAcc a, b;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 0; i < 14; i++) {
+        const uint64_t *mds = CSG_TABLE(CSG_MDS) + i * 14, *inv_mds = CSG_TABLE(CSG_INV_MDS) + i * 14;
+        f63::acc128 fwd, bwd;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 14; j++) { fwd.mac(mds[j], tc[j]); bwd.mac(inv_mds[j], tn[j]); }
+        const fe d = f63::sub(rescue::cube(bwd.reduce()), f63::add(fwd.reduce(), pv(ark0 + i)));
+        a.add(C, slot_a + i, d);
+        if (second) b.add(C, slot_b + i, d);
+    }
+    a.flush(C, flag_a);
+    if (second) b.flush(C, flag_b);
 }
 
 // ---- merkle::update::evaluate_merkle_update_auth without its two Rescue rounds (src/merkle/update/air.rs:291-369)

@@ -62,9 +62,15 @@ __global__ void __launch_bounds__(INV_THREADS) boundary_inverse_kernel(const Con
 #ifndef CSG_ECC_MINBLOCKS
 #define CSG_ECC_MINBLOCKS 3
 #endif
+#ifndef CSG_RESCUE_MINBLOCKS
+#define CSG_RESCUE_MINBLOCKS 6
+#endif
+#ifndef CSG_REST_MINBLOCKS
+#define CSG_REST_MINBLOCKS 6
+#endif
 // KIND 0: Rescue residual number blockIdx.z; KIND 1: scalar-multiplication bank blockIdx.z; KIND 2: final point addition
 template <int AIR, int KIND>
-__global__ void __launch_bounds__(CONS_THREADS, KIND == 0 ? 4 : CSG_ECC_MINBLOCKS)
+__global__ void __launch_bounds__(CONS_THREADS, KIND == 0 ? CSG_RESCUE_MINBLOCKS : CSG_ECC_MINBLOCKS)
 cons_item_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W, const fe *__restrict__ ptab,
                  fe *__restrict__ part) {
     __shared__ fe xp_s[airs::MAX_GROUPS][CONS_THREADS];   // x^adj of each degree group, one column per thread
@@ -80,7 +86,7 @@ cons_item_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, con
 }
 
 template <int AIR>
-__global__ void __launch_bounds__(CONS_THREADS, 4)
+__global__ void __launch_bounds__(CONS_THREADS, CSG_REST_MINBLOCKS)
 cons_rest_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W, const fe *__restrict__ ptab,
                  const fe *__restrict__ apoly, const fe *__restrict__ part, unsigned nparts, const fe *__restrict__ binv, fe *__restrict__ out) {
     __shared__ fe xp_s[airs::MAX_GROUPS][CONS_THREADS];

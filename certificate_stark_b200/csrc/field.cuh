@@ -124,9 +124,13 @@ struct acc128 {
     uint64_t lo, hi;
     CSG_HD acc128() : lo(0), hi(0) {}
     CSG_HD void mac(fe a, fe b) {
+#if defined(__CUDA_ARCH__)
+        asm("mad.lo.cc.u64 %0, %2, %3, %0;\n\tmadc.hi.u64 %1, %2, %3, %1;" : "+l"(lo), "+l"(hi) : "l"(a), "l"(b));   // carry chain instead of compares
+#else
         u128 t = mul_wide(a, b);
         lo += t.lo;
         hi += t.hi + (lo < t.lo ? 1 : 0);
+#endif
     }
     // value mod p (Montgomery-reduced): bring hi below p first so that t < p * 2^64
     CSG_HD fe reduce() const {
@@ -142,6 +146,10 @@ struct acc192 {
     uint64_t lo, mid, hi;
     CSG_HD acc192() : lo(0), mid(0), hi(0) {}
     CSG_HD void mac(fe a, fe b) {
+#if defined(__CUDA_ARCH__)
+        asm("mad.lo.cc.u64 %0, %3, %4, %0;\n\tmadc.hi.cc.u64 %1, %3, %4, %1;\n\taddc.u64 %2, %2, 0;" : "+l"(lo), "+l"(mid), "+l"(hi) : "l"(a), "l"(b));
+        return;
+#endif
         u128 t = mul_wide(a, b);
         lo += t.lo;
         uint64_t c = lo < t.lo ? 1 : 0;
