@@ -148,6 +148,12 @@ def main():
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up, no e2e leg, no CPU baseline (not a bench number)")
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    # torchrun pins OMP_NUM_THREADS=1; the host-side witness builder and the CPU port are OpenMP code: give them the cores
+    # (the reference arm runs on rank 0 alone and takes all of them)
+    ncpu = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncpu if args.impl == "reference" else max(1, ncpu // max(world, 1)))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -183,8 +189,7 @@ def main():
         return ctx.prove_loaded()
 
     def prove_e2e():
-        ctx.load_trace_ptr(pinned.data_ptr())
-        return ctx.prove_loaded()
+        return ctx.prove_trace_ptr(pinned.data_ptr())      # csg_prove_trace: host buffer in, proof bytes out
 
     ctx.load_trace_ptr(pinned.data_ptr())
     proof = None

@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
         "csg_set_air": (C.c_int, [vp, C.c_int, C.c_size_t, opt, _u64p, C.c_size_t]),
         "csg_load_trace": (C.c_int, [vp, _u64p]), "csg_reload_resident_trace": (C.c_int, [vp]),
         "csg_prove_loaded": (C.c_int, [vp, C.POINTER(_u8p), _szp]),
+        "csg_prove_trace": (C.c_int, [vp, _u64p, C.POINTER(_u8p), _szp]),
         "csg_extend_and_commit_trace": (C.c_int, [vp, _u8p]), "csg_eval_constraints": (C.c_int, [vp, _u64p, _u64p]),
         "csg_commit_composition": (C.c_int, [vp, _u8p]), "csg_ood": (C.c_int, [vp, C.c_uint64, _u64p, _u64p, _u64p]),
         "csg_deep": (C.c_int, [vp, _u64p, _u64p, _u64p]), "csg_fri_commit_layer": (C.c_int, [vp, _u8p]),
@@ -167,6 +168,12 @@ class Context:
     def load_trace_ptr(self, host_ptr: int):
         """same, from a raw host pointer (e.g. a pinned torch tensor's data_ptr())"""
         self._check(lib().csg_load_trace(self._h, C.cast(host_ptr, _u64p)))
+
+    def prove_trace_ptr(self, host_ptr: int) -> bytes:
+        """proof of the trace at a raw HOST pointer (pinned memory makes the copy overlap the extension) for the AIR already set"""
+        out, n = _u8p(), C.c_size_t()
+        self._check(lib().csg_prove_trace(self._h, C.cast(host_ptr, _u64p), C.byref(out), C.byref(n)))
+        return self._take_proof(out, n)
 
     def reload_resident_trace(self):
         self._check(lib().csg_reload_resident_trace(self._h))

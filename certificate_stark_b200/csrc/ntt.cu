@@ -229,17 +229,41 @@ void intt_columns(const RootTable &rt, NttScratch &sc, const fe *in, size_t in_s
     launch_pass(b, (unsigned)ncols, 1, st);
 }
 
+void CosetTables::build(const fe *shifts_host, size_t ncosets_, unsigned logn_, Stream &st) {
+    Split sp = split_of(logn_);
+    const unsigned n1 = 1u << sp.l1, n2 = 1u << sp.l2;
+    ncosets = ncosets_; logn = logn_;
+    shifts.reserve(ncosets < 64 ? 64 : ncosets);
+    tables.reserve((size_t)(n1 + n2) * ncosets);
+    CSG_CUDA(cudaMemcpyAsync(shifts.p, shifts_host, ncosets * sizeof(fe), cudaMemcpyHostToDevice, st.s));
+    dim3 grid((n1 + n2 + 127) / 128, (unsigned)ncosets);
+    CSG_LAUNCH(st, scale_tables_kernel, grid, 128, 0, shifts.p, n1, n2, tables.p);
+}
+
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
                        size_t out_coset_stride, size_t ncols, unsigned logn, const fe *shifts_host, size_t ncosets, Stream &st) {
+    // the convenience form builds the tables into the scratch (they are a few KB)
+    Split sp = split_of(logn);
+    upload_shifts(sc, shifts_host, ncosets, st);
+    build_scale_tables(sc, 1u << sp.l1, 1u << sp.l2, ncosets, st);
+    coset_ntt_columns(rt, sc, coeffs, in_stride, out, out_col_stride, out_coset_stride, ncols, logn, sc.scale.p, ncosets, st, 0);
+}
+
+void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
+                       size_t out_coset_stride, size_t ncols, unsigned logn, const CosetTables &ct, Stream &st) {
+    if (ct.logn != logn) throw std::runtime_error("coset tables were built for another size");
+    coset_ntt_columns(rt, sc, coeffs, in_stride, out, out_col_stride, out_coset_stride, ncols, logn, ct.tables.p, ct.ncosets, st, 0);
+}
+
+void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
+                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *tables_dev, size_t ncosets, Stream &st, int) {
     if (logn > rt.logn) throw std::runtime_error("root table too small");
     const size_t n = (size_t)1 << logn;
     Split sp = split_of(logn);
     const unsigned n1 = 1u << sp.l1, n2 = 1u << sp.l2;
-    upload_shifts(sc, shifts_host, ncosets, st);
-    build_scale_tables(sc, n1, n2, ncosets, st);
     PassArgs a{};
     a.W = rt.W.p; a.logW = rt.logn; a.inverse = 0;
-    a.preA = sc.scale.p; a.pre_bz = n1 + n2;
+    a.preA = tables_dev; a.pre_bz = n1 + n2;
     if (sp.l2 == 0) {
         a.in = coeffs; a.out = out; a.logS = logn; a.logT = lanes_log(logn, 31); a.nlanes = (unsigned)ncols;
         a.in_se = 1; a.in_sl = in_stride; a.out_se = 1; a.out_sl = out_col_stride; a.out_bz = out_coset_stride;
@@ -253,7 +277,7 @@ void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, si
     sc.tmp.reserve(group * ncols * n);
     for (size_t z0 = 0; z0 < ncosets; z0 += group) {
         const size_t g = z0 + group <= ncosets ? group : ncosets - z0;
-        a.preA = sc.scale.p + z0 * (n1 + n2); a.preB = a.preA + n1;
+        a.preA = tables_dev + z0 * (n1 + n2); a.preB = a.preA + n1;
         a.in = coeffs; a.out = sc.tmp.p; a.logS = sp.l1; a.logT = lanes_log(sp.l1, sp.l2); a.nlanes = n2;
         a.in_se = n2; a.in_sl = 1; a.out_se = n2; a.out_sl = 1; a.in_by = in_stride; a.in_bz = 0; a.out_by = n; a.out_bz = ncols * n;
         a.tw_logn = logn;

@@ -36,6 +36,17 @@ void intt_columns(const RootTable &rt, NttScratch &sc, const fe *in, size_t in_s
 //   out[z*out_coset_stride + c*out_col_stride + i] = sum_m coeffs[c*in_stride + m] * shift[z]^m * w_n^(m*i)
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
                        size_t out_coset_stride, size_t ncols, unsigned logn, const fe *shifts_host, size_t ncosets, Stream &st);
+// the same with pre-built per-coset scale tables (a proof extends its columns in chunks, overlapped with the H2D copy)
+struct CosetTables {
+    DBuf<fe> shifts, tables;
+    size_t ncosets = 0;
+    unsigned logn = 0;
+    void build(const fe *shifts_host, size_t ncosets, unsigned logn, Stream &st);
+};
+void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
+                       size_t out_coset_stride, size_t ncols, unsigned logn, const CosetTables &ct, Stream &st);
+void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
+                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *tables_dev, size_t ncosets, Stream &st, int);
 // inverse of the above for one coset per batch entry z: coefficients of the polynomial whose evaluations over
 // shift[z]*<w_n> are in[z*in_stride + i]; out[z*out_stride + m]  (interpolate_poly_with_offset)
 void coset_intt_columns(const RootTable &rt, NttScratch &sc, const fe *in, size_t in_stride, fe *out, size_t out_stride,

@@ -89,6 +89,9 @@ struct csg_ctx {
     csg_timings tm{};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // csg_timer_start / csg_timer_stop
     cudaEvent_t cons_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;          // H2D copies of trace column chunks, overlapped with their extension
+    std::vector<cudaEvent_t> chunk_ev;
+    CosetTables lde_tables;                      // per-coset scale tables of the LDE domain, built once per csg_set_air
 
     // ------------------------------------------------------------------------------------------ setup
     void set_air(int air_id, size_t trace_len, const csg_options *o, const uint64_t *pub, size_t npub) {
@@ -118,6 +121,7 @@ struct csg_ctx {
         ce_shift.resize(ce);
         for (size_t kc = 0; kc < ce; kc++) ce_shift[kc] = lde_shift[kc * (b / ce)];
         build_periodic_tables();
+        lde_tables.build(lde_shift.data(), b, logn, st);
         nfri = 0;
         stage = S_AIR;
     }
@@ -165,9 +169,8 @@ struct csg_ctx {
         const size_t count = (size_t)air.width * n;
         Timer &t = stage_timer;
         t.start(st);
-        d_io.reserve(count); d_polys.reserve(count);
+        d_io.reserve(count);
         CSG_CUDA(cudaMemcpyAsync(d_io.p, trace, count * sizeof(uint64_t), cudaMemcpyHostToDevice, st.s));
-        to_montgomery(d_io.p, d_polys.p, count, st);   // d_polys holds the trace until it is interpolated in place of it
         tm.h2d = t.stop(st);
         nfri = 0;
         stage = S_TRACE;
@@ -175,8 +178,6 @@ struct csg_ctx {
     // for benchmarking with inputs already resident: the trace as left on the device by the last load_trace
     void reload_resident() {
         need(S_TRACE, "no trace has been loaded");
-        const size_t count = (size_t)air.width * n;
-        to_montgomery(d_io.p, d_polys.p, count, st);
         nfri = 0;
         stage = S_TRACE;
         tm.h2d = 0;
@@ -189,16 +190,38 @@ struct csg_ctx {
     }
 
     // ------------------------------------------------------------------------------------------ stage 1 + 2
-    void extend_and_commit_trace(uint8_t root[32]) {
-        need(S_TRACE, "csg_load_trace must be called first");
+    // Stage 1 runs column chunk by column chunk: representation change, interpolation and the `blowup` coset transforms of
+    // a chunk need nothing from the other columns, so when the trace still lives in host memory (csg_prove) the H2D copy
+    // of chunk c+1 overlaps the extension of chunk c.  host == nullptr: the canonical trace is already in d_io.
+    void extend_and_commit_trace(uint8_t root[32], const uint64_t *host = nullptr) {
+        if (!host) need(S_TRACE, "csg_load_trace must be called first");
+        else need(S_AIR, "csg_set_air must be called first");
         const size_t w = air.width;
+        const size_t CHUNK = host ? 8 : w;   // nothing to overlap when the trace is already resident: one chunk
         Timer &t = stage_timer;
         t.start(st);
-        scratch.reserve(w * n);
-        intt_columns(roots, ntt, d_polys.p, n, scratch.p, n, w, logn, st);
+        d_io.reserve(w * n); d_polys.reserve(w * n); scratch.reserve(w * n); d_lde.reserve(w * lde_n);
+        if (host) {
+            if (!copy_stream) CSG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            while (chunk_ev.size() < (w + CHUNK - 1) / CHUNK) { cudaEvent_t e; CSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); chunk_ev.push_back(e); }
+            // the copies must not overtake earlier work on the proving stream that still reads d_io
+            CSG_CUDA(cudaEventRecord(chunk_ev[0], st.s));
+            CSG_CUDA(cudaStreamWaitEvent(copy_stream, chunk_ev[0], 0));
+            for (size_t c0 = 0, k = 0; c0 < w; c0 += CHUNK, k++) {
+                const size_t nc = std::min(CHUNK, w - c0);
+                CSG_CUDA(cudaMemcpyAsync(d_io.p + c0 * n, host + c0 * n, nc * n * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
+                CSG_CUDA(cudaEventRecord(chunk_ev[k], copy_stream));
+            }
+        }
+        for (size_t c0 = 0, k = 0; c0 < w; c0 += CHUNK, k++) {
+            const size_t nc = std::min(CHUNK, w - c0);
+            if (host) CSG_CUDA(cudaStreamWaitEvent(st.s, chunk_ev[k], 0));
+            to_montgomery(d_io.p + c0 * n, d_polys.p + c0 * n, nc * n, st);
+            intt_columns(roots, ntt, d_polys.p + c0 * n, n, scratch.p + c0 * n, n, nc, logn, st);
+            coset_ntt_columns(roots, ntt, scratch.p + c0 * n, n, d_lde.p + c0 * n, n, w * n, nc, logn, lde_tables, st);
+        }
         std::swap(d_polys.p, scratch.p); std::swap(d_polys.n, scratch.n);   // d_polys = coefficients
-        d_lde.reserve(w * lde_n);
-        coset_ntt_columns(roots, ntt, d_polys.p, n, d_lde.p, n, w * n, w, logn, lde_shift.data(), b, st);
+        if (host) { nfri = 0; tm.h2d = 0; }
         tm.lde = t.stop(st);
         t.start(st);
         d_tnodes.reserve(16 * lde_n);
@@ -446,8 +469,8 @@ struct csg_ctx {
         w.u8((uint8_t)opt.hash_fn); w.u8((uint8_t)opt.field_extension);
         w.u8((uint8_t)ilog2(opt.fri_folding_factor)); w.u8((uint8_t)ilog2(opt.fri_max_remainder_size));
     }
-    void prove_loaded(uint8_t **proof, size_t *proof_len) {
-        need(S_TRACE, "csg_load_trace must be called first");
+    void prove_loaded(uint8_t **proof, size_t *proof_len, const uint64_t *host = nullptr) {
+        if (!host) need(S_TRACE, "csg_load_trace must be called first");
         auto t0 = std::chrono::steady_clock::now();
         const unsigned long long launches0 = st.launches;
         const int hf = (int)opt.hash_fn;
@@ -458,7 +481,7 @@ struct csg_ctx {
         Coin coin(hf, seed.v.data(), seed.v.size());
 
         uint8_t trace_root[32], comp_root[32];
-        extend_and_commit_trace(trace_root);
+        extend_and_commit_trace(trace_root, host);
         coin.reseed(trace_root);
         std::vector<fe> t_ab(2 * nc), b_ab(2 * na + 2);
         for (size_t i = 0; i < 2 * nc; i++) t_ab[i] = coin.draw();
@@ -591,6 +614,8 @@ void csg_destroy(csg_ctx *ctx) {
     cudaStream_t s = ctx->st.s;
     if (ctx->ev_a) { cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); }
     for (auto e : ctx->cons_ev) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     cudaStreamDestroy(s);
 }
@@ -610,8 +635,13 @@ int csg_prove(csg_ctx *ctx, int air_id, const uint64_t *trace, size_t trace_len,
     return guarded(ctx, [&] {
         if (!trace || !proof || !proof_len) throw ArgError("null argument");
         ctx->set_air(air_id, trace_len, opt, pub, npub);
-        ctx->load_trace(trace);
-        ctx->prove_loaded(proof, proof_len);
+        ctx->prove_loaded(proof, proof_len, trace);
+    });
+}
+int csg_prove_trace(csg_ctx *ctx, const uint64_t *trace, uint8_t **proof, size_t *proof_len) {
+    return guarded(ctx, [&] {
+        if (!trace || !proof || !proof_len) throw ArgError("null argument");
+        ctx->prove_loaded(proof, proof_len, trace);
     });
 }
 int csg_extend_and_commit_trace(csg_ctx *ctx, uint8_t root[32]) { return guarded(ctx, [&] { ctx->extend_and_commit_trace(root); }); }

@@ -71,6 +71,8 @@ int csg_prove(csg_ctx *ctx, int air_id, const uint64_t *trace, size_t trace_len,
 int csg_set_air(csg_ctx *ctx, int air_id, size_t trace_len, const csg_options *opt, const uint64_t *pub, size_t npub);
 int csg_load_trace(csg_ctx *ctx, const uint64_t *trace);                     /* H2D copy of width*trace_len words */
 int csg_prove_loaded(csg_ctx *ctx, uint8_t **proof, size_t *proof_len);      /* proof of the resident trace */
+/* proof of a trace in HOST memory for the AIR set by csg_set_air: the H2D copy is pipelined with the trace extension */
+int csg_prove_trace(csg_ctx *ctx, const uint64_t *trace, uint8_t **proof, size_t *proof_len);
 int csg_reload_resident_trace(csg_ctx *ctx);                                 /* re-arm the trace left in HBM by the last csg_load_trace (benchmarks) */
 int csg_extend_and_commit_trace(csg_ctx *ctx, uint8_t root[32]);             /* Trace::extend + build_commitment */
 /* t_coeffs: (alpha,beta) per transition constraint; b_coeffs: (alpha,beta) per assertion in winterfell's sorted order */
