@@ -88,7 +88,9 @@ def lib() -> C.CDLL:
         "csg_timer_start": (C.c_int, [vp]), "csg_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "csg_tx_batch_new": (vp, [C.c_uint64, C.c_size_t, C.c_uint]), "csg_tx_batch_free": (None, [vp]), "csg_tx_batch_size": (C.c_size_t, [vp]),
         "csg_tx_batch_roots": (None, [vp, _u64p, _u64p]),
-        "csg_build_trace_transaction": (C.c_int, [vp, _u64p, _u64p]), "csg_build_trace_merkle_update": (C.c_int, [vp, _u64p, _u64p]),
+        "csg_build_trace_transaction": (C.c_int, [vp, _u64p, _u64p]),
+        "csg_build_trace_transaction_device": (C.c_int, [vp, vp]), "csg_download_trace": (C.c_int, [vp, _u64p]),
+        "csg_tx_batch_pack": (C.c_size_t, [vp, _u64p]), "csg_tx_batch_depth": (C.c_uint, [vp]), "csg_build_trace_merkle_update": (C.c_int, [vp, _u64p, _u64p]),
         "csg_build_trace_merkle_init": (C.c_int, [_u64p, _u64p, C.c_uint64, _u64p, _u64p]),
         "csg_sig_batch_new": (vp, [C.c_uint64, C.c_size_t]), "csg_sig_batch_free": (None, [vp]), "csg_sig_batch_size": (C.c_size_t, [vp]),
         "csg_build_trace_schnorr": (C.c_int, [vp, _u64p, _u64p]), "csg_build_trace_range": (C.c_int, [C.c_uint64, _u64p, _u64p]),
@@ -183,6 +185,15 @@ class Context:
         self._check(lib().csg_prove_loaded(self._h, C.byref(out), C.byref(n)))
         return self._take_proof(out, n)
 
+    def build_transaction_trace(self, batch: "TransactionBatch"):
+        """TransactionProver::build_trace on the device (witness_gen.cu): the trace never exists in host memory"""
+        self._check(lib().csg_build_trace_transaction_device(self._h, batch._h))
+
+    def download_trace(self, width: int, trace_len: int) -> np.ndarray:
+        out = np.empty((width, trace_len), dtype=np.uint64)
+        self._check(lib().csg_download_trace(self._h, _p64(out)))
+        return out
+
     def timer_start(self):
         """CUDA event on the proving stream"""
         self._check(lib().csg_timer_start(self._h))
@@ -268,6 +279,12 @@ class TransactionBatch:
         if getattr(self, "_h", None):
             lib().csg_tx_batch_free(self._h)
             self._h = None
+
+    def public_inputs(self) -> np.ndarray:
+        """initial_root[7] final_root[7]: TransactionProver::get_pub_inputs without building the trace"""
+        pub = np.zeros(14, dtype=np.uint64)
+        lib().csg_tx_batch_roots(self._h, _p64(pub[:7]), _p64(pub[7:]))
+        return pub
 
     def transaction_trace(self, out: np.ndarray | None = None):
         """TransactionProver::build_trace (src/prover.rs:37-98) -> (trace (94, 1024*num_tx), pub[14])"""

@@ -108,12 +108,12 @@ CSG_HD point add_full(const point &p, const point &q) {
     return {x3, y3, z3};
 }
 
-// host-only inversions for the final X/Z reduction of the witness (ecc.rs:441-446, 551-591)
-inline fp2 inv(fp2 a) {
+// inversions for the final X/Z reduction of the witness (ecc.rs:441-446, 551-591)
+CSG_HD fp2 inv(fp2 a) {
     fe t = f63::inv(f63::sub(f63::add(f63::sqr(a.c0), f63::mul(f63::dbl(a.c0), a.c1)), f63::dbl(f63::sqr(a.c1))));
     return {f63::mul(f63::add(a.c0, f63::dbl(a.c1)), t), f63::mul(f63::neg(a.c1), t)};
 }
-inline fp6 inv(const fp6 &x) {
+CSG_HD fp6 inv(const fp6 &x) {
     fp2 a = {x.c[0], x.c[1]}, b = {x.c[2], x.c[3]}, c = {x.c[4], x.c[5]};
     fp2 a2 = sqr(a), b2 = sqr(b), c2 = sqr(c);
     fp2 t = sub(mul(a, add(a2, b2)), mul(b, b2));

@@ -314,6 +314,29 @@ void csg_tx_batch_roots(const csg_tx_batch *b, uint64_t initial_root[7], uint64_
     for (int i = 0; i < 7; i++) { initial_root[i] = f63::from_mont(b->initial_roots[0][i]); final_root[i] = f63::from_mont(b->final_root[i]); }
 }
 
+// packed inputs of the device-side witness builder (csrc/witness.cuh): WIT_WORDS words per transaction
+unsigned csg_tx_batch_depth(const csg_tx_batch *b) { return b->tree_depth; }
+size_t csg_tx_batch_pack(const csg_tx_batch *B, uint64_t *out /* 276 words per transaction, or NULL for the size */) {
+    const size_t W = 276, ntx = B->deltas.size();
+    if (!out) return W * ntx;
+#pragma omp parallel for schedule(static)
+    for (size_t t = 0; t < ntx; t++) {
+        uint64_t *r = out + t * W;
+        memset(r, 0, W * sizeof(uint64_t));
+        for (int i = 0; i < 14; i++) { r[i] = B->s_old[t][i]; r[14 + i] = B->r_old[t][i]; }
+        r[28] = B->deltas[t];
+        for (int i = 0; i < 7; i++) r[29 + i] = B->initial_roots[t][i];
+        r[36] = B->s_idx[t]; r[37] = B->r_idx[t];
+        for (size_t k = 0; k < B->s_paths[t].size() && k < 16; k++)
+            for (int i = 0; i < 7; i++) { r[38 + 7 * k + i] = B->s_paths[t][k][i]; r[150 + 7 * k + i] = B->r_paths[t][k][i]; }
+        for (int i = 0; i < 6; i++) r[262 + i] = B->sigs[t].rx[i];
+        for (int i = 0; i < 4; i++) r[268 + i] = B->sigs[t].s.w[i];
+        U256 h = hash_to_scalar_bits(hash_message(B->sigs[t].rx.data(), B->msgs[t]));
+        for (int i = 0; i < 4; i++) r[272 + i] = h.w[i];
+    }
+    return W * ntx;
+}
+
 int csg_build_trace_transaction(const csg_tx_batch *B, uint64_t *trace, uint64_t pub[14]) {
     size_t ntx = B->deltas.size(), n = ntx * TX_CYCLE;
     if (ntx & (ntx - 1)) return CSG_ERR_ARG;

@@ -20,6 +20,7 @@
 #include "host/transcript.hpp"
 #include "ntt.cuh"
 #include "stages.cuh"
+#include "witness.cuh"
 
 namespace csg {
 using namespace f63;
@@ -73,7 +74,10 @@ struct csg_ctx {
     unsigned logn = 0;
     std::vector<fe> lde_shift, ce_shift;   // s_k = offset * w_lde^k ; ce cosets are the LDE cosets k = kc * (b / ce)
 
-    DBuf<uint64_t> d_io;
+    DBuf<uint64_t> d_io, d_wit_in;
+    DBuf<fe> d_wit_finals;
+    std::vector<uint64_t> wit_packed;
+    const csg_tx_batch *wit_packed_for = nullptr;
     DBuf<uint32_t> d_idx, d_dig;
     DBuf<fe> d_parts, d_polys, d_lde, d_comb, d_e, d_cpolys, d_clde, d_abc, d_abc_lde, d_deep, d_ptab, d_apoly;
     DBuf<uint32_t> d_tnodes, d_cnodes;
@@ -733,6 +737,38 @@ long long csg_debug_count_unreduced(csg_ctx *ctx, int which) {
         for (fe v : h) bad += v >= P;
     });
     return bad;
+}
+int csg_build_trace_transaction_device(csg_ctx *ctx, const csg_tx_batch *b) {
+    return guarded(ctx, [&] {
+        ctx->need(S_AIR, "csg_set_air must be called first");
+        if (!b) throw ArgError("null batch");
+        const size_t ntx = csg_tx_batch_size(b);
+        if (ctx->air.id != CSG_AIR_TRANSACTION || ctx->n != ntx * 1024) throw ArgError("the AIR set on this context is not the transaction AIR of this batch size");
+        if (csg_tx_batch_depth(b) != 15) throw ArgError("the transaction AIR is built for tree depth 15");
+        // the packed record of a batch does not change: pack once per batch object (the message hashes cost ~0.2 ms each)
+        std::vector<uint64_t> &packed = ctx->wit_packed;
+        if (ctx->wit_packed_for != b || packed.size() != csg_tx_batch_pack(b, nullptr)) {
+            packed.resize(csg_tx_batch_pack(b, nullptr));
+            csg_tx_batch_pack(b, packed.data());
+            ctx->wit_packed_for = b;
+        }
+        Timer &t = ctx->stage_timer;
+        t.start(ctx->st);
+        DBuf<uint64_t> &in = ctx->d_wit_in;
+        in.reserve(packed.size()); ctx->d_wit_finals.reserve(ntx * 48); ctx->d_io.reserve((size_t)ctx->air.width * ctx->n);
+        CSG_CUDA(cudaMemcpyAsync(in.p, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice, ctx->st.s));
+        build_transaction_trace(in.p, ntx, 15, ctx->d_io.p, ctx->d_wit_finals.p, ctx->st);
+        ctx->tm.h2d = t.stop(ctx->st);   // here: witness generation time
+        ctx->nfri = 0;
+        ctx->stage = S_TRACE;
+    });
+}
+int csg_download_trace(csg_ctx *ctx, uint64_t *trace) {
+    return guarded(ctx, [&] {
+        ctx->need(S_TRACE, "no trace is resident");
+        CSG_CUDA(cudaMemcpyAsync(trace, ctx->d_io.p, (size_t)ctx->air.width * ctx->n * 8, cudaMemcpyDeviceToHost, ctx->st.s));
+        CSG_CUDA(cudaStreamSynchronize(ctx->st.s));
+    });
 }
 int csg_timer_start(csg_ctx *ctx) {
     return guarded(ctx, [&] {

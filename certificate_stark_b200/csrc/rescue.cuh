@@ -68,8 +68,8 @@ CSG_HD void round_residual(const fe (&cur)[14], const fe (&next)[14], const fe *
     for (int i = 0; i < 14; i++) d[i] = f63::sub(b[i], a[i]);
 }
 
-// ---- host-only: the permutation itself, for witness generation (rescue.rs:239-263, 108-152)
-inline void apply_round(fe *state, size_t step) {
+// ---- the permutation itself, for witness generation on the host and on the device (rescue.rs:239-263, 108-152)
+CSG_HD void apply_round(fe *state, size_t step) {
     const uint64_t *ark = CSG_TABLE(CSG_ARK) + (step % CYCLE) * 28;
     fe s[14], t[14];
     for (int i = 0; i < 14; i++) s[i] = state[i];

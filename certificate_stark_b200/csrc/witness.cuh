@@ -1,0 +1,25 @@
+// Device-side witness generation (witness_gen.cu) and the packed per-transaction input record both sides agree on.
+#pragma once
+#include "dev.cuh"
+
+namespace csg {
+
+// one record of WIT_WORDS u64 per transaction, field elements in Montgomery form (host: csg_tx_batch_pack, witness.cpp)
+enum : int {
+    WIT_S_OLD = 0,      // sender leaf before the transfer: key[12], balance, nonce
+    WIT_R_OLD = 14,     // receiver leaf
+    WIT_DELTA = 28,
+    WIT_ROOT = 29,      // tree root before this transaction [7]
+    WIT_S_IDX = 36, WIT_R_IDX = 37,
+    WIT_S_PATH = 38,    // authentication path of the sender: 16 nodes of 7 elements, node k+1 = sibling at level k
+    WIT_R_PATH = 150,
+    WIT_RX = 262,       // x coordinate of the signature's R [6]
+    WIT_S = 268,        // signature scalar s, 4 little-endian words
+    WIT_H = 272,        // message hash h as 4 little-endian words (the bits driving h.P)
+    WIT_WORDS = 276
+};
+
+// canonical column-major trace of ntx transactions (94 x 1024*ntx) into trace_dev; finals_dev: 48 elements per transaction
+void build_transaction_trace(const uint64_t *inputs_dev, size_t ntx, unsigned tree_depth, uint64_t *trace_dev, fe *finals_dev, Stream &st);
+
+}  // namespace csg

@@ -112,6 +112,13 @@ void csg_tx_batch_free(csg_tx_batch *b);
 size_t csg_tx_batch_size(const csg_tx_batch *b);
 void csg_tx_batch_roots(const csg_tx_batch *b, uint64_t initial_root[7], uint64_t final_root[7]);
 int csg_build_trace_transaction(const csg_tx_batch *b, uint64_t *trace /* 94 x 1024*num_tx */, uint64_t pub[14]);   /* src/prover.rs:37-98 */
+/* the same witness built ON THE DEVICE into the context's resident trace: call after csg_set_air for
+ * CSG_AIR_TRANSACTION with trace_len = 1024 * num_tx, then csg_prove_loaded.  Only the packed batch (2.2 KB per transaction)
+ * crosses PCIe.  csg_download_trace copies the resident canonical trace back (tests). */
+int csg_build_trace_transaction_device(csg_ctx *ctx, const csg_tx_batch *b);
+int csg_download_trace(csg_ctx *ctx, uint64_t *trace /* width x trace_len */);
+size_t csg_tx_batch_pack(const csg_tx_batch *b, uint64_t *out /* NULL: returns the word count */);
+unsigned csg_tx_batch_depth(const csg_tx_batch *b);
 int csg_build_trace_merkle_update(const csg_tx_batch *b, uint64_t *trace /* 65 x 512*num_tx */, uint64_t pub[14]); /* src/merkle/update/prover.rs:37-80 */
 int csg_build_trace_merkle_init(const uint64_t s_inputs[14], const uint64_t r_inputs[14], uint64_t delta,
                                 uint64_t *trace /* 58 x 16 */, uint64_t pub[29]);                                   /* src/merkle/init/prover.rs:35-53 */

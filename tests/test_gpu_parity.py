@@ -196,3 +196,19 @@ def test_device_montgomery_reduction_selftest(ctx, csg):
     L = csg.lib()
     L.csg_debug_redc_selftest.restype, L.csg_debug_redc_selftest.argtypes = C.c_longlong, [C.c_void_p]
     assert L.csg_debug_redc_selftest(ctx._h) == 0
+
+
+@pytest.mark.parametrize("num_tx", [1, 4, 32])
+def test_device_witness_matches_host_builder(csg, oracle, num_tx):
+    # TransactionProver::build_trace on the GPU, bit for bit the table the host builder produces
+    batch = csg.TransactionBatch(seed=21 + num_tx, num_tx=num_tx)
+    want, pub = batch.transaction_trace()
+    assert np.array_equal(pub, batch.public_inputs())
+    with csg.Context(0) as c:
+        c.set_air(csg.AIR_TRANSACTION, 1024 * num_tx, pub, csg.ProofOptions())
+        c.build_transaction_trace(batch)
+        got = c.download_trace(94, 1024 * num_tx)
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, f"first differing (column, row): {bad[0]}"
+        proof = c.prove_loaded()
+    assert proof == oracle.prove(oracle.AIR_TRANSACTION, want, pub, oracle.options())
