@@ -343,7 +343,12 @@ class TransactionExample:
         self.ctx = Context(device)
         self.pub_inputs = None
 
-    def prove(self) -> bytes:
-        trace, pub = self.batch.transaction_trace()      # prover.build_trace(&tx_metadata)   src/lib.rs:130
-        self.pub_inputs = pub
-        return self.ctx.prove(AIR_TRANSACTION, trace, pub, self.options)   # prover.prove(trace)   src/lib.rs:140
+    def prove(self, witness_on_device: bool = True) -> bytes:
+        if not witness_on_device:
+            trace, pub = self.batch.transaction_trace()      # prover.build_trace(&tx_metadata)   src/lib.rs:130  (host)
+            self.pub_inputs = pub
+            return self.ctx.prove(AIR_TRANSACTION, trace, pub, self.options)   # prover.prove(trace)   src/lib.rs:140
+        self.pub_inputs = pub = self.batch.public_inputs()
+        self.ctx.set_air(AIR_TRANSACTION, 1024 * self.batch.num_tx, pub, self.options)
+        self.ctx.build_transaction_trace(self.batch)         # build_trace on the device (witness_gen.cu)
+        return self.ctx.prove_loaded()

@@ -174,8 +174,9 @@ def test_reproving_a_resident_trace_gives_the_same_bytes(ctx, csg):
 
 def test_example_facade(csg, oracle):
     ex = csg.get_example(2, seed=4)
-    proof = ex.prove()
+    proof = ex.prove()                                   # witness built on the device
     assert oracle.verify(oracle.AIR_TRANSACTION, ex.pub_inputs, proof) == 0
+    assert ex.prove(witness_on_device=False) == proof    # witness built on the host: same trace, same proof
 
 
 def test_errors_are_reported_not_swallowed(ctx, csg):
