@@ -71,21 +71,50 @@ fe slot_coefficient(const fe *alpha, const fe *beta, const uint8_t *group, const
     return f63::add(alpha[slot], f63::mul(beta[slot], xp[group[slot] * xp_stride]));
 }
 
-// the random linear combination: coefficient of result slot s at this row is alpha[s] + beta[s] * xp[group[s]]
-struct Comb {
+// The random linear combination T(x) = sum_s result_s * (alpha_s + beta_s * x^adj(group(s))).
+//   combined mode (SPLIT = false): `sum` accumulates T(x) itself, the coefficient of a slot is alpha_s + beta_s * xp[g].
+//   split mode    (SPLIT = true):  `sum` accumulates A = sum_s alpha_s * result_s and part[g] accumulates
+//                                  B_g = sum_{s in g} beta_s * result_s, so that T = A + sum_g x^adj_g * B_g can be formed later.
+// Split mode exists for the constraints whose degree stays below half the composition degree (Rescue rounds, Merkle and
+// copy logic: < 4n for the transaction and Schnorr AIRs): A and the B_g are then polynomials of degree < 4n, evaluated on
+// half of the constraint-evaluation cosets only and extended to the other half with two small transforms.
+constexpr int MAX_SPLIT_GROUPS = 6;
+template <bool SPLIT>
+struct CombT {
+    static constexpr bool split = SPLIT;
     const fe *alpha, *beta;
     const uint8_t *group;
-    const fe *xp;        // x^adj per degree group, element g at xp[g * xp_stride]
+    const fe *xp;        // x^adj per degree group, element g at xp[g * xp_stride]   (combined mode only)
     size_t xp_stride;
     f63::acc192 sum;
+    f63::acc192 part[SPLIT ? MAX_SPLIT_GROUPS : 1];
     CSG_HD fe coef(int slot) const { return slot_coefficient(alpha, beta, group, xp, xp_stride, slot); }
-    CSG_HD void add(int slot, fe v) { sum.mac(coef(slot), v); }
+    CSG_HD void add(int slot, fe v) {
+        if (!SPLIT) { sum.mac(coef(slot), v); return; }
+        sum.mac(alpha[slot], v);
+        const fe bv = beta[slot];
+        switch (group[slot]) {   // uniform across the warp: every thread works on the same slot
+        case 0: part[0].mac(bv, v); break;
+        case 1: part[SPLIT ? 1 : 0].mac(bv, v); break;
+        case 2: part[SPLIT ? 2 : 0].mac(bv, v); break;
+        case 3: part[SPLIT ? 3 : 0].mac(bv, v); break;
+        case 4: part[SPLIT ? 4 : 0].mac(bv, v); break;
+        default: part[SPLIT ? 5 : 0].mac(bv, v); break;
+        }
+    }
 };
-// contributions that share one flag: sum_k coef(slot_k) * v_k, multiplied by the flag once at the end
+using Comb = CombT<false>;
+using SplitComb = CombT<true>;
+// contributions that share one flag.  Combined mode: sum_k coef(slot_k) * v_k, multiplied by the flag once at flush time;
+// split mode: the flag is multiplied into every value (there is no single coefficient to factor it out of).
 struct FlagAcc {
     f63::acc192 s;
-    CSG_HD void add(const Comb &C, int slot, fe v) { s.mac(C.coef(slot), v); }
-    CSG_HD void flush(Comb &C, fe flag) { C.sum.mac(flag, s.reduce()); }
+    fe flag;
+    CSG_HD explicit FlagAcc(fe f) : flag(f) {}
+    template <class CB> CSG_HD void add(CB &C, int slot, fe v) {
+        if (!CB::split) s.mac(C.coef(slot), v); else C.add(slot, f63::mul(flag, v));
+    }
+    template <class CB> CSG_HD void flush(CB &C) { if (!CB::split) C.sum.mac(flag, s.reduce()); }
 };
 
 CSG_HD fe f_not(fe a) { return f63::sub(f63::ONE, a); }
@@ -98,8 +127,8 @@ CSG_HD fe f_bin(fe a) { return f63::sub(f63::sqr(a), a); }
 // Row i of both products is formed, cubed/offset and consumed inside one rolled loop, so no 14-element intermediate is
 // ever indexed dynamically (on the GPU that would put it in local memory: the first version of this kernel wrote 4x its
 // algorithmic bytes to DRAM that way).
-template <class PV>
-CSG_HD void rescue_state(const Frame &f, const PV &pv, Comb &C, int col0, int ark0, fe flag_a, int slot_a, bool second, fe flag_b, int slot_b) {
+template <class PV, class CB>
+CSG_HD void rescue_state(const Frame &f, const PV &pv, CB &C, int col0, int ark0, fe flag_a, int slot_a, bool second, fe flag_b, int slot_b) {
     fe tc[14], tn[14];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -108,7 +137,7 @@ CSG_HD void rescue_state(const Frame &f, const PV &pv, Comb &C, int col0, int ar
         tc[j] = rescue::cube(f.cur(col0 + j));
         tn[j] = f63::sub(f.next(col0 + j), pv(ark0 + 14 + j));
     }
-    FlagAcc a, b;
+    FlagAcc a(flag_a), b(flag_b);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -123,17 +152,19 @@ CSG_HD void rescue_state(const Frame &f, const PV &pv, Comb &C, int col0, int ar
         a.add(C, slot_a + i, d);
         if (second) b.add(C, slot_b + i, d);
     }
-    a.flush(C, flag_a);
-    if (second) b.flush(C, flag_b);
+    a.flush(C);
+    if (second) b.flush(C);
 }
 
 // ---- merkle::update::evaluate_merkle_update_auth without its two Rescue rounds (src/merkle/update/air.rs:291-369)
-CSG_HD void merkle_auth_path(const Frame &f, Comb &C, int base, fe tx_hash, fe hash_input, fe hashf) {
+template <class CB>
+CSG_HD void merkle_auth_path(const Frame &f, CB &C, int base, fe tx_hash, fe hash_input, fe hashf) {
     const fe copy_flag = f63::mul(tx_hash, f_not(f63::add(hashf, hash_input)));
     const fe init_flag = f63::mul(tx_hash, hash_input);
     const fe bit = f.next(base + HSW), nbit = f_not(bit);
     C.add(base + HSW, f63::mul(tx_hash, f_bin(bit)));
-    FlagAcc keep, to_rate, place_bit, place_nbit;
+    const fe init_bit = f63::mul(init_flag, bit), init_nbit = f63::mul(init_flag, nbit);
+    FlagAcc keep(f63::add(copy_flag, init_nbit)), to_rate(init_bit), place_bit(init_bit), place_nbit(init_nbit);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -147,15 +178,15 @@ CSG_HD void merkle_auth_path(const Frame &f, Comb &C, int base, fe tx_hash, fe h
     }
     for (int i = 0; i < HRW; i++) place_bit.add(C, base + i, f63::sub(f.next(base + HSW + 1 + i), f.next(base + i)));
     for (int i = HRW; i < HSW; i++) place_nbit.add(C, base + i, f63::sub(f.next(base + HSW + 1 + i), f.next(base + i)));
-    const fe init_bit = f63::mul(init_flag, bit), init_nbit = f63::mul(init_flag, nbit);
-    keep.flush(C, f63::add(copy_flag, init_nbit));
-    to_rate.flush(C, init_bit);
-    place_bit.flush(C, init_bit);
-    place_nbit.flush(C, init_nbit);
+    keep.flush(C);
+    to_rate.flush(C);
+    place_bit.flush(C);
+    place_nbit.flush(C);
 }
 // root bookkeeping of merkle::update::evaluate_constraints (src/merkle/update/air.rs:250-288)
-CSG_HD void merkle_roots(const Frame &f, Comb &C, fe finish) {
-    FlagAcc carry, fin;
+template <class CB>
+CSG_HD void merkle_roots(const Frame &f, CB &C, fe finish) {
+    FlagAcc carry(f_not(finish)), fin(finish);
     for (int i = 0; i < HRW; i++) {
         fe nr = f.next(PREV_ROOT + i), cr = f.cur(PREV_ROOT + i);
         carry.add(C, PREV_ROOT + i, f63::sub(nr, cr));
@@ -163,11 +194,12 @@ CSG_HD void merkle_roots(const Frame &f, Comb &C, fe finish) {
         fin.add(C, INT_ROOT_RES + i, f63::sub(f.cur(SENDER_UPDATED + i), f.cur(RECEIVER_INITIAL + i)));
         fin.add(C, ROOT_MATCH_RES + i, f63::sub(f.next(SENDER_INITIAL + i), cr));
     }
-    carry.flush(C, f_not(finish));
-    fin.flush(C, finish);
+    carry.flush(C);
+    fin.flush(C);
 }
 // value / balance / nonce block (src/merkle/update/air.rs:96-144 and src/air.rs:405-453), added to `a`
-CSG_HD void value_block(const Frame &f, const Comb &C, FlagAcc &a) {
+template <class CB>
+CSG_HD void value_block(const Frame &f, CB &C, FlagAcc &a) {
     for (int i = 0; i < APW; i++) {
         a.add(C, VALUE_RES + i, f63::sub(f.cur(SENDER_INITIAL + i), f.cur(SENDER_UPDATED + i)));
         a.add(C, VALUE_RES + APW + i, f63::sub(f.cur(RECEIVER_INITIAL + i), f.cur(RECEIVER_UPDATED + i)));
@@ -180,7 +212,8 @@ CSG_HD void value_block(const Frame &f, const Comb &C, FlagAcc &a) {
 
 // ---- curve part of schnorr::evaluate_constraints: one scalar multiplication register bank (point at column o, its
 // bit at o+18) against the affine point q (src/schnorr/air.rs:415-452, src/utils/ecc.rs:73-144)
-CSG_HD void scalar_mult_bank(const Frame &f, Comb &C, int o, const fe (&q)[12], fe doubling, fe addition) {
+template <class CB>
+CSG_HD void scalar_mult_bank(const Frame &f, CB &C, int o, const fe (&q)[12], fe doubling, fe addition) {
     // operands are (re)loaded where they are used instead of being held across the two formulas: the curve arithmetic
     // alone needs ~100 64-bit temporaries, and the loads hit L1
     auto load_point = [&]() {
@@ -194,31 +227,32 @@ CSG_HD void scalar_mult_bank(const Frame &f, Comb &C, int o, const fe (&q)[12], 
     const fe bit = f.cur(o + PPW);
     {
         ecc::point d = ecc::double_point(load_point());
-        FlagAcc a;
+        FlagAcc a(doubling);
         for (int i = 0; i < 6; i++) {
             a.add(C, o + i, f63::sub(f.next(o + i), d.x.c[i]));
             a.add(C, o + 6 + i, f63::sub(f.next(o + 6 + i), d.y.c[i]));
             a.add(C, o + 12 + i, f63::sub(f.next(o + 12 + i), d.z.c[i]));
         }
         a.add(C, o + PPW, f_bin(bit));
-        a.flush(C, doubling);
+        a.flush(C);
     }
     {
         ecc::point m = ecc::add_mixed(load_point(), ecc::load6(q), ecc::load6(q + 6));
         const fe nbit = f_not(bit);
-        FlagAcc a;
+        FlagAcc a(addition);
         for (int i = 0; i < 6; i++) {
             a.add(C, o + i, f63::sub(f.next(o + i), f63::add(f63::mul(bit, m.x.c[i]), f63::mul(nbit, f.cur(o + i)))));
             a.add(C, o + 6 + i, f63::sub(f.next(o + 6 + i), f63::add(f63::mul(bit, m.y.c[i]), f63::mul(nbit, f.cur(o + 6 + i)))));
             a.add(C, o + 12 + i, f63::sub(f.next(o + 12 + i), f63::add(f63::mul(bit, m.z.c[i]), f63::mul(nbit, f.cur(o + 12 + i)))));
         }
         a.add(C, o + PPW, f63::sub(bit, f.next(o + PPW)));
-        a.flush(C, addition);
+        a.flush(C);
     }
 }
 // last step of a signature: S + h.P, x reduced to affine, and h must equal the hash output
 // (src/schnorr/air.rs:506-530, src/utils/ecc.rs:146-172)
-CSG_HD void schnorr_final_addition(const Frame &f, Comb &C, fe final_add) {
+template <class CB>
+CSG_HD void schnorr_final_addition(const Frame &f, CB &C, fe final_add) {
     ecc::point s, hp;
     for (int i = 0; i < 6; i++) {
         s.x.c[i] = f.cur(i); s.y.c[i] = f.cur(6 + i); s.z.c[i] = f.cur(12 + i);
@@ -228,22 +262,22 @@ CSG_HD void schnorr_final_addition(const Frame &f, Comb &C, fe final_add) {
     ecc::fp6 nx;
     for (int i = 0; i < 6; i++) nx.c[i] = f.next(i);
     ecc::fp6 xz = ecc::mul(nx, r.z);
-    FlagAcc a;
+    FlagAcc a(final_add);
     for (int i = 0; i < 6; i++) {
         a.add(C, i, f63::sub(xz.c[i], r.x.c[i]));
         a.add(C, 6 + i, f63::sub(f.next(6 + i), r.y.c[i]));
         a.add(C, 12 + i, f63::sub(f.next(12 + i), r.z.c[i]));
     }
     for (int i = 0; i < 4; i++) a.add(C, LIMBS + 1 + i, f63::sub(f.cur(LIMBS + 1 + i), f.cur(SIG_HASH + i)));
-    a.flush(C, final_add);
+    a.flush(C);
 }
 // the light part of schnorr::evaluate_constraints: limb reconstruction of h and the hash copy/injection constraints.
 // IN(i): message element injected into the hash at this row.
-template <class IN>
-CSG_HD void schnorr_light(const Frame &f, Comb &C, fe doubling, fe addition, const fe (&digest)[4], fe copy_hash, IN in) {
+template <class IN, class CB>
+CSG_HD void schnorr_light(const Frame &f, CB &C, fe doubling, fe addition, const fe (&digest)[4], fe copy_hash, IN in) {
     // the four limbs of h are rebuilt from its bits while its scalar multiplication runs (src/schnorr/air.rs:454-486)
     const fe hbit_next = f.next(LIMBS);
-    FlagAcc hold;
+    FlagAcc hold(addition);
     for (int i = 0; i < 4; i++) {
         const int c = LIMBS + 4 - i;
         fe cv = f.cur(c), nv = f.next(c);
@@ -251,14 +285,14 @@ CSG_HD void schnorr_light(const Frame &f, Comb &C, fe doubling, fe addition, con
         C.add(c, f63::mul(f63::mul(f_not(digest[i]), doubling), f63::sub(cv, nv)));
         hold.add(C, LIMBS + 1 + i, f63::sub(f.cur(LIMBS + 1 + i), f.next(LIMBS + 1 + i)));
     }
-    hold.flush(C, addition);
+    hold.flush(C);
     // enforce_hash_copy (src/schnorr/air.rs:309-330)
-    FlagAcc a;
+    FlagAcc a(copy_hash);
     for (int i = 0; i < HRW; i++) {
         a.add(C, SIG_HASH + i, f63::sub(f.cur(SIG_HASH + i), f.next(SIG_HASH + i)));
         a.add(C, SIG_HASH + HRW + i, f63::sub(f.next(SIG_HASH + HRW + i), in(i)));
     }
-    a.flush(C, copy_hash);
+    a.flush(C);
 }
 
 // ================================================================================================ the six AIRs
@@ -276,8 +310,8 @@ template <> struct Items<RANGE> { static constexpr int rescue = 0, ecc = 0; };
 template <> struct Items<RESCUE> { static constexpr int rescue = 1, ecc = 0; };
 
 // ---- Rescue residual number s of the AIR
-template <int AIR, class PV>
-CSG_HD void eval_rescue_item(int s, const Frame &f, const PV &pv, Comb &C) {
+template <int AIR, class PV, class CB>
+CSG_HD void eval_rescue_item(int s, const Frame &f, const PV &pv, CB &C) {
     if (AIR == TRANSACTION) {
         // the four leaf/path hash states serve both the leaf-hash phase (setup flag, slots 0,14,28,42:
         // src/merkle/init/air.rs:171-201) and the authentication paths (hash flag, slots = columns); the fifth state is the
@@ -297,8 +331,8 @@ CSG_HD void eval_rescue_item(int s, const Frame &f, const PV &pv, Comb &C) {
     }
 }
 // ---- curve items: bank 0 = S (generator), bank 1 = h.P (public key); then the final addition
-template <int AIR, class PV>
-CSG_HD void eval_ecc_bank(int bank, const Frame &f, const PV &pv, Comb &C) {
+template <int AIR, class PV, class CB>
+CSG_HD void eval_ecc_bank(int bank, const Frame &f, const PV &pv, CB &C) {
     if (AIR != TRANSACTION && AIR != SCHNORR) return;
     const fe scalar_mult = pv(AIR == TRANSACTION ? TX_SCALAR_MULT : 1);
     const fe doubling = pv(AIR == TRANSACTION ? TX_DOUBLING : 2), addition = f63::mul(f_not(doubling), scalar_mult);
@@ -307,21 +341,21 @@ CSG_HD void eval_ecc_bank(int bank, const Frame &f, const PV &pv, Comb &C) {
     for (int j = 0; j < 12; j++) q[j] = bank == 0 ? gen[j] : (AIR == TRANSACTION ? f.next(SENDER_KEY + j) : pv(7 + j));
     scalar_mult_bank(f, C, bank * (PPW + 1), q, doubling, addition);
 }
-template <int AIR, class PV>
-CSG_HD void eval_ecc_final(const Frame &f, const PV &pv, Comb &C) {
+template <int AIR, class PV, class CB>
+CSG_HD void eval_ecc_final(const Frame &f, const PV &pv, CB &C) {
     if (AIR != TRANSACTION && AIR != SCHNORR) return;
     const fe mask = pv(AIR == TRANSACTION ? TX_SCHNORR : 0), scalar_mult = pv(AIR == TRANSACTION ? TX_SCALAR_MULT : 1);
     schnorr_final_addition(f, C, f63::mul(f_not(scalar_mult), mask));
 }
 
-template <class PV>
-CSG_HD void rest_transaction(const Frame &f, const PV &pv, Comb &C) {
+template <class PV, class CB>
+CSG_HD void rest_transaction(const Frame &f, const PV &pv, CB &C) {
     const fe setup = pv(TX_SETUP), tx_hash = pv(TX_MERKLE), hash_input = pv(TX_HASH_INPUT), finish = pv(TX_FINISH), hashf = pv(TX_HASH);
     const fe schnorr_mask = pv(TX_SCHNORR), scalar_mult = pv(TX_SCALAR_MULT), doubling = pv(TX_DOUBLING), schnorr_hash = pv(TX_SCHNORR_HASH);
     const fe copy_hash = f63::mul(f_not(schnorr_hash), schnorr_mask);
     const fe addition = f63::mul(f_not(doubling), scalar_mult);
     {   // setup row of a transaction: leaf consistency and copies into the carried registers (src/air.rs:405-504)
-        FlagAcc a;
+        FlagAcc a(setup);
         value_block(f, C, a);
         for (int o = 0; o < APW; o++) {
             a.add(C, SENDER_KEY_RES + o, f63::sub(f.next(SENDER_KEY + o), f.cur(SENDER_INITIAL + o)));
@@ -330,10 +364,10 @@ CSG_HD void rest_transaction(const Frame &f, const PV &pv, Comb &C) {
         a.add(C, DELTA_COPY_RES, f63::sub(f.next(DELTA_COPY), f63::sub(f.cur(SENDER_INITIAL + APW), f.cur(SENDER_UPDATED + APW))));
         a.add(C, SIGMA_COPY_RES, f63::sub(f.next(SIGMA_COPY), f.cur(SENDER_UPDATED + APW)));
         a.add(C, NONCE_COPY_RES, f63::sub(f.next(NONCE_COPY), f.cur(SENDER_INITIAL + APW + 1)));
-        a.flush(C, setup);
+        a.flush(C);
     }
     {   // carried registers stay put afterwards (src/air.rs:506-529); note the overlapping slot ranges are the reference's
-        FlagAcc a;
+        FlagAcc a(pv(TX_VALUE_COPY));
         for (int o = 0; o < APW; o++) {
             a.add(C, SENDER_KEY_RES + o, f63::sub(f.next(SENDER_KEY + o), f.cur(SENDER_KEY + o)));
             a.add(C, RECEIVER_KEY_RES + o, f63::sub(f.next(RECEIVER_KEY + o), f.cur(RECEIVER_KEY + o)));
@@ -341,7 +375,7 @@ CSG_HD void rest_transaction(const Frame &f, const PV &pv, Comb &C) {
         a.add(C, DELTA_COPY_RES, f63::sub(f.next(DELTA_COPY), f.cur(DELTA_COPY)));
         a.add(C, SIGMA_COPY_RES, f63::sub(f.next(SIGMA_COPY), f.cur(SIGMA_COPY)));
         a.add(C, NONCE_COPY_RES, f63::sub(f.next(NONCE_COPY), f.cur(NONCE_COPY)));
-        a.flush(C, pv(TX_VALUE_COPY));
+        a.flush(C);
     }
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -366,29 +400,29 @@ CSG_HD void rest_transaction(const Frame &f, const PV &pv, Comb &C) {
     schnorr_light(f, C, doubling, addition, digest, copy_hash, in);
 
     {   // range proofs of delta and sigma (src/air.rs:582-609); the sigma finish check compares the delta registers, as the reference does
-        FlagAcc a;
+        FlagAcc a(pv(TX_RANGE_STEP));
         fe db = f.next(DELTA_BIT), sb = f.next(SIGMA_BIT);
         a.add(C, DELTA_ACC, f63::sub(f.next(DELTA_ACC), f63::add(f63::dbl(f.cur(DELTA_ACC)), db)));
         a.add(C, DELTA_BIT, f_bin(db));
         a.add(C, SIGMA_ACC, f63::sub(f.next(SIGMA_ACC), f63::add(f63::dbl(f.cur(SIGMA_ACC)), sb)));
         a.add(C, SIGMA_BIT, f_bin(sb));
-        a.flush(C, pv(TX_RANGE_STEP));
-        FlagAcc b;
+        a.flush(C);
+        FlagAcc b(pv(TX_RANGE_FINISH));
         fe v = f63::sub(f.next(DELTA_ACC), f.next(DELTA_COPY));
         b.add(C, DELTA_RANGE_RES, v);
         b.add(C, SIGMA_RANGE_RES, v);
-        b.flush(C, pv(TX_RANGE_FINISH));
+        b.flush(C);
     }
 }
 
 // ---- everything that is not a heavy item
-template <int AIR, class PV>
-CSG_HD void eval_rest(const Frame &f, const PV &pv, Comb &C) {
+template <int AIR, class PV, class CB>
+CSG_HD void eval_rest(const Frame &f, const PV &pv, CB &C) {
     if (AIR == TRANSACTION) rest_transaction(f, pv, C);
     else if (AIR == MERKLE_UPDATE) {   // periodic = setup, tx_hash, hash_input, finish, hash, ark[28] (src/merkle/update/air.rs:73-156, 182-212)
-        FlagAcc a;
+        FlagAcc a(pv(0));
         value_block(f, C, a);
-        a.flush(C, pv(0));
+        a.flush(C);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -403,19 +437,19 @@ CSG_HD void eval_rest(const Frame &f, const PV &pv, Comb &C) {
         C.add(1, f63::sub(f.next(1), f63::add(f63::dbl(f.cur(1)), b)));
         C.add(0, f_bin(b));
     } else if (AIR == RESCUE) {        // benches/rescue.rs:205-222: periodic = cycle mask, ark[28]
-        FlagAcc a;
+        FlagAcc a(f_not(pv(0)));
         for (int i = 0; i < HRW; i++) {
             a.add(C, i, f63::sub(f.cur(i), f.next(i)));
             a.add(C, HRW + i, f.next(HRW + i));
         }
-        a.flush(C, f_not(pv(0)));
+        a.flush(C);
     }
     // MERKLE_INIT (src/merkle/init/air.rs:76-90) is its four Rescue rounds only
 }
 
 // the whole of Air::evaluate_transition, merged: what one row contributes to T(x)
-template <int AIR, class PV>
-CSG_HD void eval_transition(const Frame &f, const PV &pv, Comb &C) {
+template <int AIR, class PV, class CB>
+CSG_HD void eval_transition(const Frame &f, const PV &pv, CB &C) {
     for (int s = 0; s < Items<AIR>::rescue; s++) eval_rescue_item<AIR>(s, f, pv, C);
     if (Items<AIR>::ecc) { eval_ecc_bank<AIR>(0, f, pv, C); eval_ecc_bank<AIR>(1, f, pv, C); eval_ecc_final<AIR>(f, pv, C); }
     eval_rest<AIR>(f, pv, C);

@@ -5,8 +5,11 @@
 // adds the cheap linear constraints, sums the partials, applies the divisors and the boundary constraints and writes the
 // merged column.  Splitting the row's work this way keeps each kernel's code and register footprint small (the
 // monolithic version ran at 8 warps/SM with 20 % of its stalls on instruction fetch) and multiplies the parallelism.
+#include <vector>
+
 #include "airs.cuh"
 #include "constraints.cuh"
+#include "stages.cuh"
 
 namespace csg {
 using namespace f63;
@@ -120,6 +123,77 @@ cons_rest_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, con
     out[kc * n + i] = res;
 }
 
+// ---- low-degree split (constraints.cuh): Rescue residuals and the linear rest on the EVEN ce cosets only, in split mode.
+// KIND 0: Rescue residual number blockIdx.z; KIND 3: the linear rest.  Writes 1 + ngroups partial sums per row:
+// low[((item * NP + p) * L + j) * n + i], p = 0 the alpha part, p = 1 + g the beta part of degree group g, j = kc / 2.
+template <int AIR, int KIND>
+__global__ void __launch_bounds__(CONS_THREADS, KIND == 0 ? 4 : 4)
+cons_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W, const fe *__restrict__ ptab,
+                fe *__restrict__ low, unsigned item0) {
+    const unsigned j = blockIdx.y, kc = 2 * j, item = item0 + blockIdx.z, L = A->ncosets / 2, NP = 1 + A->ngroups;
+    const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long inext = (i + 1) & (n - 1);
+    const fe *base = lde + A->lde_coset_stride[kc];
+    airs::Frame f{base + i, base + inext, (size_t)A->col_stride};
+    airs::Periodic pv{ptab + kc * A->ptab_coset_stride, A->poff, A->pmask, (uint32_t)i};
+    airs::SplitComb C{A->alpha, A->beta, A->group, nullptr, 0, acc192(), {}};
+    if (KIND == 0) airs::eval_rescue_item<AIR>((int)blockIdx.z, f, pv, C);
+    else airs::eval_rest<AIR>(f, pv, C);
+    fe *dst = low + (((unsigned long long)item * NP) * L + j) * n + i;
+    dst[0] = C.sum.reduce();
+    for (unsigned g = 0; g + 1 < NP; g++) {
+        fe v;
+        switch (g) {   // static indices keep the accumulators in registers
+        case 0: v = C.part[0].reduce(); break;
+        case 1: v = C.part[1].reduce(); break;
+        case 2: v = C.part[2].reduce(); break;
+        case 3: v = C.part[3].reduce(); break;
+        case 4: v = C.part[4].reduce(); break;
+        default: v = C.part[5].reduce(); break;
+        }
+        dst[(unsigned long long)(1 + g) * L * n] = v;
+    }
+}
+
+// T(x) from its pieces on every ce coset, then divisors and boundary constraints.
+//   low_even / low_odd: [NP][L][n] values of A and B_g on the even / odd cosets; hi: [nhi][ncosets][n] partial sums of the
+//   high-degree items (curve arithmetic), already complete.
+__global__ void __launch_bounds__(CONS_THREADS)
+cons_final_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W, const fe *__restrict__ apoly,
+                  const fe *__restrict__ low_even, const fe *__restrict__ low_odd, const fe *__restrict__ hi, unsigned nhi,
+                  const fe *__restrict__ binv, fe *__restrict__ out) {
+    const unsigned kc = blockIdx.y, L = A->ncosets / 2;
+    const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const fe x = mul(A->shift[kc], W[i]);
+    const fe *low = ((kc & 1) ? low_odd : low_even) + (unsigned long long)(kc >> 1) * n + i;
+    acc192 s;
+    for (unsigned g = 0; g < A->ngroups; g++)
+        s.mac(mul(A->shift_adj[kc][g], W[(A->adj_mod[g] * i) & (n - 1)]), low[(unsigned long long)(1 + g) * L * n]);
+    fe t = add(s.reduce(), low[0]);
+    for (unsigned p = 0; p < nhi; p++) t = add(t, hi[((unsigned long long)p * A->ncosets + kc) * n + i]);
+    fe res = mul(mul(t, sub(x, A->g_last)), A->zinv[kc]);
+    const fe *cur = lde + A->lde_coset_stride[kc] + i;
+    unsigned a = 0;
+    for (unsigned g = 0; g < A->nbgroups; g++) {
+        const fe xpb = mul(A->b_shift_adj[kc][g], W[(A->b_adj_mod[g] * i) & (n - 1)]);
+        acc192 b;
+        for (; a < A->nassertions && A->a_group[a] == g; a++) {
+            fe v = A->a_value[a];
+            if (A->a_poly_len[a] > 1) {
+                const fe *poly = apoly + A->a_poly_off[a];
+                const fe y = mul(x, A->a_xoff[a]);
+                v = 0;
+                for (unsigned m = A->a_poly_len[a]; m-- > 0;) v = add(mul(v, y), poly[m]);
+            }
+            b.mac(add(A->a_alpha[a], mul(A->a_beta[a], xpb)), sub(cur[(unsigned long long)A->a_col[a] * A->col_stride], v));
+        }
+        res = add(res, mul(b.reduce(), binv[((unsigned long long)g * A->ncosets + kc) * n + i]));
+    }
+    out[kc * n + i] = res;
+}
+
 template <int AIR>
 void launch(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab, const fe *apoly, fe *part, fe *out, Stream &st,
             cudaEvent_t *ev) {
@@ -145,6 +219,52 @@ void launch(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe
                (const fe *)binv, out);
     mark(4);
 }
+// Low-degree split: the Rescue residuals and the linear rest have degree < (ce/2) * n for these AIRs, so their alpha and
+// per-group beta parts are evaluated on the even ce cosets only (half the rows), interpolated there and evaluated on the
+// odd cosets (NP * ce/2 size-n inverse transforms, an L x L mix, NP * ce/2 forward transforms); the curve items, whose
+// degree needs the whole domain, run on every coset as before.
+template <int AIR>
+void launch_split(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab, const fe *apoly, fe *part, fe *out, Stream &st,
+                  cudaEvent_t *ev, const RootTable &rt, NttScratch &sc) {
+    const unsigned long long n = 1ULL << h.logn;
+    const unsigned gx = (unsigned)((n + CONS_THREADS - 1) / CONS_THREADS), ce = h.ncosets, L = ce / 2, NP = 1 + h.ngroups;
+    constexpr int NR = airs::Items<AIR>::rescue, NE = airs::Items<AIR>::ecc;
+    const size_t slab = (size_t)NP * L * n;
+    fe *low_parts = part, *low_sum = low_parts + (size_t)(NR + 1) * slab, *low_coef = low_sum + slab, *low_mix = low_coef + slab,
+       *low_odd = low_mix + slab, *hi = low_odd + slab, *binv = hi + (size_t)NE * ce * n;
+    auto mark = [&](int k) { if (ev) CSG_CUDA(cudaEventRecord(ev[k], st.s)); };
+    mark(0);
+    CSG_LAUNCH(st, (cons_low_kernel<AIR, 0>), dim3(gx, L, NR), CONS_THREADS, 0, args_dev, lde, W, ptab, low_parts, 0u);
+    mark(1);
+    CSG_LAUNCH(st, (cons_item_kernel<AIR, 1>), dim3(gx, ce, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, hi);
+    mark(2);
+    CSG_LAUNCH(st, (cons_item_kernel<AIR, 2>), dim3(gx, ce, 1), CONS_THREADS, 0, args_dev, lde, W, ptab, hi);
+    mark(3);
+    CSG_LAUNCH(st, (cons_low_kernel<AIR, 3>), dim3(gx, L, 1), CONS_THREADS, 0, args_dev, lde, W, ptab, low_parts, (unsigned)NR);
+    sum_slices(low_parts, low_sum, slab, NR + 1, st);
+    // interpolate on the even cosets, evaluate on the odd ones
+    std::vector<fe> sinv(NP * L), sodd(NP * L), mix(L * L);
+    for (unsigned p = 0; p < NP; p++)
+        for (unsigned j = 0; j < L; j++) { sinv[p * L + j] = inv(h.shift[2 * j]); sodd[p * L + j] = h.shift[2 * j + 1]; }
+    const fe w2l = root_of_unity(ilog2(2 * L)), linv = inv(to_mont(L));
+    for (unsigned jo = 0; jo < L; jo++)
+        for (unsigned je = 0; je < L; je++) {
+            const unsigned e = (2 * (jo + L - je) + 1) % (2 * L);   // 2 (j' - j) + 1 mod 2L
+            fe acc = 0, step = f63::pow(w2l, e), cur = ONE;
+            for (unsigned t = 0; t < L; t++) { acc = add(acc, cur); cur = mul(cur, step); }
+            mix[jo * L + je] = mul(acc, linv);
+        }
+    coset_intt_columns(rt, sc, low_sum, n, low_coef, n, h.logn, sinv.data(), (size_t)NP * L, st);
+    coset_mix(low_coef, low_mix, n, L, NP, mix.data(), st);
+    coset_ntt_entries(rt, sc, low_mix, low_odd, (size_t)NP * L, h.logn, sodd.data(), st);
+    if (h.nbgroups > 0)
+        CSG_LAUNCH(st, boundary_inverse_kernel, dim3((unsigned)((n + INV_CHUNK * INV_THREADS - 1) / (INV_CHUNK * INV_THREADS)), ce, h.nbgroups),
+                   INV_THREADS, 0, args_dev, W, binv);
+    CSG_LAUNCH(st, cons_final_kernel, dim3(gx, ce), CONS_THREADS, 0, args_dev, lde, W, apoly, (const fe *)low_sum, (const fe *)low_odd, (const fe *)hi,
+               (unsigned)NE, (const fe *)binv, out);
+    mark(4);
+    CSG_CUDA(cudaStreamSynchronize(st.s));   // the host staging vectors above are read by async copies
+}
 }  // namespace
 
 #if defined(CSG_REDC_CHECK)
@@ -168,11 +288,17 @@ size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets) {
     case airs::RESCUE: items = airs::Items<airs::RESCUE>::rescue; break;
     default: break;
     }
-    return (items + CONS_MAX_BGROUPS) * n * ncosets;
+    // split path: (rescue items + rest) x (1 + groups) x ce/2 partial slabs, 4 more slabs for the extension, curve items, divisors
+    const size_t split = ((items + 1 + 4) * (1 + CONS_MAX_GROUPS) / 2 + 3 + CONS_MAX_BGROUPS) * n * ncosets;
+    const size_t plain = (items + CONS_MAX_BGROUPS) * n * ncosets;
+    return split > plain ? split : plain;
 }
 
 void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab,
-                      const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev) {
+                      const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc) {
+    const bool split = rt && sc && h.ncosets == 8 && h.ngroups <= (unsigned)airs::MAX_SPLIT_GROUPS;
+    if (split && air_id == airs::TRANSACTION) { launch_split<airs::TRANSACTION>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev, *rt, *sc); return; }
+    if (split && air_id == airs::SCHNORR) { launch_split<airs::SCHNORR>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev, *rt, *sc); return; }
     switch (air_id) {
     case airs::TRANSACTION: launch<airs::TRANSACTION>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;
     case airs::MERKLE_UPDATE: launch<airs::MERKLE_UPDATE>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;

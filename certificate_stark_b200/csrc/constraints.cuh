@@ -8,6 +8,7 @@
 // On a coset x^n is a constant, so the transition divisor costs one multiplication per row.
 #pragma once
 #include "dev.cuh"
+#include "ntt.cuh"
 
 namespace csg {
 
@@ -50,7 +51,8 @@ struct ConsArgs {
 // lde: coset-major extended trace; W: root table of size n; ptab / apoly: periodic tables and assertion value
 // polynomials; part: scratch of constraint_scratch_elements() for the per-item partial sums; out[kc * n + i] receives C(x)
 void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &args_host, const fe *lde, const fe *W, const fe *ptab,
-                      const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr);   // ev: 5 events bracketing the 4 kernels
+                      const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr,   // ev: 5 events bracketing the 4 phases
+                      const RootTable *rt = nullptr, NttScratch *sc = nullptr);   // given: low-degree constraints use half of the cosets (TX, Schnorr)
 size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets);
 
 unsigned long long redc_violations();   // debug builds (-DCSG_REDC_CHECK): reductions entered with an out-of-range operand

@@ -255,8 +255,16 @@ void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, si
     coset_ntt_columns(rt, sc, coeffs, in_stride, out, out_col_stride, out_coset_stride, ncols, logn, ct.tables.p, ct.ncosets, st, 0);
 }
 
+void coset_ntt_entries(const RootTable &rt, NttScratch &sc, const fe *in, fe *out, size_t nentries, unsigned logn, const fe *shifts_host, Stream &st) {
+    Split sp = split_of(logn);
+    const size_t n = (size_t)1 << logn;
+    upload_shifts(sc, shifts_host, nentries, st);
+    build_scale_tables(sc, 1u << sp.l1, 1u << sp.l2, nentries, st);
+    coset_ntt_columns(rt, sc, in, n, out, n, n, 1, logn, sc.scale.p, nentries, st, (int)n);
+}
+
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
-                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *tables_dev, size_t ncosets, Stream &st, int) {
+                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *tables_dev, size_t ncosets, Stream &st, int in_coset_stride) {
     if (logn > rt.logn) throw std::runtime_error("root table too small");
     const size_t n = (size_t)1 << logn;
     Split sp = split_of(logn);
@@ -266,7 +274,7 @@ void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, si
     a.preA = tables_dev; a.pre_bz = n1 + n2;
     if (sp.l2 == 0) {
         a.in = coeffs; a.out = out; a.logS = logn; a.logT = lanes_log(logn, 31); a.nlanes = (unsigned)ncols;
-        a.in_se = 1; a.in_sl = in_stride; a.out_se = 1; a.out_sl = out_col_stride; a.out_bz = out_coset_stride;
+        a.in_se = 1; a.in_sl = in_stride; a.out_se = 1; a.out_sl = out_col_stride; a.out_bz = out_coset_stride; a.in_bz = (unsigned long long)in_coset_stride;
         launch_pass(a, 1, (unsigned)ncosets, st);
         return;
     }
@@ -278,8 +286,8 @@ void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, si
     for (size_t z0 = 0; z0 < ncosets; z0 += group) {
         const size_t g = z0 + group <= ncosets ? group : ncosets - z0;
         a.preA = tables_dev + z0 * (n1 + n2); a.preB = a.preA + n1;
-        a.in = coeffs; a.out = sc.tmp.p; a.logS = sp.l1; a.logT = lanes_log(sp.l1, sp.l2); a.nlanes = n2;
-        a.in_se = n2; a.in_sl = 1; a.out_se = n2; a.out_sl = 1; a.in_by = in_stride; a.in_bz = 0; a.out_by = n; a.out_bz = ncols * n;
+        a.in = coeffs + z0 * (size_t)in_coset_stride; a.out = sc.tmp.p; a.logS = sp.l1; a.logT = lanes_log(sp.l1, sp.l2); a.nlanes = n2;
+        a.in_se = n2; a.in_sl = 1; a.out_se = n2; a.out_sl = 1; a.in_by = in_stride; a.in_bz = (unsigned long long)in_coset_stride; a.out_by = n; a.out_bz = ncols * n;
         a.tw_logn = logn;
         launch_pass(a, (unsigned)ncols, (unsigned)g, st);
         PassArgs b{};

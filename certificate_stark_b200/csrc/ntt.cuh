@@ -46,7 +46,9 @@ struct CosetTables {
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
                        size_t out_coset_stride, size_t ncols, unsigned logn, const CosetTables &ct, Stream &st);
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
-                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *tables_dev, size_t ncosets, Stream &st, int);
+                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *tables_dev, size_t ncosets, Stream &st, int in_coset_stride);
+// independent entries, each with its own coefficients and shift: out[z*n + i] = sum_m in[z*n + m] * shift[z]^m * w_n^(m*i)
+void coset_ntt_entries(const RootTable &rt, NttScratch &sc, const fe *in, fe *out, size_t nentries, unsigned logn, const fe *shifts_host, Stream &st);
 // inverse of the above for one coset per batch entry z: coefficients of the polynomial whose evaluations over
 // shift[z]*<w_n> are in[z*in_stride + i]; out[z*out_stride + m]  (interpolate_poly_with_offset)
 void coset_intt_columns(const RootTable &rt, NttScratch &sc, const fe *in, size_t in_stride, fe *out, size_t out_stride,

@@ -93,6 +93,7 @@ struct csg_ctx {
     csg_timings tm{};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // csg_timer_start / csg_timer_stop
     cudaEvent_t cons_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool split_low_degree = getenv("CSG_NO_SPLIT") == nullptr;   // CSG_NO_SPLIT=1: evaluate every constraint on every coset (A/B testing)
     cudaStream_t copy_stream = nullptr;          // H2D copies of trace column chunks, overlapped with their extension
     std::vector<cudaEvent_t> chunk_ev;
     CosetTables lde_tables;                      // per-coset scale tables of the LDE domain, built once per csg_set_air
@@ -284,7 +285,8 @@ struct csg_ctx {
         d_comb.reserve(ce * n);
         d_parts.reserve(constraint_scratch_elements(air.id, n, ce));
         if (!cons_ev[0]) for (auto &e : cons_ev) CSG_CUDA(cudaEventCreate(&e));
-        csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st, cons_ev);
+        csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st, cons_ev,
+                              split_low_degree ? &roots : nullptr, split_low_degree ? &ntt : nullptr);
         tm.constraints = t.stop(st);   // also keeps `polys` alive until the copy has completed
         float *parts_ms[4] = {&tm.cons_rescue, &tm.cons_ecc_banks, &tm.cons_ecc_final, &tm.cons_rest};
         for (int k = 0; k < 4; k++) CSG_CUDA(cudaEventElapsedTime(parts_ms[k], cons_ev[k], cons_ev[k + 1]));

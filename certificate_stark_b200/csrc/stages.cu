@@ -36,6 +36,29 @@ __global__ void composition_columns_kernel(const fe *__restrict__ e, fe *__restr
     }
 }
 
+// out[p][j'][m] = sum_j M[j'*L + j] * in[p][j][m]: the same L x L linear map applied across the L cosets of every polynomial
+__global__ void coset_mix_kernel(const fe *__restrict__ in, fe *__restrict__ out, unsigned long long n, unsigned L, CrossMat M) {
+    unsigned long long m = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const fe *src = in + (unsigned long long)blockIdx.y * L * n + m;
+    fe *dst = out + (unsigned long long)blockIdx.y * L * n + m;
+    fe v[16];
+    for (unsigned j = 0; j < L; j++) v[j] = src[j * n];
+    for (unsigned t = 0; t < L; t++) {
+        acc192 s;
+        for (unsigned j = 0; j < L; j++) s.mac(M.m[t * L + j], v[j]);
+        dst[t * n] = s.reduce();
+    }
+}
+// out[e] = sum_k in[k * stride + e], k < count
+__global__ void sum_slices_kernel(const fe *__restrict__ in, fe *__restrict__ out, unsigned long long stride, unsigned count) {
+    unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (e >= stride) return;
+    fe s = in[e];
+    for (unsigned k = 1; k < count; k++) s = add(s, in[k * stride + e]);
+    out[e] = s;
+}
+
 constexpr unsigned EVAL_THREADS = 256, EVAL_CHUNK = 32;
 struct EvalPoints { fe z[4], z_stride[4]; };   // z_stride = z^EVAL_THREADS
 __global__ void __launch_bounds__(EVAL_THREADS) eval_polys_kernel(const fe *__restrict__ polys, unsigned long long stride, unsigned long long n,
@@ -180,6 +203,17 @@ void composition_columns(const fe *e, fe *cols, size_t n, unsigned ce, const fe 
     CrossMat M;
     for (unsigned i = 0; i < ce * ce; i++) M.m[i] = mat_host[i];
     CSG_LAUNCH(st, composition_columns_kernel, (unsigned)((n + 255) / 256), 256, 0, e, cols, (unsigned long long)n, ce, M);
+}
+
+void coset_mix(const fe *in, fe *out, size_t n, unsigned L, size_t npolys, const fe *mat_host, Stream &st) {
+    if (L > 16) throw std::runtime_error("at most 16 cosets can be mixed");
+    CrossMat M;
+    for (unsigned i = 0; i < L * L; i++) M.m[i] = mat_host[i];
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)npolys);
+    CSG_LAUNCH(st, coset_mix_kernel, grid, 256, 0, in, out, (unsigned long long)n, L, M);
+}
+void sum_slices(const fe *in, fe *out, size_t stride, unsigned count, Stream &st) {
+    CSG_LAUNCH(st, sum_slices_kernel, (unsigned)((stride + 255) / 256), 256, 0, in, out, (unsigned long long)stride, count);
 }
 
 void eval_polys_at(const fe *polys, size_t stride, size_t ncols, size_t n, const fe *points_host, size_t npoints, fe *values_host,

@@ -15,6 +15,10 @@ void to_montgomery(const uint64_t *in, fe *out, size_t count, Stream &st);
 // mat[t*ce + k] = offset^(-n t) / ce * w_ce^(-k t)
 void composition_columns(const fe *e, fe *cols, size_t n, unsigned ce, const fe *mat_host, Stream &st);
 
+// out[p][j'][m] = sum_j mat[j'*L + j] * in[p][j][m] for npolys blocks of L x n elements; out[e] = sum_k in[k*stride + e]
+void coset_mix(const fe *in, fe *out, size_t n, unsigned L, size_t npolys, const fe *mat_host, Stream &st);
+void sum_slices(const fe *in, fe *out, size_t stride, unsigned count, Stream &st);
+
 // values[p * ncols + c] = poly_c(points[p]) for ncols polynomials of n coefficients at polys[c * stride ..]; the final
 // reduction over per-CTA partial sums runs on the host (a few hundred KB)
 void eval_polys_at(const fe *polys, size_t stride, size_t ncols, size_t n, const fe *points_host, size_t npoints, fe *values_host,
