@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
         "csg_open_trace": (C.c_int, [vp, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
         "csg_open_composition": (C.c_int, [vp, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
         "csg_open_fri_layer": (C.c_int, [vp, C.c_size_t, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
+        "csg_verify": (C.c_int, [C.c_int, _u64p, C.c_size_t, _u8p, C.c_size_t]),
         "csg_get_timings": (C.c_int, [vp, C.POINTER(Timings)]),
         "csg_timer_start": (C.c_int, [vp]), "csg_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "csg_tx_batch_new": (vp, [C.c_uint64, C.c_size_t, C.c_uint]), "csg_tx_batch_free": (None, [vp]), "csg_tx_batch_size": (C.c_size_t, [vp]),
@@ -114,6 +115,17 @@ def _p64(a):
 
 def _p8(a):
     return a.ctypes.data_as(_u8p)
+
+
+VERIFY_ERRORS = {16: "malformed proof", 17: "inconsistent out-of-domain constraint evaluations", 18: "proof of work check failed",
+                 19: "trace query does not match the commitment", 20: "constraint query does not match the commitment", 21: "FRI verification failed"}
+
+
+def verify(air_id: int, pub: np.ndarray, proof: bytes) -> int:
+    """winterfell::verify::<Air>(proof, pub_inputs): 0 when the proof is accepted, else a key of VERIFY_ERRORS.  Host-only."""
+    pub = np.ascontiguousarray(pub, dtype=np.uint64)
+    buf = np.frombuffer(proof, dtype=np.uint8)
+    return lib().csg_verify(air_id, _p64(pub), pub.size, _p8(buf), buf.size)
 
 
 class Context:
@@ -333,7 +345,7 @@ def get_example(num_transactions: int, seed: int = 1, device: int = 0) -> "Trans
 
 class TransactionExample:
     """TransactionExample::{new, prove} (src/lib.rs:92-141): a batch of transactions and the proof of their state transition.
-    `verify` is not part of the GPU path (src/lib.rs:144-150 calls winterfell::verify on the host) and is not provided."""
+    `verify` runs on the host, as winterfell::verify does for the reference (src/lib.rs:144-150)."""
 
     def __init__(self, options: ProofOptions, num_transactions: int, seed: int = 1, device: int = 0):
         if num_transactions < 1 or num_transactions & (num_transactions - 1):
@@ -342,6 +354,16 @@ class TransactionExample:
         self.batch = TransactionBatch(seed, num_transactions)
         self.ctx = Context(device)
         self.pub_inputs = None
+
+    def verify(self, proof: bytes) -> bool:
+        """TransactionExample::verify (src/lib.rs:144-150)"""
+        return verify(AIR_TRANSACTION, self.batch.public_inputs(), proof) == 0
+
+    def verify_with_wrong_inputs(self, proof: bytes) -> bool:
+        """TransactionExample::verify_with_wrong_inputs (src/lib.rs:152-161): every limb of the final root replaced by its first"""
+        pub = self.batch.public_inputs()
+        pub[7:] = pub[7]
+        return verify(AIR_TRANSACTION, pub, proof) == 0
 
     def prove(self, witness_on_device: bool = True) -> bytes:
         if not witness_on_device:

@@ -25,6 +25,9 @@ extern "C" {
 #endif
 
 enum { CSG_OK = 0, CSG_ERR_ARG = 1, CSG_ERR_CUDA = 2, CSG_ERR_STATE = 3, CSG_ERR_UNSUPPORTED = 4, CSG_ERR_COIN = 5 };
+/* csg_verify results other than CSG_OK (the VerifierError kinds of winterfell::verify) */
+enum { CSG_VERIFY_MALFORMED = 16, CSG_VERIFY_OOD_MISMATCH = 17, CSG_VERIFY_POW = 18, CSG_VERIFY_TRACE_QUERY = 19,
+       CSG_VERIFY_CONSTRAINT_QUERY = 20, CSG_VERIFY_FRI = 21 };
 
 /* AIR ids: the six `impl Air` of the reference */
 enum {
@@ -63,6 +66,10 @@ void csg_free(void *p);                     /* frees buffers returned by csg_pro
  * proof: malloc'ed StarkProof::to_bytes(); release with csg_free. */
 int csg_prove(csg_ctx *ctx, int air_id, const uint64_t *trace, size_t trace_len, const uint64_t *pub, size_t npub,
               const csg_options *opt, uint8_t **proof, size_t *proof_len);
+
+/* ---- verification: replaces `winterfell::verify::<Air>(proof, pub_inputs)` (src/lib.rs:144-150).  Host-only, as in the
+ * reference; needs no context and no GPU.  Returns CSG_OK or one of CSG_VERIFY_*. */
+int csg_verify(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len);
 
 /* ---- level 2: the stages of Prover::prove, transcript on the caller's side --------------------------------------
  * call order: set_air, load_trace, [extend_and_commit_trace, eval_constraints, commit_composition, ood, deep,

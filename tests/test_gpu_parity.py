@@ -177,6 +177,7 @@ def test_example_facade(csg, oracle):
     proof = ex.prove()                                   # witness built on the device
     assert oracle.verify(oracle.AIR_TRANSACTION, ex.pub_inputs, proof) == 0
     assert ex.prove(witness_on_device=False) == proof    # witness built on the host: same trace, same proof
+    assert ex.verify(proof) and not ex.verify_with_wrong_inputs(proof)     # src/tests.rs:12-37 with the product's own verifier
 
 
 def test_errors_are_reported_not_swallowed(ctx, csg):

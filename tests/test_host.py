@@ -73,3 +73,29 @@ def test_proof_options_mirror(csg):
     o = csg.ProofOptions()
     assert (o.num_queries, o.blowup_factor, o.grinding_factor, o.hash_fn, o.field_extension, o.fri_folding_factor, o.fri_max_remainder_size) == \
         (42, 8, 0, csg.HASH_BLAKE3_256, 1, 4, 256)      # get_example, src/lib.rs:78-86
+
+
+def test_product_verifier_accepts_valid_and_rejects_invalid_proofs(csg, oracle):
+    # csg_verify = winterfell::verify (src/lib.rs:144-150): host-only, so it is tested here against proofs from the CPU oracle,
+    # with the reference's own test pattern: accept, reject wrong public inputs (src/tests.rs:32-37), reject tampering
+    z = np.zeros(14, dtype=np.uint64)
+    batch = csg.TransactionBatch(seed=2, num_tx=2)
+    cases = [(csg.AIR_RESCUE, csg.build_rescue_trace(np.arange(42, 49, dtype=np.uint64), 16), 4, 2),
+             (csg.AIR_RANGE, csg.build_range_trace(2**63 - 1), 8, 3),
+             (csg.AIR_MERKLE_INIT, csg.build_merkle_init_trace(z, z, 1), 4, 2),
+             (csg.AIR_MERKLE_UPDATE, batch.merkle_update_trace(), 8, 2),
+             (csg.AIR_TRANSACTION, batch.transaction_trace(), 8, 2),
+             (csg.AIR_SCHNORR, csg.SignatureBatch(seed=2, num_sig=2).schnorr_trace(), 8, 2)]
+    for air, (trace, pub), blowup, hash_fn in cases:
+        proof = oracle.prove(air, trace, pub, oracle.options(blowup=blowup, hash_fn=hash_fn))
+        assert csg.verify(air, pub, proof) == 0
+        assert oracle.verify(air, pub, proof) == 0
+        wrong = pub.copy()
+        wrong[-1] = (int(wrong[-1]) + 1) % csg.P
+        assert csg.verify(air, wrong, proof) == 17                      # inconsistent out-of-domain evaluations
+        for where in (len(proof) // 3, len(proof) // 2, len(proof) - 20):
+            bad = bytearray(proof)
+            bad[where] ^= 0x40
+            assert csg.verify(air, pub, bytes(bad)) != 0, f"air {air}: flipped bit at {where} accepted"
+        assert csg.verify(air, pub, proof[:-1]) == 16 and csg.verify(air, pub, proof + b"\0") == 16
+        assert csg.verify((air + 1) % 6, pub, proof) != 0
