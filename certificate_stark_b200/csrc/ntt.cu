@@ -24,6 +24,7 @@ struct PassArgs {
     const fe *W; unsigned logW;                    // root table
     int inverse;
     const fe *preA, *preB; unsigned long long pre_bz;    // input (e, lane) *= preA[e] * preB[lane]
+    const fe *preFull; unsigned long long pre_full_bz;   // or, when given: input at offset m inside its column *= preFull[m]
     const fe *postA, *postB; unsigned long long post_bz;  // output (e, lane) *= postA[e] * postB[lane]
     unsigned tw_logn;                              // != 0: output (e, lane) *= w_{2^tw_logn}^(+-e*lane)
     int use_scalar; fe scalar;                     // output *= scalar
@@ -93,9 +94,13 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
         if (lane_fast_in) { l = idx & (T - 1); e = idx >> a.logT; } else { e = idx & (S - 1); l = idx >> a.logS; }
         fe v = 0;
         if (lane0 + l < a.nlanes) {
-            v = in[e * a.in_se + (lane0 + l) * a.in_sl];
-            if (preA) v = mul(v, preA[e]);
-            if (preB) v = mul(v, preB[lane0 + l]);
+            const unsigned long long m = e * a.in_se + (lane0 + l) * a.in_sl;
+            v = in[m];
+            if (a.preFull) v = mul(v, a.preFull[blockIdx.z * a.pre_full_bz + m]);
+            else {
+                if (preA) v = mul(v, preA[e]);
+                if (preB) v = mul(v, preB[lane0 + l]);
+            }
         }
         unsigned r = a.logS ? (__brev(e) >> (32 - a.logS)) : 0;
         sm[l * SP + pad(r)] = v;
@@ -229,6 +234,14 @@ void intt_columns(const RootTable &rt, NttScratch &sc, const fe *in, size_t in_s
     launch_pass(b, (unsigned)ncols, 1, st);
 }
 
+// full[z][m] = A_z[m / n2] * B_z[m % n2] = shift_z^m
+__global__ void full_scale_kernel(const fe *tables, unsigned n1, unsigned n2, fe *full) {
+    const unsigned long long m = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x, n = (unsigned long long)n1 * n2;
+    if (m >= n) return;
+    const fe *A = tables + (size_t)blockIdx.y * (n1 + n2), *B = A + n1;
+    full[blockIdx.y * n + m] = mul(A[m / n2], B[m % n2]);
+}
+
 void CosetTables::build(const fe *shifts_host, size_t ncosets_, unsigned logn_, Stream &st) {
     Split sp = split_of(logn_);
     const unsigned n1 = 1u << sp.l1, n2 = 1u << sp.l2;
@@ -238,6 +251,12 @@ void CosetTables::build(const fe *shifts_host, size_t ncosets_, unsigned logn_, 
     CSG_CUDA(cudaMemcpyAsync(shifts.p, shifts_host, ncosets * sizeof(fe), cudaMemcpyHostToDevice, st.s));
     dim3 grid((n1 + n2 + 127) / 128, (unsigned)ncosets);
     CSG_LAUNCH(st, scale_tables_kernel, grid, 128, 0, shifts.p, n1, n2, tables.p);
+    has_full = sp.l2 != 0;   // two-pass sizes: one table lookup and one multiplication per element instead of two
+    if (has_full) {
+        const size_t n = (size_t)n1 * n2;
+        full.reserve(n * ncosets);
+        CSG_LAUNCH(st, full_scale_kernel, dim3((unsigned)((n + 255) / 256), (unsigned)ncosets), 256, 0, (const fe *)tables.p, n1, n2, full.p);
+    }
 }
 
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
@@ -252,7 +271,8 @@ void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, si
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
                        size_t out_coset_stride, size_t ncols, unsigned logn, const CosetTables &ct, Stream &st) {
     if (ct.logn != logn) throw std::runtime_error("coset tables were built for another size");
-    coset_ntt_columns(rt, sc, coeffs, in_stride, out, out_col_stride, out_coset_stride, ncols, logn, ct.tables.p, ct.ncosets, st, 0);
+    coset_ntt_columns(rt, sc, coeffs, in_stride, out, out_col_stride, out_coset_stride, ncols, logn, ct.tables.p, ct.ncosets, st, 0,
+                      ct.has_full ? ct.full.p : nullptr);
 }
 
 void coset_ntt_entries(const RootTable &rt, NttScratch &sc, const fe *in, fe *out, size_t nentries, unsigned logn, const fe *shifts_host, Stream &st) {
@@ -264,7 +284,8 @@ void coset_ntt_entries(const RootTable &rt, NttScratch &sc, const fe *in, fe *ou
 }
 
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
-                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *tables_dev, size_t ncosets, Stream &st, int in_coset_stride) {
+                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *tables_dev, size_t ncosets, Stream &st, int in_coset_stride,
+                       const fe *full_tables) {
     if (logn > rt.logn) throw std::runtime_error("root table too small");
     const size_t n = (size_t)1 << logn;
     Split sp = split_of(logn);
@@ -286,6 +307,7 @@ void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, si
     for (size_t z0 = 0; z0 < ncosets; z0 += group) {
         const size_t g = z0 + group <= ncosets ? group : ncosets - z0;
         a.preA = tables_dev + z0 * (n1 + n2); a.preB = a.preA + n1;
+        a.preFull = full_tables ? full_tables + z0 * n : nullptr; a.pre_full_bz = n;
         a.in = coeffs + z0 * (size_t)in_coset_stride; a.out = sc.tmp.p; a.logS = sp.l1; a.logT = lanes_log(sp.l1, sp.l2); a.nlanes = n2;
         a.in_se = n2; a.in_sl = 1; a.out_se = n2; a.out_sl = 1; a.in_by = in_stride; a.in_bz = (unsigned long long)in_coset_stride; a.out_by = n; a.out_bz = ncols * n;
         a.tw_logn = logn;

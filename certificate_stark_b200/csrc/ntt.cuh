@@ -38,15 +38,17 @@ void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, si
                        size_t out_coset_stride, size_t ncols, unsigned logn, const fe *shifts_host, size_t ncosets, Stream &st);
 // the same with pre-built per-coset scale tables (a proof extends its columns in chunks, overlapped with the H2D copy)
 struct CosetTables {
-    DBuf<fe> shifts, tables;
+    DBuf<fe> shifts, tables, full;   // full[z][m] = shift_z^m for two-pass sizes
     size_t ncosets = 0;
     unsigned logn = 0;
+    bool has_full = false;
     void build(const fe *shifts_host, size_t ncosets, unsigned logn, Stream &st);
 };
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
                        size_t out_coset_stride, size_t ncols, unsigned logn, const CosetTables &ct, Stream &st);
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,
-                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *tables_dev, size_t ncosets, Stream &st, int in_coset_stride);
+                       size_t out_coset_stride, size_t ncols, unsigned logn, const fe *tables_dev, size_t ncosets, Stream &st, int in_coset_stride,
+                       const fe *full_tables = nullptr);
 // independent entries, each with its own coefficients and shift: out[z*n + i] = sum_m in[z*n + m] * shift[z]^m * w_n^(m*i)
 void coset_ntt_entries(const RootTable &rt, NttScratch &sc, const fe *in, fe *out, size_t nentries, unsigned logn, const fe *shifts_host, Stream &st);
 // inverse of the above for one coset per batch entry z: coefficients of the polynomial whose evaluations over

@@ -99,20 +99,45 @@ __global__ void combine_polys_kernel(const fe *__restrict__ polys, unsigned long
     for (int t = 0; t < NCOMB; t++) out[t * out_stride + m] = s[t].reduce();
 }
 
-__global__ void deep_quotients_kernel(const fe *__restrict__ abc, const fe *__restrict__ W, unsigned long long n, DeepArgs a, fe *__restrict__ deep) {
-    unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (j >= n * a.ncosets) return;
-    const unsigned k = (unsigned)(j % a.ncosets);
-    const unsigned long long i = j / a.ncosets;
-    const fe x = mul(a.shift[k], W[i]);
-    const fe *src = abc + (unsigned long long)k * 3 * n + i;
-    const fe na = sub(src[0], a.az), nb = sub(src[n], a.bzg), nc = sub(src[2 * n], a.czm);
-    const fe d1 = sub(x, a.z), d2 = sub(x, a.zg), d3 = sub(x, a.zm);
-    const fe d12 = mul(d1, d2), pinv = inv(mul(d12, d3));
-    const fe i3 = mul(pinv, d12), i12 = mul(pinv, d3);   // 1/d3, 1/(d1 d2)
-    const fe i1 = mul(i12, d2), i2 = mul(i12, d1);
-    fe s = add(add(mul(na, i1), mul(nb, i2)), mul(nc, i3));
-    deep[j] = mul(s, add(a.lambda, mul(a.mu, x)));
+// Each thread handles DEEP_CHUNK consecutive-stride elements and inverts the product of all their denominators once
+// (Montgomery's trick): 3 multiplications per denominator instead of a ~90-multiplication inversion per element.
+constexpr int DEEP_CHUNK = 8, DEEP_THREADS = 128;
+__global__ void __launch_bounds__(DEEP_THREADS) deep_quotients_kernel(const fe *__restrict__ abc, const fe *__restrict__ W, unsigned long long n, DeepArgs a,
+                                                                     fe *__restrict__ deep) {
+    const unsigned long long total = n * a.ncosets;
+    const unsigned long long base = blockIdx.x * (unsigned long long)(DEEP_CHUNK * DEEP_THREADS) + threadIdx.x;
+    fe den[DEEP_CHUNK], pre[DEEP_CHUNK], xs[DEEP_CHUNK];
+    fe acc = ONE;
+#pragma unroll
+    for (int c = 0; c < DEEP_CHUNK; c++) {
+        const unsigned long long j = base + (unsigned long long)c * DEEP_THREADS;
+        fe d = ONE, x = 0;
+        if (j < total) {
+            x = mul(a.shift[j % a.ncosets], W[j / a.ncosets]);
+            d = mul(mul(sub(x, a.z), sub(x, a.zg)), sub(x, a.zm));
+        }
+        xs[c] = x; den[c] = d; pre[c] = acc;
+        acc = mul(acc, d);
+    }
+    fe ainv = inv(acc);
+#pragma unroll
+    for (int c = DEEP_CHUNK - 1; c >= 0; c--) {
+        const unsigned long long j = base + (unsigned long long)c * DEEP_THREADS;
+        const fe pinv = mul(ainv, pre[c]);   // 1 / (d1 d2 d3) of element c
+        ainv = mul(ainv, den[c]);
+        if (j >= total) continue;
+        const unsigned k = (unsigned)(j % a.ncosets);
+        const unsigned long long i = j / a.ncosets;
+        const fe x = xs[c];
+        const fe *src = abc + (unsigned long long)k * 3 * n + i;
+        const fe na = sub(src[0], a.az), nb = sub(src[n], a.bzg), nc = sub(src[2 * n], a.czm);
+        const fe d1 = sub(x, a.z), d2 = sub(x, a.zg), d3 = sub(x, a.zm);
+        const fe d12 = mul(d1, d2);
+        const fe i3 = mul(pinv, d12), i12 = mul(pinv, d3);   // 1/d3, 1/(d1 d2)
+        const fe i1 = mul(i12, d2), i2 = mul(i12, d1);
+        fe s = add(add(mul(na, i1), mul(nb, i2)), mul(nc, i3));
+        deep[j] = mul(s, add(a.lambda, mul(a.mu, x)));
+    }
 }
 
 __global__ void fri_fold4_kernel(const fe *__restrict__ e, unsigned long long q, const fe *__restrict__ W, FoldArgs a, fe *__restrict__ out) {
@@ -247,8 +272,8 @@ void combine_polys(const fe *polys, size_t stride, size_t ncols, size_t n, const
 }
 
 void deep_quotients(const fe *abc, const fe *W, size_t n, const DeepArgs &a, fe *deep, Stream &st) {
-    const size_t total = n * a.ncosets;
-    CSG_LAUNCH(st, deep_quotients_kernel, (unsigned)((total + 255) / 256), 256, 0, abc, W, (unsigned long long)n, a, deep);
+    const size_t total = n * a.ncosets, per_block = (size_t)DEEP_CHUNK * DEEP_THREADS;
+    CSG_LAUNCH(st, deep_quotients_kernel, (unsigned)((total + per_block - 1) / per_block), DEEP_THREADS, 0, abc, W, (unsigned long long)n, a, deep);
 }
 
 void fri_fold4(const fe *evals, size_t m, const fe *W, const FoldArgs &a, fe *out, Stream &st) {
