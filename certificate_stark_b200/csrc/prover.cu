@@ -112,6 +112,11 @@ struct csg_ctx {
         n = trace_len; logn = ilog2(n); b = o->blowup_factor; ce = air.ce_blowup(); lde_n = n * b;
         if (ce > b) throw ArgError("blowup factor is smaller than the constraint evaluation blowup of this AIR");
         if (logn > 22) throw ArgError("trace length above 2^22 is not supported");
+        {   // the FRI remainder layer is committed as rows of 4: it needs at least 2 rows
+            size_t m = lde_n;
+            while (m > o->fri_max_remainder_size) m /= 4;
+            if (m < 8) throw ArgError("FRI remainder would have fewer than 8 elements: raise fri_max_remainder_size");
+        }
         if (air.num_constraints() > (size_t)CONS_MAX_CONSTRAINTS || air.periodic.size() > (size_t)CONS_MAX_PERIODIC ||
             air.assertions.size() > (size_t)CONS_MAX_ASSERTIONS)
             throw ArgError("AIR exceeds the compiled table sizes");

@@ -214,3 +214,30 @@ def test_device_witness_matches_host_builder(csg, oracle, num_tx):
         assert bad.size == 0, f"first differing (column, row): {bad[0]}"
         proof = c.prove_loaded()
     assert proof == oracle.prove(oracle.AIR_TRANSACTION, want, pub, oracle.options())
+
+
+@pytest.mark.parametrize("num_queries,grinding,max_remainder,blowup", [(8, 0, 256, 4), (100, 0, 64, 8), (42, 8, 1024, 16), (1, 4, 16, 4), (27, 0, 16, 16)])
+def test_proof_options_are_honoured(ctx, oracle, csg, num_queries, grinding, max_remainder, blowup):
+    # ProofOptions::new(num_queries, blowup, grinding, hash, extension, folding, max_remainder) (src/lib.rs:78-86): every field
+    # that changes the proof must change it the same way on both sides
+    trace, pub = csg.build_rescue_trace(np.arange(42, 49, dtype=np.uint64), 32)
+    want = oracle.prove(oracle.AIR_RESCUE, trace, pub, oracle.options(num_queries=num_queries, blowup=blowup, grinding=grinding, max_remainder=max_remainder))
+    got = ctx.prove(csg.AIR_RESCUE, trace, pub, csg.ProofOptions(num_queries=num_queries, blowup_factor=blowup, grinding_factor=grinding,
+                                                                   fri_max_remainder_size=max_remainder))
+    assert_same_proof(got, want)
+    assert csg.verify(csg.AIR_RESCUE, pub, got) == 0 and oracle.verify(oracle.AIR_RESCUE, pub, got) == 0
+
+
+def test_degenerate_shapes_fail_cleanly(ctx, csg):
+    trace, pub = csg.build_rescue_trace(np.arange(42, 49, dtype=np.uint64), 1)      # 8 rows: 32 LDE points < 42 queries
+    with pytest.raises(csg.CsgError, match="query positions"):
+        ctx.prove(csg.AIR_RESCUE, trace, pub, csg.ProofOptions(blowup_factor=4))
+    with pytest.raises(csg.CsgError):
+        ctx.prove(csg.AIR_RESCUE, trace[:, :6], pub, csg.ProofOptions(blowup_factor=4))  # not a power of two
+    with pytest.raises(csg.CsgError):
+        ctx.prove(csg.AIR_RANGE, *csg.build_range_trace(1), csg.ProofOptions(field_extension=3))   # cubic extension: not implemented
+    with pytest.raises(csg.CsgError, match="remainder"):
+        ctx.prove(csg.AIR_RESCUE, *csg.build_rescue_trace(np.arange(42, 49, dtype=np.uint64), 32), csg.ProofOptions(blowup_factor=32, fri_max_remainder_size=4))
+    # the context stays usable after errors
+    t, p = csg.build_range_trace(123)
+    assert csg.verify(csg.AIR_RANGE, p, ctx.prove(csg.AIR_RANGE, t, p, csg.ProofOptions())) == 0
