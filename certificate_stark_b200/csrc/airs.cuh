@@ -87,20 +87,25 @@ struct CombT {
     const fe *xp;        // x^adj per degree group, element g at xp[g * xp_stride]   (combined mode only)
     size_t xp_stride;
     f63::acc192 sum;
-    f63::acc192 part[SPLIT ? MAX_SPLIT_GROUPS : 1];
+    // split mode: the 192-bit accumulator of B_g lives in memory (shared memory on the device), word k at
+    // part[(3 * g + k) * part_stride] -- the group of a slot is only known at run time, and a register file cannot be indexed
+    uint64_t *part;
+    size_t part_stride;
     CSG_HD fe coef(int slot) const { return slot_coefficient(alpha, beta, group, xp, xp_stride, slot); }
     CSG_HD void add(int slot, fe v) {
         if (!SPLIT) { sum.mac(coef(slot), v); return; }
         sum.mac(alpha[slot], v);
-        const fe bv = beta[slot];
-        switch (group[slot]) {   // uniform across the warp: every thread works on the same slot
-        case 0: part[0].mac(bv, v); break;
-        case 1: part[SPLIT ? 1 : 0].mac(bv, v); break;
-        case 2: part[SPLIT ? 2 : 0].mac(bv, v); break;
-        case 3: part[SPLIT ? 3 : 0].mac(bv, v); break;
-        case 4: part[SPLIT ? 4 : 0].mac(bv, v); break;
-        default: part[SPLIT ? 5 : 0].mac(bv, v); break;
-        }
+        uint64_t *q = part + (size_t)group[slot] * 3 * part_stride;
+        f63::acc192 t;
+        t.lo = q[0]; t.mid = q[part_stride]; t.hi = q[2 * part_stride];
+        t.mac(beta[slot], v);
+        q[0] = t.lo; q[part_stride] = t.mid; q[2 * part_stride] = t.hi;
+    }
+    CSG_HD fe part_value(int g) const {   // split mode: B_g, reduced
+        const uint64_t *q = part + (size_t)g * 3 * part_stride;
+        f63::acc192 t;
+        t.lo = q[0]; t.mid = q[part_stride]; t.hi = q[2 * part_stride];
+        return t.reduce();
     }
 };
 using Comb = CombT<false>;

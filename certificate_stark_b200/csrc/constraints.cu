@@ -81,7 +81,7 @@ cons_item_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, con
     const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
     if (i >= n) return;
     RowCtx r = row_setup(A, lde, W, ptab, kc, i, xp_s);
-    airs::Comb C{A->alpha, A->beta, A->group, &xp_s[0][threadIdx.x], (size_t)CONS_THREADS, acc192()};
+    airs::Comb C{A->alpha, A->beta, A->group, &xp_s[0][threadIdx.x], (size_t)CONS_THREADS, acc192(), nullptr, 0};
     if (KIND == 0) airs::eval_rescue_item<AIR>((int)item, r.f, r.pv, C);
     else if (KIND == 1) airs::eval_ecc_bank<AIR>((int)item, r.f, r.pv, C);
     else airs::eval_ecc_final<AIR>(r.f, r.pv, C);
@@ -97,7 +97,7 @@ cons_rest_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, con
     const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
     if (i >= n) return;
     RowCtx r = row_setup(A, lde, W, ptab, kc, i, xp_s);
-    airs::Comb C{A->alpha, A->beta, A->group, &xp_s[0][threadIdx.x], (size_t)CONS_THREADS, acc192()};
+    airs::Comb C{A->alpha, A->beta, A->group, &xp_s[0][threadIdx.x], (size_t)CONS_THREADS, acc192(), nullptr, 0};
     airs::eval_rest<AIR>(r.f, r.pv, C);
     fe t = C.sum.reduce();
     for (unsigned p = 0; p < nparts; p++) t = add(t, part[((unsigned long long)p * A->ncosets + kc) * n + i]);
@@ -137,23 +137,14 @@ cons_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, cons
     const fe *base = lde + A->lde_coset_stride[kc];
     airs::Frame f{base + i, base + inext, (size_t)A->col_stride};
     airs::Periodic pv{ptab + kc * A->ptab_coset_stride, A->poff, A->pmask, (uint32_t)i};
-    airs::SplitComb C{A->alpha, A->beta, A->group, nullptr, 0, acc192(), {}};
+    __shared__ uint64_t part_s[3 * airs::MAX_SPLIT_GROUPS][CONS_THREADS];   // the per-group beta accumulators of this thread: one column
+    for (unsigned k = 0; k < 3 * (NP - 1); k++) part_s[k][threadIdx.x] = 0;
+    airs::SplitComb C{A->alpha, A->beta, A->group, nullptr, 0, acc192(), &part_s[0][threadIdx.x], (size_t)CONS_THREADS};
     if (KIND == 0) airs::eval_rescue_item<AIR>((int)blockIdx.z, f, pv, C);
     else airs::eval_rest<AIR>(f, pv, C);
     fe *dst = low + (((unsigned long long)item * NP) * L + j) * n + i;
     dst[0] = C.sum.reduce();
-    for (unsigned g = 0; g + 1 < NP; g++) {
-        fe v;
-        switch (g) {   // static indices keep the accumulators in registers
-        case 0: v = C.part[0].reduce(); break;
-        case 1: v = C.part[1].reduce(); break;
-        case 2: v = C.part[2].reduce(); break;
-        case 3: v = C.part[3].reduce(); break;
-        case 4: v = C.part[4].reduce(); break;
-        default: v = C.part[5].reduce(); break;
-        }
-        dst[(unsigned long long)(1 + g) * L * n] = v;
-    }
+    for (unsigned g = 0; g + 1 < NP; g++) dst[(unsigned long long)(1 + g) * L * n] = C.part_value((int)g);
 }
 
 // T(x) from its pieces on every ce coset, then divisors and boundary constraints.

@@ -123,7 +123,7 @@ fe eval_merged(const AirDesc &air, const TransitionGroups &tg, const std::vector
     std::vector<fe> pvp(pv); pvp.push_back(0);
     airs::Frame f{m.data(), m.data() + 1, 2};
     airs::Periodic Pv{pvp.data(), off.data(), mask.data(), 0};
-    airs::Comb C{alpha.data(), beta.data(), tg.group_of.data(), xp.data(), 1, acc192()};
+    airs::Comb C{alpha.data(), beta.data(), tg.group_of.data(), xp.data(), 1, acc192(), nullptr, 0};
     airs::eval_transition<AIR>(f, Pv, C);
     return C.sum.reduce();
 }

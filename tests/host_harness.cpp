@@ -56,15 +56,16 @@ static void check_eval(const csg::AirDesc &d, air_t *o) {
         for (size_t c = 0; c <= np; c++) off[c] = (uint32_t)c;
         airs::Frame f{m.data(), m.data() + 1, 2};
         airs::Periodic P{pv.data(), off.data(), mask.data(), 0};
-        airs::Comb C{alpha.data(), beta.data(), tg.group_of.data(), xp.data(), 1, f63::acc192()};
+        airs::Comb C{alpha.data(), beta.data(), tg.group_of.data(), xp.data(), 1, f63::acc192(), nullptr, 0};
         airs::eval_transition<AIR>(f, P, C);
         fe got = C.sum.reduce();
         CHECK(got == expect, "air %d rep %d: fused evaluation %016llx != oracle %016llx", AIR, rep, (unsigned long long)got, (unsigned long long)expect);
         // split mode: T = A + sum_g x^adj_g * B_g with the alpha and per-group beta parts accumulated separately
-        airs::SplitComb S{alpha.data(), beta.data(), tg.group_of.data(), nullptr, 0, f63::acc192(), {}};
+        std::vector<uint64_t> parts(3 * airs::MAX_SPLIT_GROUPS, 0);
+        airs::SplitComb S{alpha.data(), beta.data(), tg.group_of.data(), nullptr, 0, f63::acc192(), parts.data(), 1};
         airs::eval_transition<AIR>(f, P, S);
         fe t = S.sum.reduce();
-        for (size_t g = 0; g < tg.adj.size(); g++) t = f63::add(t, f63::mul(xp[g], S.part[g].reduce()));
+        for (size_t g = 0; g < tg.adj.size(); g++) t = f63::add(t, f63::mul(xp[g], S.part_value((int)g)));
         CHECK(t == expect, "air %d rep %d: split evaluation differs from the oracle", AIR, rep);
     }
 }
