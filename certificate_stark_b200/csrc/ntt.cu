@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
     const fe *preA = a.preA ? a.preA + blockIdx.z * a.pre_bz : nullptr;
     const fe *preB = a.preB ? a.preB + blockIdx.z * a.pre_bz : nullptr;
     const bool lane_fast_in = a.in_sl == 1 && T > 1;
+#pragma unroll 8   // several global loads in flight per thread: the staging phase is latency-bound otherwise
     for (unsigned idx = tid; idx < S * T; idx += nth) {
         unsigned e, l;
         if (lane_fast_in) { l = idx & (T - 1); e = idx >> a.logT; } else { e = idx & (S - 1); l = idx >> a.logS; }
@@ -136,11 +137,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
 void launch_pass(const PassArgs &a, unsigned ncols, unsigned ncosets, Stream &st) {
     const unsigned S = 1u << a.logS, T = 1u << a.logT;
     size_t smem = ((size_t)T * lane_pitch(S) + S / 2 + 1) * sizeof(fe);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (smem > 48 * 1024)   // per device and cheap: set whenever a launch needs more than the default 48 KB
         CSG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
-    }
     unsigned threads = NTT_THREADS;
     while (threads > 32 && threads > (S * T) / 8) threads >>= 1;
     dim3 grid((a.nlanes + T - 1) / T, ncols, ncosets);
