@@ -43,7 +43,7 @@ class ProofOptions(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d", "lde", "commit_trace", "constraints", "composition", "ood_deep", "fri", "queries", "total")] + \
-               [("kernel_launches", C.c_uint64)] + [(n, C.c_float) for n in ("cons_rescue", "cons_ecc_banks", "cons_ecc_final", "cons_rest")]
+               [("kernel_launches", C.c_uint64)] + [(n, C.c_float) for n in ("cons_rescue", "cons_ecc_banks", "cons_ecc_final", "cons_rest", "comm")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -86,6 +86,8 @@ def lib() -> C.CDLL:
         "csg_open_fri_layer": (C.c_int, [vp, C.c_size_t, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
         "csg_verify": (C.c_int, [C.c_int, _u64p, C.c_size_t, _u8p, C.c_size_t]),
         "csg_get_timings": (C.c_int, [vp, C.POINTER(Timings)]),
+        "csg_dist_unique_id": (C.c_int, [_u8p]), "csg_dist_init": (C.c_int, [vp, C.c_int, C.c_int, _u8p]),
+        "csg_dist_init_local": (C.c_int, [C.POINTER(vp), C.c_int]), "csg_dist_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "csg_timer_start": (C.c_int, [vp]), "csg_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "csg_tx_batch_new": (vp, [C.c_uint64, C.c_size_t, C.c_uint]), "csg_tx_batch_free": (None, [vp]), "csg_tx_batch_size": (C.c_size_t, [vp]),
         "csg_tx_batch_roots": (None, [vp, _u64p, _u64p]),
@@ -158,6 +160,27 @@ class Context:
         proof = C.string_at(out, n.value)
         lib().csg_free(out)
         return proof
+
+    # ---- one proof sharded over several GPUs by LDE coset (csg.h, csg_dist_*)
+    def dist_init(self, rank: int, world: int, unique_id: bytes):
+        """attach to a group of `world` contexts in `world` processes (NCCL); unique_id from dist_unique_id() on rank 0"""
+        buf = np.frombuffer(unique_id, dtype=np.uint8).copy()
+        if buf.size != 128:
+            raise CsgError("an NCCL unique id has 128 bytes")
+        self._check(lib().csg_dist_init(self._h, rank, world, _p8(buf)))
+
+    def dist_init_torch(self):
+        """attach to the torch.distributed world: rank 0 creates the NCCL id, broadcast through the default process group"""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.dist_init(rank, world, box[0])
+
+    def dist_info(self):
+        r, w = C.c_int(), C.c_int()
+        lib().csg_dist_info(self._h, C.byref(r), C.byref(w))
+        return r.value, w.value
 
     # ---- level 1: Prover::prove(trace)
     def prove(self, air_id: int, trace: np.ndarray, pub: np.ndarray, options: ProofOptions) -> bytes:
@@ -250,6 +273,64 @@ class Context:
         ms = (C.c_float * 4)()
         self._check(lib().csg_k_sweep(self._h, width, n, blowup, hash_fn, iters, ms))
         return dict(zip(("lde_ms", "hash_rows_ms", "merkle_ms", "fri_fold_ms"), [float(v) for v in ms]))
+
+
+def dist_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 of a sharded proof calls it and hands the bytes to the other ranks)"""
+    buf = np.zeros(128, dtype=np.uint8)
+    if lib().csg_dist_unique_id(_p8(buf)):
+        raise CsgError("NCCL is not available (libnccl.so.2 could not be loaded)")
+    return buf.tobytes()
+
+
+class LocalGroup:
+    """`world` contexts of THIS process proving one trace together (csg_dist_init_local): one host thread per context, the
+    exchanges are peer copies.  devices: one CUDA device per context; they may repeat (all ranks on one GPU is how the
+    tests cover the sharded path on a single-GPU box)."""
+
+    def __init__(self, world: int, devices=None):
+        devices = list(devices) if devices is not None else [0] * world
+        if len(devices) != world:
+            raise CsgError("one device per context")
+        self.ctxs = [Context(d) for d in devices]
+        arr = (C.c_void_p * world)(*[c._h for c in self.ctxs])
+        if lib().csg_dist_init_local(arr, world):
+            raise CsgError("cannot form a local group: " + lib().csg_last_error(self.ctxs[0]._h).decode())
+        self.world = world
+
+    def run(self, fn):
+        """fn(ctx, rank) on every context concurrently (the library calls block until the peers arrive); results by rank"""
+        import threading
+        out, err = [None] * self.world, [None] * self.world
+
+        def work(r):
+            try:
+                out[r] = fn(self.ctxs[r], r)
+            except BaseException as e:   # noqa: BLE001 - re-raised below
+                err[r] = e
+        ts = [threading.Thread(target=work, args=(r,)) for r in range(self.world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+    def prove(self, air_id, trace, pub, options):
+        """every context's proof bytes (all equal to the single-GPU proof)"""
+        return self.run(lambda ctx, r: ctx.prove(air_id, trace, pub, options))
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 # ---------------------------------------------------------------------------------------------- witness builders (host)

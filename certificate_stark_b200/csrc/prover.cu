@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/csg.h"
+#include "comm.cuh"
 #include "commit.cuh"
 #include "constraints.cuh"
 #include "hash.cuh"
@@ -73,13 +74,20 @@ struct csg_ctx {
     size_t n = 0, b = 0, ce = 0, lde_n = 0;
     unsigned logn = 0;
     std::vector<fe> lde_shift, ce_shift;   // s_k = offset * w_lde^k ; ce cosets are the LDE cosets k = kc * (b / ce)
+    // coset-sharded proof (comm.cuh): this context owns the LDE cosets [k0, k0 + bl) and the ce cosets among them; with
+    // no communicator G = 1 and it owns everything.  lde_shift / ce_shift hold the OWNED cosets only.
+    std::unique_ptr<Comm> comm;
+    size_t G = 1, rank = 0, bl = 0, k0 = 0, cel = 0, kc0 = 0;
+    DBuf<uint64_t> d_gather;               // slices under exchange
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> comm_ev;
+    size_t comm_used = 0;
 
     DBuf<uint64_t> d_io, d_wit_in;
     DBuf<fe> d_wit_finals;
     std::vector<uint64_t> wit_packed;
     const csg_tx_batch *wit_packed_for = nullptr;
     DBuf<uint32_t> d_idx, d_dig;
-    DBuf<fe> d_parts, d_polys, d_lde, d_comb, d_e, d_cpolys, d_clde, d_abc, d_abc_lde, d_deep, d_ptab, d_apoly;
+    DBuf<fe> d_parts, d_polys, d_lde, d_comb, d_e, d_eg, d_cpolys, d_clde, d_abc, d_abc_lde, d_deep, d_ptab, d_apoly;
     DBuf<uint32_t> d_tnodes, d_cnodes;
     DBuf<ConsArgs> d_cargs;
     std::unique_ptr<ConsArgs> h_cargs;
@@ -111,6 +119,9 @@ struct csg_ctx {
         opt = *o;
         n = trace_len; logn = ilog2(n); b = o->blowup_factor; ce = air.ce_blowup(); lde_n = n * b;
         if (ce > b) throw ArgError("blowup factor is smaller than the constraint evaluation blowup of this AIR");
+        G = comm ? (size_t)comm->world : 1; rank = comm ? (size_t)comm->rank : 0;
+        if (G > b || b % G) throw ArgError("the number of ranks of a sharded proof must divide the blowup factor");
+        bl = b / G; k0 = rank * bl;
         if (logn > 22) throw ArgError("trace length above 2^22 is not supported");
         {   // the FRI remainder layer is committed as rows of 4: it needs at least 2 rows
             size_t m = lde_n;
@@ -125,13 +136,19 @@ struct csg_ctx {
         if (tg.adj.size() > (size_t)CONS_MAX_GROUPS || bg.groups.size() > (size_t)CONS_MAX_BGROUPS) throw ArgError("too many constraint groups");
         roots.build(logn, st);
         const fe offset = to_mont(GENERATOR), w_lde = root_of_unity(ilog2(lde_n));
-        lde_shift.resize(b);
+        std::vector<fe> all_shift(b);
         fe acc = offset;
-        for (size_t k = 0; k < b; k++) { lde_shift[k] = acc; acc = mul(acc, w_lde); }
-        ce_shift.resize(ce);
-        for (size_t kc = 0; kc < ce; kc++) ce_shift[kc] = lde_shift[kc * (b / ce)];
+        for (size_t k = 0; k < b; k++) { all_shift[k] = acc; acc = mul(acc, w_lde); }
+        lde_shift.assign(all_shift.begin() + k0, all_shift.begin() + k0 + bl);
+        ce_shift.clear();
+        kc0 = 0;
+        for (size_t kc = 0; kc < ce; kc++) {
+            const size_t k = kc * (b / ce);
+            if (k >= k0 && k < k0 + bl) { if (ce_shift.empty()) kc0 = kc; ce_shift.push_back(all_shift[k]); }
+        }
+        cel = ce_shift.size();
         build_periodic_tables();
-        lde_tables.build(lde_shift.data(), b, logn, st);
+        lde_tables.build(lde_shift.data(), bl, logn, st);
         nfri = 0;
         stage = S_AIR;
     }
@@ -152,7 +169,7 @@ struct csg_ctx {
             total += P;
         }
         A.ptab_coset_stride = total;
-        d_ptab.reserve((total ? total : 1) * ce);
+        d_ptab.reserve((total ? total : 1) * (cel ? cel : 1));
         std::vector<bool> done(np, false);
         DBuf<fe> vals, coef;
         for (size_t c0 = 0; c0 < np; c0++) {
@@ -167,9 +184,9 @@ struct csg_ctx {
             vals.reserve(nc * P); coef.reserve(nc * P);
             CSG_CUDA(cudaMemcpyAsync(vals.p, host.data(), nc * P * sizeof(fe), cudaMemcpyHostToDevice, st.s));
             intt_columns(roots, ntt, vals.p, P, coef.p, P, nc, ilog2(P), st);
-            std::vector<fe> shifts(ce);
-            for (size_t kc = 0; kc < ce; kc++) shifts[kc] = f63::pow(ce_shift[kc], n / P);
-            coset_ntt_columns(roots, ntt, coef.p, P, d_ptab.p + A.poff[c0], P, total, nc, ilog2(P), shifts.data(), ce, st);
+            std::vector<fe> shifts(cel);
+            for (size_t kc = 0; kc < cel; kc++) shifts[kc] = f63::pow(ce_shift[kc], n / P);
+            if (cel) coset_ntt_columns(roots, ntt, coef.p, P, d_ptab.p + A.poff[c0], P, total, nc, ilog2(P), shifts.data(), cel, st);
             CSG_CUDA(cudaStreamSynchronize(st.s));   // host staging vector goes out of scope
         }
     }
@@ -207,39 +224,90 @@ struct csg_ctx {
         if (!host) need(S_TRACE, "csg_load_trace must be called first");
         else need(S_AIR, "csg_set_air must be called first");
         const size_t w = air.width;
-        const size_t CHUNK = host ? 8 : w;   // nothing to overlap when the trace is already resident: one chunk
+        // sharded proof: this context interpolates the column block [c_lo, c_hi), the coefficient blocks are all-gathered,
+        // and every context extends all columns onto its own cosets
+        const size_t cpr = (w + G - 1) / G, c_lo = std::min(w, rank * cpr), c_hi = std::min(w, c_lo + cpr), wpad = cpr * G;
+        const size_t CHUNK = host ? 8 : cpr;   // nothing to overlap when the trace is already resident: one chunk
         Timer &t = stage_timer;
         t.start(st);
-        d_io.reserve(w * n); d_polys.reserve(w * n); scratch.reserve(w * n); d_lde.reserve(w * lde_n);
+        d_io.reserve(w * n); d_polys.reserve(wpad * n); scratch.reserve(wpad * n); d_lde.reserve(w * n * bl);
         if (host) {
             if (!copy_stream) CSG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-            while (chunk_ev.size() < (w + CHUNK - 1) / CHUNK) { cudaEvent_t e; CSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); chunk_ev.push_back(e); }
+            while (chunk_ev.size() < (cpr + CHUNK - 1) / CHUNK + 1) { cudaEvent_t e; CSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); chunk_ev.push_back(e); }
             // the copies must not overtake earlier work on the proving stream that still reads d_io
             CSG_CUDA(cudaEventRecord(chunk_ev[0], st.s));
             CSG_CUDA(cudaStreamWaitEvent(copy_stream, chunk_ev[0], 0));
-            for (size_t c0 = 0, k = 0; c0 < w; c0 += CHUNK, k++) {
-                const size_t nc = std::min(CHUNK, w - c0);
+            for (size_t c0 = c_lo, k = 0; c0 < c_hi; c0 += CHUNK, k++) {
+                const size_t nc = std::min(CHUNK, c_hi - c0);
                 CSG_CUDA(cudaMemcpyAsync(d_io.p + c0 * n, host + c0 * n, nc * n * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
                 CSG_CUDA(cudaEventRecord(chunk_ev[k], copy_stream));
             }
         }
-        for (size_t c0 = 0, k = 0; c0 < w; c0 += CHUNK, k++) {
-            const size_t nc = std::min(CHUNK, w - c0);
+        for (size_t c0 = c_lo, k = 0; c0 < c_hi; c0 += CHUNK, k++) {
+            const size_t nc = std::min(CHUNK, c_hi - c0);
             if (host) CSG_CUDA(cudaStreamWaitEvent(st.s, chunk_ev[k], 0));
             to_montgomery(d_io.p + c0 * n, d_polys.p + c0 * n, nc * n, st);
             intt_columns(roots, ntt, d_polys.p + c0 * n, n, scratch.p + c0 * n, n, nc, logn, st);
-            coset_ntt_columns(roots, ntt, scratch.p + c0 * n, n, d_lde.p + c0 * n, n, w * n, nc, logn, lde_tables, st);
+            if (G == 1) coset_ntt_columns(roots, ntt, scratch.p + c0 * n, n, d_lde.p + c0 * n, n, w * n, nc, logn, lde_tables, st);
+        }
+        if (G > 1) {
+            gather(scratch.p, cpr * n * sizeof(fe));
+            coset_ntt_columns(roots, ntt, scratch.p, n, d_lde.p, n, w * n, w, logn, lde_tables, st);
         }
         std::swap(d_polys.p, scratch.p); std::swap(d_polys.n, scratch.n);   // d_polys = coefficients
         if (host) { nfri = 0; tm.h2d = 0; }
         tm.lde = t.stop(st);
         t.start(st);
-        d_tnodes.reserve(16 * lde_n);
-        hash_rows(d_lde.p, (unsigned)w, n, (unsigned)b, w * n, n, (int)opt.hash_fn, d_tnodes.p + 8 * lde_n, st);
-        merkle_build(d_tnodes.p, lde_n, (int)opt.hash_fn, st);
+        commit_rows(d_lde.p, (unsigned)w, w * n, d_tnodes);
         download_root(d_tnodes, root);
         tm.commit_trace = t.stop(st);
         stage = S_COMMITTED;
+    }
+
+    // ------------------------------------------------------------------------------------------ exchanges of a sharded proof
+    void comm_events() {
+        if (comm_ev.size() == comm_used) {
+            cudaEvent_t a, e;
+            CSG_CUDA(cudaEventCreate(&a)); CSG_CUDA(cudaEventCreate(&e));
+            comm_ev.emplace_back(a, e);
+        }
+    }
+    void gather(void *buf, size_t bytes) {
+        comm_events();
+        CSG_CUDA(cudaEventRecord(comm_ev[comm_used].first, st.s));
+        comm->all_gather(buf, bytes, st);
+        CSG_CUDA(cudaEventRecord(comm_ev[comm_used++].second, st.s));
+    }
+    void reduce_rows(uint64_t *buf, size_t count) {
+        comm_events();
+        CSG_CUDA(cudaEventRecord(comm_ev[comm_used].first, st.s));
+        comm->all_reduce_sum_u64(buf, count, st);
+        CSG_CUDA(cudaEventRecord(comm_ev[comm_used++].second, st.s));
+    }
+    float comm_ms() {
+        float total = 0;
+        for (size_t i = 0; i < comm_used; i++) {
+            float ms = 0;
+            CSG_CUDA(cudaEventSynchronize(comm_ev[i].second));
+            CSG_CUDA(cudaEventElapsedTime(&ms, comm_ev[i].first, comm_ev[i].second));
+            total += ms;
+        }
+        return total;
+    }
+    // Row digests of a coset-major matrix into the leaves of `nodes`, then the tree.  Sharded: each context hashes the rows
+    // of its cosets, the digests are all-gathered and put in natural order, and every context builds the whole tree --
+    // 2^23 leaves take 0.35 ms, less than the second exchange that per-GPU subtrees would need to answer the queries.
+    void commit_rows(const fe *data, unsigned width, size_t coset_stride, DBuf<uint32_t> &nodes) {
+        const int hf = (int)opt.hash_fn;
+        nodes.reserve(16 * lde_n);
+        if (G == 1) hash_rows(data, width, n, (unsigned)b, coset_stride, n, hf, nodes.p + 8 * lde_n, st);
+        else {
+            d_gather.reserve(4 * lde_n);
+            hash_rows(data, width, n, (unsigned)bl, coset_stride, n, hf, (uint32_t *)d_gather.p + 8 * rank * bl * n, st);
+            gather(d_gather.p, bl * n * 32);
+            interleave_slices(d_gather.p, (uint64_t *)(nodes.p + 8 * lde_n), n, (unsigned)bl, (unsigned)G, 4, st);
+        }
+        merkle_build(nodes.p, lde_n, hf, st);
     }
 
     // ------------------------------------------------------------------------------------------ stage 3
@@ -249,7 +317,7 @@ struct csg_ctx {
         t.start(st);
         ConsArgs &A = *h_cargs;
         const fe g = root_of_unity(logn);
-        A.logn = logn; A.ncosets = (unsigned)ce; A.col_stride = n; A.width = air.width;
+        A.logn = logn; A.ncosets = (unsigned)cel; A.col_stride = n; A.width = air.width;
         A.g_last = f63::pow(g, n - 1);
         A.nconstraints = (unsigned)air.num_constraints(); A.ngroups = (unsigned)tg.adj.size();
         for (size_t i = 0; i < air.num_constraints(); i++) { A.alpha[i] = t_ab[2 * i]; A.beta[i] = t_ab[2 * i + 1]; A.group[i] = tg.group_of[i]; }
@@ -258,9 +326,9 @@ struct csg_ctx {
         for (size_t gi = 0; gi < bg.groups.size(); gi++) {
             A.b_adj_mod[gi] = bg.groups[gi].adj % n; A.b_steps[gi] = bg.groups[gi].num_steps; A.b_offset[gi] = bg.groups[gi].offset;
         }
-        for (size_t kc = 0; kc < ce; kc++) {
+        for (size_t kc = 0; kc < cel; kc++) {
             const fe s = ce_shift[kc];
-            A.lde_coset_stride[kc] = (unsigned long long)(kc * (b / ce)) * air.width * n;
+            A.lde_coset_stride[kc] = (unsigned long long)((kc0 + kc) * (b / ce) - k0) * air.width * n;
             A.shift[kc] = s;
             A.zinv[kc] = inv(sub(f63::pow(s, n), ONE));
             for (size_t gi = 0; gi < tg.adj.size(); gi++) A.shift_adj[kc][gi] = f63::pow(s, tg.adj[gi]);
@@ -287,11 +355,14 @@ struct csg_ctx {
         if (!polys.empty()) CSG_CUDA(cudaMemcpyAsync(d_apoly.p, polys.data(), polys.size() * sizeof(fe), cudaMemcpyHostToDevice, st.s));
         d_cargs.reserve(1);
         CSG_CUDA(cudaMemcpyAsync(d_cargs.p, &A, sizeof A, cudaMemcpyHostToDevice, st.s));
-        d_comb.reserve(ce * n);
-        d_parts.reserve(constraint_scratch_elements(air.id, n, ce));
+        d_comb.reserve((cel ? cel : 1) * n);
+        d_parts.reserve(constraint_scratch_elements(air.id, n, cel ? cel : 1));
         if (!cons_ev[0]) for (auto &e : cons_ev) CSG_CUDA(cudaEventCreate(&e));
-        csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st, cons_ev,
-                              split_low_degree ? &roots : nullptr, split_low_degree ? &ntt : nullptr);
+        // the low-degree split interpolates across the even cosets: only when this context owns all of them
+        const bool split = split_low_degree && G == 1;
+        if (cel) csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st, cons_ev,
+                                       split ? &roots : nullptr, split ? &ntt : nullptr);
+        else for (auto &e : cons_ev) CSG_CUDA(cudaEventRecord(e, st.s));
         tm.constraints = t.stop(st);   // also keeps `polys` alive until the copy has completed
         float *parts_ms[4] = {&tm.cons_rescue, &tm.cons_ecc_banks, &tm.cons_ecc_final, &tm.cons_rest};
         for (int k = 0; k < 4; k++) CSG_CUDA(cudaEventElapsedTime(parts_ms[k], cons_ev[k], cons_ev[k + 1]));
@@ -316,21 +387,31 @@ struct csg_ctx {
         Timer &t = stage_timer;
         t.start(st);
         // per-coset interpolants, divided by s_kc^m; then the cross-coset step yields the ce column polynomials
-        std::vector<fe> sinv(ce);
-        for (size_t kc = 0; kc < ce; kc++) sinv[kc] = inv(ce_shift[kc]);
+        std::vector<fe> sinv(cel);
+        for (size_t kc = 0; kc < cel; kc++) sinv[kc] = inv(ce_shift[kc]);
         d_e.reserve(ce * n); d_cpolys.reserve(ce * n);
-        coset_intt_columns(roots, ntt, d_comb.p, n, d_e.p, n, logn, sinv.data(), ce, st);
+        const fe *e_all = d_e.p;
+        if (G == 1) coset_intt_columns(roots, ntt, d_comb.p, n, d_e.p, n, logn, sinv.data(), ce, st);
+        else {
+            // every context interpolates on its ce cosets; the slices are all-gathered ("composition slices") and each context
+            // runs the small cross-coset step itself.  With more ranks than ce cosets the idle ranks contribute a dummy slice.
+            const size_t slot = cel ? cel : 1;
+            d_eg.reserve(G * slot * n);
+            if (cel) coset_intt_columns(roots, ntt, d_comb.p, n, d_eg.p + rank * slot * n, n, logn, sinv.data(), cel, st);
+            gather(d_eg.p, slot * n * sizeof(fe));
+            if (G <= ce) e_all = d_eg.p;
+            else for (size_t kc = 0; kc < ce; kc++)
+                CSG_CUDA(cudaMemcpyAsync(d_e.p + kc * n, d_eg.p + kc * (G / ce) * n, n * sizeof(fe), cudaMemcpyDeviceToDevice, st.s));
+        }
         std::vector<fe> mat(ce * ce);
         const fe off_n_inv = inv(f63::pow(to_mont(GENERATOR), n)), ce_inv = inv(to_mont(ce)), w_ce_inv = inv(root_of_unity(ilog2(ce)));
         for (size_t tt = 0; tt < ce; tt++)
             for (size_t k = 0; k < ce; k++)
                 mat[tt * ce + k] = mul(mul(f63::pow(off_n_inv, tt), ce_inv), f63::pow(w_ce_inv, (k * tt) % ce));
-        composition_columns(d_e.p, d_cpolys.p, n, (unsigned)ce, mat.data(), st);
-        d_clde.reserve(ce * lde_n);
-        coset_ntt_columns(roots, ntt, d_cpolys.p, n, d_clde.p, n, ce * n, ce, logn, lde_shift.data(), b, st);
-        d_cnodes.reserve(16 * lde_n);
-        hash_rows(d_clde.p, (unsigned)ce, n, (unsigned)b, ce * n, n, (int)opt.hash_fn, d_cnodes.p + 8 * lde_n, st);
-        merkle_build(d_cnodes.p, lde_n, (int)opt.hash_fn, st);
+        composition_columns(e_all, d_cpolys.p, n, (unsigned)ce, mat.data(), st);
+        d_clde.reserve(ce * n * bl);
+        coset_ntt_columns(roots, ntt, d_cpolys.p, n, d_clde.p, n, ce * n, ce, logn, lde_shift.data(), bl, st);
+        commit_rows(d_clde.p, (unsigned)ce, ce * n, d_cnodes);
         download_root(d_cnodes, root);
         tm.composition = t.stop(st);
         stage = S_COMPOSED;
@@ -368,13 +449,19 @@ struct csg_ctx {
             a.bzg = add(a.bzg, mul(coef[w + c], ood_next[c]));
         }
         for (size_t r = 0; r < ce; r++) a.czm = add(a.czm, mul(comp_d[r], ood_comp[r]));
-        a.lambda = lambda; a.mu = mu; a.ncosets = (unsigned)b;
-        for (size_t k = 0; k < b; k++) a.shift[k] = lde_shift[k];
-        d_abc.reserve(3 * n); d_abc_lde.reserve(3 * lde_n); d_deep.reserve(lde_n);
+        a.lambda = lambda; a.mu = mu; a.ncosets = (unsigned)bl;
+        for (size_t k = 0; k < bl; k++) a.shift[k] = lde_shift[k];
+        d_abc.reserve(3 * n); d_abc_lde.reserve(3 * n * bl); d_deep.reserve(lde_n);
         combine_polys(d_polys.p, n, w, n, coef.data(), 2, d_abc.p, n, scratch2, st);
         combine_polys(d_cpolys.p, n, ce, n, comp_d, 1, d_abc.p + 2 * n, n, scratch, st);
-        coset_ntt_columns(roots, ntt, d_abc.p, n, d_abc_lde.p, n, 3 * n, 3, logn, lde_shift.data(), b, st);
-        deep_quotients(d_abc_lde.p, roots.W.p, n, a, d_deep.p, st);
+        coset_ntt_columns(roots, ntt, d_abc.p, n, d_abc_lde.p, n, 3 * n, 3, logn, lde_shift.data(), bl, st);
+        if (G == 1) deep_quotients(d_abc_lde.p, roots.W.p, n, a, d_deep.p, st);
+        else {   // own rows as [i][kl], all-gather, natural order; FRI then runs whole on every context (layers are <= 64 MB)
+            d_gather.reserve(lde_n);
+            deep_quotients(d_abc_lde.p, roots.W.p, n, a, (fe *)d_gather.p + rank * bl * n, st);
+            gather(d_gather.p, bl * n * sizeof(fe));
+            interleave_slices(d_gather.p, (uint64_t *)d_deep.p, n, (unsigned)bl, (unsigned)G, 1, st);
+        }
         if (fri.empty()) fri.emplace_back(new FriLayer());
         nfri = 1;
         fri[0]->evals = d_deep.p; fri[0]->m = lde_n; fri[0]->committed = false;
@@ -425,19 +512,31 @@ struct csg_ctx {
     size_t num_fri_folds() const { size_t r = 0, d = lde_n; while (d > opt.fri_max_remainder_size) { d /= 4; r++; } return r; }
 
     // ------------------------------------------------------------------------------------------ stage 9
-    void upload_positions(const std::vector<size_t> &pos) {
-        std::vector<uint32_t> p32(pos.begin(), pos.end());
+    void upload_positions(const std::vector<uint32_t> &p32) {
         d_idx.reserve(std::max<size_t>(p32.size(), 4096));
         CSG_CUDA(cudaMemcpyAsync(d_idx.p, p32.data(), p32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st.s));
         CSG_CUDA(cudaStreamSynchronize(st.s));
     }
     // rows (canonical, row-major) of a coset-major matrix at the given natural positions
-    std::vector<uint64_t> open_rows(const fe *data, unsigned width, unsigned ncosets, size_t coset_stride, size_t col_stride, const std::vector<size_t> &pos) {
-        upload_positions(pos);
+    // sharded (the LDE matrices of a split proof): every context gathers the rows of its own cosets, zeros elsewhere, and the
+    // row buffers are summed across the ranks
+    std::vector<uint64_t> open_rows(const fe *data, unsigned width, unsigned ncosets, size_t coset_stride, size_t col_stride, const std::vector<size_t> &pos,
+                                    bool sharded = false) {
+        std::vector<uint32_t> p32(pos.begin(), pos.end());
+        sharded = sharded && G > 1;
+        if (sharded) {
+            for (auto &p : p32) {
+                const size_t k = p % b, i = p / b;
+                p = (k >= k0 && k < k0 + bl) ? (uint32_t)((k - k0) + bl * i) : 0xFFFFFFFFu;
+            }
+            ncosets = (unsigned)bl;
+        }
+        upload_positions(p32);
         std::vector<uint64_t> rows(pos.size() * width);
         // d_io still holds the resident trace for re-proving; rows go through a separate small buffer
         d_rows.reserve(std::max<size_t>(rows.size(), 1 << 16));
         gather_rows(data, width, ncosets, coset_stride, col_stride, d_idx.p, pos.size(), d_rows.p, st);
+        if (sharded) reduce_rows(d_rows.p, rows.size());
         CSG_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, rows.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st.s));
         CSG_CUDA(cudaStreamSynchronize(st.s));
         return rows;
@@ -484,6 +583,7 @@ struct csg_ctx {
         if (!host) need(S_TRACE, "csg_load_trace must be called first");
         auto t0 = std::chrono::steady_clock::now();
         const unsigned long long launches0 = st.launches;
+        comm_used = 0;
         const int hf = (int)opt.hash_fn;
         const size_t w = air.width, nc = air.num_constraints(), na = air.assertions.size();
         Bytes seed;
@@ -535,14 +635,14 @@ struct csg_ctx {
         pf.put(trace_root, 32); pf.put(comp_root, 32);
         for (auto &r : fri_roots) pf.put(r.data(), 32);
         {
-            std::vector<uint64_t> rows = open_rows(d_lde.p, (unsigned)w, (unsigned)b, w * n, n, pos);
+            std::vector<uint64_t> rows = open_rows(d_lde.p, (unsigned)w, (unsigned)b, w * n, n, pos, true);
             pf.u32((uint32_t)(rows.size() * 8));
             for (uint64_t v : rows) pf.u64(v);
             std::vector<uint8_t> paths = open_paths(d_tnodes, lde_n, pos);
             pf.u32((uint32_t)paths.size()); pf.put(paths.data(), paths.size());
         }
         {
-            std::vector<uint64_t> rows = open_rows(d_clde.p, (unsigned)ce, (unsigned)b, ce * n, n, pos);
+            std::vector<uint64_t> rows = open_rows(d_clde.p, (unsigned)ce, (unsigned)b, ce * n, n, pos, true);
             pf.u32((uint32_t)(rows.size() * 8));
             for (uint64_t v : rows) pf.u64(v);
             std::vector<uint8_t> paths = open_paths(d_cnodes, lde_n, pos);
@@ -580,6 +680,7 @@ struct csg_ctx {
         pf.u64(nonce);
         tm.queries = tq.stop(st);
         tm.kernel_launches = st.launches - launches0;
+        tm.comm = comm_ms();
         tm.total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
         *proof = (uint8_t *)malloc(pf.v.size());
@@ -626,6 +727,8 @@ void csg_destroy(csg_ctx *ctx) {
     if (ctx->ev_a) { cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); }
     for (auto e : ctx->cons_ev) if (e) cudaEventDestroy(e);
     for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+    for (auto &e : ctx->comm_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    ctx->comm.reset();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     cudaStreamDestroy(s);
@@ -705,14 +808,14 @@ int csg_open_trace(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_
         ctx->need(S_COMMITTED, "the trace must be committed first");
         std::vector<size_t> pos(positions, positions + npos);
         const size_t w = ctx->air.width;
-        copy_opening(ctx->open_rows(ctx->d_lde.p, (unsigned)w, (unsigned)ctx->b, w * ctx->n, ctx->n, pos), ctx->open_paths(ctx->d_tnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
+        copy_opening(ctx->open_rows(ctx->d_lde.p, (unsigned)w, (unsigned)ctx->b, w * ctx->n, ctx->n, pos, true), ctx->open_paths(ctx->d_tnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
     });
 }
 int csg_open_composition(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
     return guarded(ctx, [&] {
         ctx->need(S_COMPOSED, "the composition polynomial must be committed first");
         std::vector<size_t> pos(positions, positions + npos);
-        copy_opening(ctx->open_rows(ctx->d_clde.p, (unsigned)ctx->ce, (unsigned)ctx->b, ctx->ce * ctx->n, ctx->n, pos), ctx->open_paths(ctx->d_cnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
+        copy_opening(ctx->open_rows(ctx->d_clde.p, (unsigned)ctx->ce, (unsigned)ctx->b, ctx->ce * ctx->n, ctx->n, pos, true), ctx->open_paths(ctx->d_cnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
     });
 }
 int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
@@ -790,6 +893,44 @@ int csg_timer_stop(csg_ctx *ctx, float *ms) {
         CSG_CUDA(cudaEventSynchronize(ctx->ev_b));
         CSG_CUDA(cudaEventElapsedTime(ms, ctx->ev_a, ctx->ev_b));
     });
+}
+// ---- coset-sharded proofs: attach the context to a group of `world` contexts (one per GPU) before csg_set_air
+int csg_dist_unique_id(uint8_t id[128]) {
+    if (!id) return CSG_ERR_ARG;
+    try { nccl_unique_id(id); return CSG_OK; } catch (const std::exception &) { return CSG_ERR_UNSUPPORTED; }
+}
+static void check_world(int rank, int world) {
+    if (world < 1 || world > 32 || (world & (world - 1)) || rank < 0 || rank >= world) throw ArgError("world must be a power of two up to 32, rank below it");
+}
+int csg_dist_init(csg_ctx *ctx, int rank, int world, const uint8_t id[128]) {
+    return guarded(ctx, [&] {
+        check_world(rank, world);
+        if (!id) throw ArgError("null NCCL id");
+        CSG_CUDA(cudaStreamSynchronize(ctx->st.s));
+        ctx->comm.reset();
+        if (world > 1) ctx->comm = make_nccl_comm(rank, world, id);
+        ctx->stage = S_NONE;   // the coset ownership is fixed by csg_set_air
+    });
+}
+int csg_dist_init_local(csg_ctx **ctxs, int world) {
+    if (!ctxs) return CSG_ERR_ARG;
+    for (int r = 0; r < world; r++) if (!ctxs[r]) return CSG_ERR_ARG;
+    return guarded(ctxs[0], [&] {
+        check_world(0, world);
+        auto comms = make_local_comms(world);
+        for (int r = 0; r < world; r++) {
+            CSG_CUDA(cudaSetDevice(ctxs[r]->device));
+            CSG_CUDA(cudaStreamSynchronize(ctxs[r]->st.s));
+            ctxs[r]->comm.reset();
+            if (world > 1) ctxs[r]->comm = std::move(comms[r]);
+            ctxs[r]->stage = S_NONE;
+        }
+    });
+}
+int csg_dist_info(const csg_ctx *ctx, int *rank, int *world) {
+    if (!ctx || !rank || !world) return CSG_ERR_ARG;
+    *rank = ctx->comm ? ctx->comm->rank : 0; *world = ctx->comm ? ctx->comm->world : 1;
+    return CSG_OK;
 }
 int csg_get_timings(const csg_ctx *ctx, csg_timings *out) { if (!ctx || !out) return CSG_ERR_ARG; *out = ctx->tm; return CSG_OK; }
 

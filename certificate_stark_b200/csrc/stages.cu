@@ -167,6 +167,7 @@ __global__ void gather_rows_kernel(const fe *__restrict__ data, unsigned width, 
     unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= npos * width) return;
     unsigned r = t / width, c = t % width;
+    if (pos[r] == 0xFFFFFFFFu) { rows[t] = 0; return; }   // a row another context of a sharded proof owns
     unsigned long long j = pos[r], k = j % ncosets, i = j / ncosets;
     rows[t] = from_mont(data[k * coset_stride + c * col_stride + i]);
 }

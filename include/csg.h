@@ -97,6 +97,23 @@ int csg_open_trace(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_
 int csg_open_composition(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len);
 int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len);
 
+/* ---- one proof sharded over several GPUs by LDE coset (the reference has no multi-device path) -----------
+ * `world` contexts, one per GPU (world a power of two dividing the blowup factor), each owning blowup/world cosets of the
+ * LDE domain: column blocks are interpolated per context and the coefficients all-gathered; extension, row hashing,
+ * constraint evaluation, composition LDE and DEEP quotients run on the owned cosets only; leaf digests, per-coset
+ * composition interpolants and DEEP evaluations are all-gathered; trees and FRI are then built by every context, so every
+ * context follows the same transcript and returns the same proof bytes (identical to the single-GPU proof).
+ * After attaching, EVERY context of the group makes the same sequence of calls (csg_set_air .. csg_prove_loaded, or
+ * csg_prove) with the same arguments; calls block until the peers arrive.
+ *   csg_dist_init        one process per GPU (torchrun): NCCL; rank 0 creates the id with csg_dist_unique_id and the host
+ *                        distributes it (torch.distributed broadcast, MPI, a file)
+ *   csg_dist_init_local  one process, one host thread per context: peer copies; contexts may share a device (tests)
+ * world = 1 detaches. */
+int csg_dist_unique_id(uint8_t id[128]);
+int csg_dist_init(csg_ctx *ctx, int rank, int world, const uint8_t id[128]);
+int csg_dist_init_local(csg_ctx **ctxs, int world);
+int csg_dist_info(const csg_ctx *ctx, int *rank, int *world);
+
 /* per-stage device times of the last proof, milliseconds (CUDA events on the proving stream) */
 typedef struct {
     float h2d, lde, commit_trace, constraints, composition, ood_deep, fri, queries, total;
@@ -104,6 +121,7 @@ typedef struct {
     /* the four kernels of the constraint stage: Rescue residuals, scalar-multiplication banks, final point addition,
      * linear constraints + divisors + boundary terms (CUDA events between the launches) */
     float cons_rescue, cons_ecc_banks, cons_ecc_final, cons_rest;
+    float comm; /* sharded proofs: time inside the exchanges (all-gathers, row sums), already included in the stage times */
 } csg_timings;
 int csg_get_timings(const csg_ctx *ctx, csg_timings *out);
 /* CUDA events on the proving stream around an arbitrary sequence of calls (bench.py's timed region) */
