@@ -21,7 +21,7 @@ P = 0x4180000000000001  # f63 modulus (/root/reference/src/range/tests.rs:59)
 
 AIR_TRANSACTION, AIR_MERKLE_UPDATE, AIR_MERKLE_INIT, AIR_SCHNORR, AIR_RANGE, AIR_RESCUE = range(6)
 HASH_BLAKE3_256, HASH_SHA3_256 = 2, 3
-FIELD_EXTENSION_NONE = 1
+FIELD_EXTENSION_NONE, FIELD_EXTENSION_QUADRATIC, FIELD_EXTENSION_CUBIC = 1, 2, 3
 TRACE_WIDTH = {AIR_TRANSACTION: 94, AIR_MERKLE_UPDATE: 65, AIR_MERKLE_INIT: 58, AIR_SCHNORR: 56, AIR_RANGE: 2, AIR_RESCUE: 14}
 _ERRORS = {1: "invalid argument", 2: "CUDA error", 3: "call out of order", 4: "unsupported", 5: "random coin failure"}
 
@@ -80,7 +80,8 @@ def lib() -> C.CDLL:
         "csg_extend_and_commit_trace": (C.c_int, [vp, _u8p]), "csg_eval_constraints": (C.c_int, [vp, _u64p, _u64p]),
         "csg_commit_composition": (C.c_int, [vp, _u8p]), "csg_ood": (C.c_int, [vp, C.c_uint64, _u64p, _u64p, _u64p]),
         "csg_deep": (C.c_int, [vp, _u64p, _u64p, _u64p]), "csg_fri_commit_layer": (C.c_int, [vp, _u8p]),
-        "csg_fri_fold": (C.c_int, [vp, C.c_uint64]), "csg_fri_remainder": (C.c_int, [vp, _u64p, C.c_size_t, _szp]),
+        "csg_fri_fold": (C.c_int, [vp, C.c_uint64]), "csg_fri_fold_ext": (C.c_int, [vp, _u64p]),
+        "csg_ood_ext": (C.c_int, [vp, _u64p, _u64p, _u64p, _u64p]), "csg_fri_remainder": (C.c_int, [vp, _u64p, C.c_size_t, _szp]),
         "csg_open_trace": (C.c_int, [vp, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
         "csg_open_composition": (C.c_int, [vp, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
         "csg_open_fri_layer": (C.c_int, [vp, C.c_size_t, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),

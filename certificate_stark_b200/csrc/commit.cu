@@ -7,16 +7,20 @@ using namespace f63;
 
 namespace {
 
-template <int HASH>
+// SUB: column c lives at (c / sub) * col_stride + (c % sub) * sub_stride (rows of extension-field elements stored as planes)
+template <int HASH, bool SUB>
 __global__ void __launch_bounds__(128) hash_rows_kernel(const fe *__restrict__ data, unsigned width, unsigned long long n, unsigned ncosets,
                                                         unsigned long long coset_stride, unsigned long long col_stride,
-                                                        uint32_t *__restrict__ leaves) {
+                                                        uint32_t *__restrict__ leaves, unsigned sub, unsigned long long sub_stride) {
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned k = blockIdx.y;
     const fe *p = data + k * coset_stride + i;
     uint32_t d[8];
-    auto get = [&](uint32_t c) -> uint64_t { return from_mont(__ldg(p + c * col_stride)); };
+    auto get = [&](uint32_t c) -> uint64_t {
+        if (SUB) return from_mont(__ldg(p + (c / sub) * col_stride + (c % sub) * sub_stride));
+        return from_mont(__ldg(p + c * col_stride));
+    };
     if (HASH == hashes::SHA3_256) hashes::k3::hash_words64(get, width, d); else hashes::b3::hash_words64(get, width, d);
     uint4 *o = reinterpret_cast<uint4 *>(leaves + 8ULL * (k + (unsigned long long)ncosets * i));
     o[0] = make_uint4(d[0], d[1], d[2], d[3]);
@@ -68,15 +72,14 @@ __global__ void gather_digests_kernel(const uint32_t *nodes, const uint32_t *idx
 }  // namespace
 
 void hash_rows(const fe *data, unsigned width, size_t n, unsigned ncosets, size_t coset_stride, size_t col_stride, int hash_fn,
-               uint32_t *leaves, Stream &st) {
+               uint32_t *leaves, Stream &st, unsigned sub, size_t sub_stride) {
     if (width > 128) throw std::runtime_error("rows wider than one Blake3 chunk are not supported");
     dim3 grid((unsigned)((n + 127) / 128), ncosets);
-    if (hash_fn == hashes::SHA3_256)
-        CSG_LAUNCH(st, hash_rows_kernel<hashes::SHA3_256>, grid, 128, 0, data, width, (unsigned long long)n, ncosets,
-                   (unsigned long long)coset_stride, (unsigned long long)col_stride, leaves);
-    else
-        CSG_LAUNCH(st, hash_rows_kernel<hashes::BLAKE3_256>, grid, 128, 0, data, width, (unsigned long long)n, ncosets,
-                   (unsigned long long)coset_stride, (unsigned long long)col_stride, leaves);
+#define CSG_HASH_ROWS(H, S) CSG_LAUNCH(st, (hash_rows_kernel<H, S>), grid, 128, 0, data, width, (unsigned long long)n, ncosets, \
+                                       (unsigned long long)coset_stride, (unsigned long long)col_stride, leaves, sub, (unsigned long long)sub_stride)
+    if (hash_fn == hashes::SHA3_256) { if (sub > 1) CSG_HASH_ROWS(hashes::SHA3_256, true); else CSG_HASH_ROWS(hashes::SHA3_256, false); }
+    else { if (sub > 1) CSG_HASH_ROWS(hashes::BLAKE3_256, true); else CSG_HASH_ROWS(hashes::BLAKE3_256, false); }
+#undef CSG_HASH_ROWS
 }
 
 void merkle_build(uint32_t *nodes, size_t nleaves, int hash_fn, Stream &st) {

@@ -11,8 +11,9 @@ namespace csg {
 
 // digest of row j = k + ncosets*i of a coset-major matrix: elements data[k*coset_stride + c*col_stride + i], c < width,
 // hashed as canonical little-endian bytes.  Writes 8 words to leaves + 8*j.
+// sub > 1: column c lives at (c / sub) * col_stride + (c % sub) * sub_stride (extension-field elements stored as planes).
 void hash_rows(const fe *data, unsigned width, size_t n, unsigned ncosets, size_t coset_stride, size_t col_stride, int hash_fn,
-               uint32_t *leaves, Stream &st);
+               uint32_t *leaves, Stream &st, unsigned sub = 1, size_t sub_stride = 0);
 // interior nodes of the tree whose leaves are already in nodes[8*L ..)
 void merkle_build(uint32_t *nodes, size_t nleaves, int hash_fn, Stream &st);
 // out[8*t ..] = nodes[8*idx[t] ..]

@@ -10,6 +10,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "../ext.cuh"
 #include "../hash.cuh"
 
 namespace csg {
@@ -39,6 +40,19 @@ class Coin {
     // rejection-samples the first 8 bytes of successive outputs until they form a canonical element
     fe draw() {
         for (int i = 0; i < 1000; i++) { uint64_t v = next_u64(); if (v < f63::P) return f63::to_mont(v); }
+        throw std::runtime_error("random coin failed to draw a field element");
+    }
+    // an element of the degree-d extension: the first 8*d bytes of one output as d canonical words, the whole output
+    // rejected unless every word is below p (coin.draw::<E>())
+    f63::xe draw_x(int d) {
+        for (int i = 0; i < 1000; i++) {
+            uint8_t t[32];
+            counter_++; merge_with_int(counter_, t);
+            f63::xe r = f63::x_zero();
+            bool ok = true;
+            for (int j = 0; j < d && ok; j++) { uint64_t v; memcpy(&v, t + 8 * j, 8); if (v >= f63::P) ok = false; else r.c[j] = f63::to_mont(v); }
+            if (ok) return r;
+        }
         throw std::runtime_error("random coin failed to draw a field element");
     }
     std::vector<size_t> draw_integers(size_t count, size_t domain_size) {

@@ -16,6 +16,7 @@
 #include "comm.cuh"
 #include "commit.cuh"
 #include "constraints.cuh"
+#include "ext_stages.cuh"
 #include "hash.cuh"
 #include "host/air_desc.hpp"
 #include "host/transcript.hpp"
@@ -98,6 +99,12 @@ struct csg_ctx {
 
     fe z = 0;
     std::vector<fe> ood_cur, ood_next, ood_comp;
+    // FieldExtension::Quadratic / Cubic: d = 2 / 3; challenges, composition, OOD frame, DEEP and FRI are E-valued (ext_stages.cuh)
+    int d = 1;
+    ExtConsts xk{};
+    xe xz{};
+    std::vector<xe> xood_cur, xood_next, xood_comp;
+    DBuf<fe> d_pw;
     csg_timings tm{};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // csg_timer_start / csg_timer_stop
     cudaEvent_t cons_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -109,7 +116,7 @@ struct csg_ctx {
     // ------------------------------------------------------------------------------------------ setup
     void set_air(int air_id, size_t trace_len, const csg_options *o, const uint64_t *pub, size_t npub) {
         if (!o) throw ArgError("options missing");
-        if (o->field_extension != CSG_FIELD_EXT_NONE) throw ArgError("only FieldExtension::None is implemented");
+        if (o->field_extension < CSG_FIELD_EXT_NONE || o->field_extension > CSG_FIELD_EXT_CUBIC) throw ArgError("field extension must be None (1), Quadratic (2) or Cubic (3)");
         if (o->fri_folding_factor != 4) throw ArgError("only FRI folding factor 4 is implemented");
         if (o->hash_fn != CSG_HASH_BLAKE3_256 && o->hash_fn != CSG_HASH_SHA3_256) throw ArgError("hash function must be Blake3_256 or Sha3_256");
         if (o->num_queries == 0 || o->num_queries > 255 || o->grinding_factor >= 32) throw ArgError("num_queries in 1..255, grinding factor below 32");
@@ -117,6 +124,8 @@ struct csg_ctx {
         if (o->fri_max_remainder_size < 4 || (o->fri_max_remainder_size & (o->fri_max_remainder_size - 1))) throw ArgError("FRI remainder size must be a power of two");
         try { air = make_air(air_id, trace_len, pub, npub); } catch (const std::invalid_argument &e) { throw ArgError(e.what()); }
         opt = *o;
+        d = (int)o->field_extension;
+        if (d > 1) xk = ext_consts();
         n = trace_len; logn = ilog2(n); b = o->blowup_factor; ce = air.ce_blowup(); lde_n = n * b;
         if (ce > b) throw ArgError("blowup factor is smaller than the constraint evaluation blowup of this AIR");
         G = comm ? (size_t)comm->world : 1; rank = comm ? (size_t)comm->rank : 0;
@@ -311,7 +320,9 @@ struct csg_ctx {
     }
 
     // ------------------------------------------------------------------------------------------ stage 3
-    void eval_constraints(const fe *t_ab, const fe *b_ab) {
+    // plane: which component of the E-valued coefficients these are (0 for the base field); the merged column of component j
+    // lands in d_comb[j][ce coset][row]
+    void eval_constraints(const fe *t_ab, const fe *b_ab, int plane = 0) {
         need(S_COMMITTED, "the trace must be committed first");
         Timer &t = stage_timer;
         t.start(st);
@@ -355,18 +366,31 @@ struct csg_ctx {
         if (!polys.empty()) CSG_CUDA(cudaMemcpyAsync(d_apoly.p, polys.data(), polys.size() * sizeof(fe), cudaMemcpyHostToDevice, st.s));
         d_cargs.reserve(1);
         CSG_CUDA(cudaMemcpyAsync(d_cargs.p, &A, sizeof A, cudaMemcpyHostToDevice, st.s));
-        d_comb.reserve((cel ? cel : 1) * n);
+        const size_t comb_plane = (cel ? cel : 1) * n;
+        d_comb.reserve(comb_plane * d);
         d_parts.reserve(constraint_scratch_elements(air.id, n, cel ? cel : 1));
         if (!cons_ev[0]) for (auto &e : cons_ev) CSG_CUDA(cudaEventCreate(&e));
         // the low-degree split interpolates across the even cosets: only when this context owns all of them
         const bool split = split_low_degree && G == 1;
-        if (cel) csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st, cons_ev,
+        if (cel) csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p + plane * comb_plane, st, cons_ev,
                                        split ? &roots : nullptr, split ? &ntt : nullptr);
         else for (auto &e : cons_ev) CSG_CUDA(cudaEventRecord(e, st.s));
-        tm.constraints = t.stop(st);   // also keeps `polys` alive until the copy has completed
+        const float ms = t.stop(st);   // also keeps `polys` alive until the copy has completed
+        tm.constraints = plane ? tm.constraints + ms : ms;
         float *parts_ms[4] = {&tm.cons_rescue, &tm.cons_ecc_banks, &tm.cons_ecc_final, &tm.cons_rest};
-        for (int k = 0; k < 4; k++) CSG_CUDA(cudaEventElapsedTime(parts_ms[k], cons_ev[k], cons_ev[k + 1]));
-        stage = S_EVALUATED;
+        for (int k = 0; k < 4; k++) { float pm = 0; CSG_CUDA(cudaEventElapsedTime(&pm, cons_ev[k], cons_ev[k + 1])); *parts_ms[k] = plane ? *parts_ms[k] + pm : pm; }
+        if (plane + 1 == d) stage = S_EVALUATED;
+    }
+    // E-valued coefficients: the constraint values are base-field elements, so component j of the merged column is the same
+    // combination with component j of every coefficient -- d passes of the base-field evaluation
+    void eval_constraints_x(const xe *t_ab, const xe *b_ab) {
+        const size_t nc = air.num_constraints(), na = air.assertions.size();
+        std::vector<fe> tj(2 * nc), bj(2 * na + 2);
+        for (int j = 0; j < d; j++) {
+            for (size_t i = 0; i < 2 * nc; i++) tj[i] = t_ab[i].c[j];
+            for (size_t i = 0; i < 2 * na; i++) bj[i] = b_ab[i].c[j];
+            eval_constraints(tj.data(), bj.data(), j);
+        }
     }
     // coefficients of the polynomial taking the given values on <w_len> (host, tiny: one value per signature)
     static std::vector<fe> host_interpolate(const std::vector<fe> &vals) {
@@ -389,29 +413,34 @@ struct csg_ctx {
         // per-coset interpolants, divided by s_kc^m; then the cross-coset step yields the ce column polynomials
         std::vector<fe> sinv(cel);
         for (size_t kc = 0; kc < cel; kc++) sinv[kc] = inv(ce_shift[kc]);
-        d_e.reserve(ce * n); d_cpolys.reserve(ce * n);
-        const fe *e_all = d_e.p;
-        if (G == 1) coset_intt_columns(roots, ntt, d_comb.p, n, d_e.p, n, logn, sinv.data(), ce, st);
-        else {
-            // every context interpolates on its ce cosets; the slices are all-gathered ("composition slices") and each context
-            // runs the small cross-coset step itself.  With more ranks than ce cosets the idle ranks contribute a dummy slice.
-            const size_t slot = cel ? cel : 1;
-            d_eg.reserve(G * slot * n);
-            if (cel) coset_intt_columns(roots, ntt, d_comb.p, n, d_eg.p + rank * slot * n, n, logn, sinv.data(), cel, st);
-            gather(d_eg.p, slot * n * sizeof(fe));
-            if (G <= ce) e_all = d_eg.p;
-            else for (size_t kc = 0; kc < ce; kc++)
-                CSG_CUDA(cudaMemcpyAsync(d_e.p + kc * n, d_eg.p + kc * (G / ce) * n, n * sizeof(fe), cudaMemcpyDeviceToDevice, st.s));
-        }
+        d_e.reserve(ce * n); d_cpolys.reserve(ce * d * n);
         std::vector<fe> mat(ce * ce);
         const fe off_n_inv = inv(f63::pow(to_mont(GENERATOR), n)), ce_inv = inv(to_mont(ce)), w_ce_inv = inv(root_of_unity(ilog2(ce)));
         for (size_t tt = 0; tt < ce; tt++)
             for (size_t k = 0; k < ce; k++)
                 mat[tt * ce + k] = mul(mul(f63::pow(off_n_inv, tt), ce_inv), f63::pow(w_ce_inv, (k * tt) % ce));
-        composition_columns(e_all, d_cpolys.p, n, (unsigned)ce, mat.data(), st);
-        d_clde.reserve(ce * n * bl);
-        coset_ntt_columns(roots, ntt, d_cpolys.p, n, d_clde.p, n, ce * n, ce, logn, lde_shift.data(), bl, st);
-        commit_rows(d_clde.p, (unsigned)ce, ce * n, d_cnodes);
+        // component j of composition column r is the base-field column r*d + j: rows hash as ce elements of E
+        for (int j = 0; j < d; j++) {
+        const fe *comb = d_comb.p + (size_t)j * (cel ? cel : 1) * n;
+        const fe *e_all = d_e.p;
+        if (G == 1) coset_intt_columns(roots, ntt, comb, n, d_e.p, n, logn, sinv.data(), ce, st);
+        else {
+            // every context interpolates on its ce cosets; the slices are all-gathered ("composition slices") and each context
+            // runs the small cross-coset step itself.  With more ranks than ce cosets the idle ranks contribute a dummy slice.
+            const size_t slot = cel ? cel : 1;
+            d_eg.reserve(G * slot * n);
+            if (cel) coset_intt_columns(roots, ntt, comb, n, d_eg.p + rank * slot * n, n, logn, sinv.data(), cel, st);
+            gather(d_eg.p, slot * n * sizeof(fe));
+            if (G <= ce) e_all = d_eg.p;
+            else for (size_t kc = 0; kc < ce; kc++)
+                CSG_CUDA(cudaMemcpyAsync(d_e.p + kc * n, d_eg.p + kc * (G / ce) * n, n * sizeof(fe), cudaMemcpyDeviceToDevice, st.s));
+        }
+        composition_columns(e_all, d_cpolys.p + (size_t)j * n, n, (unsigned)ce, mat.data(), st, (size_t)d * n);
+        }
+        const size_t cw = ce * d;
+        d_clde.reserve(cw * n * bl);
+        coset_ntt_columns(roots, ntt, d_cpolys.p, n, d_clde.p, n, cw * n, cw, logn, lde_shift.data(), bl, st);
+        commit_rows(d_clde.p, (unsigned)cw, cw * n, d_cnodes);
         download_root(d_cnodes, root);
         tm.composition = t.stop(st);
         stage = S_COMPOSED;
@@ -470,6 +499,88 @@ struct csg_ctx {
         stage = S_DEEP;
     }
 
+    // ------------------------------------------------------------------------------------------ stage 5 + 6 over E
+    void ood_x(const xe &z_) {
+        need(S_COMPOSED, "the composition polynomial must be committed first");
+        Timer &t = stage_timer;
+        t.start(st);
+        xz = z_;
+        const size_t w = air.width, cw = ce * d;
+        const xe pts[2] = {xz, x_scale(xz, root_of_unity(logn))};
+        d_pw.reserve(2 * (size_t)d * n);
+        ext_power_table(d, pts, 2, n, d_pw.p, st);
+        std::vector<fe> vals(w * 2 * d);
+        dot_columns(d_polys.p, n, w, n, d_pw.p, 2 * d, vals.data(), scratch2, st);
+        xood_cur.assign(w, x_zero()); xood_next.assign(w, x_zero());
+        for (size_t c = 0; c < w; c++)
+            for (int j = 0; j < d; j++) { xood_cur[c].c[j] = vals[c * 2 * d + j]; xood_next[c].c[j] = vals[c * 2 * d + d + j]; }
+        // composition column r at z^ce: sum_j phi^j * (column (r, j) at z^ce)
+        const xe zm = x_pow(d, xz, ce);
+        ext_power_table(d, &zm, 1, n, d_pw.p, st);
+        std::vector<fe> cv(cw * d);
+        dot_columns(d_cpolys.p, n, cw, n, d_pw.p, d, cv.data(), scratch2, st);
+        xe phi = x_zero(); phi.c[1] = ONE;
+        xood_comp.assign(ce, x_zero());
+        for (size_t r = 0; r < ce; r++) {
+            xe basis = x_one();
+            for (int j = 0; j < d; j++) {
+                xe sv = x_zero();
+                for (int k = 0; k < d; k++) sv.c[k] = cv[(r * d + j) * d + k];
+                xood_comp[r] = x_add(xood_comp[r], x_mul(d, basis, sv));
+                basis = x_mul(d, basis, phi);
+            }
+        }
+        tm.ood_deep = t.stop(st);
+        stage = S_OOD;
+    }
+    void deep_x(const xe *trace_ab, const xe *comp_d, const xe &lambda, const xe &mu) {
+        need(S_OOD, "the out-of-domain frame must be computed first");
+        Timer &t = stage_timer;
+        t.start(st);
+        const size_t w = air.width, cw = ce * d;
+        DeepArgsX a{};
+        a.d = d; a.k = xk;
+        a.z = xz; a.zg = x_scale(xz, root_of_unity(logn)); a.zm = x_pow(d, xz, ce);
+        a.az = x_zero(); a.bzg = x_zero(); a.czm = x_zero();
+        std::vector<fe> coef(2 * (size_t)d * w), ccoef((size_t)d * cw);
+        for (size_t c = 0; c < w; c++) {
+            for (int j = 0; j < d; j++) { coef[(size_t)j * w + c] = trace_ab[2 * c].c[j]; coef[((size_t)d + j) * w + c] = trace_ab[2 * c + 1].c[j]; }
+            a.az = x_add(a.az, x_mul(d, trace_ab[2 * c], xood_cur[c]));
+            a.bzg = x_add(a.bzg, x_mul(d, trace_ab[2 * c + 1], xood_next[c]));
+        }
+        xe phi = x_zero(); phi.c[1] = ONE;
+        for (size_t r = 0; r < ce; r++) {
+            a.czm = x_add(a.czm, x_mul(d, comp_d[r], xood_comp[r]));
+            xe cf = comp_d[r];    // delta_r * phi^j multiplies the base-field column (r, j)
+            for (int j = 0; j < d; j++) {
+                for (int k = 0; k < d; k++) ccoef[(size_t)k * cw + r * d + j] = cf.c[k];
+                cf = x_mul(d, cf, phi);
+            }
+        }
+        a.lambda = lambda; a.mu = mu; a.ncosets = (unsigned)bl;
+        for (size_t k = 0; k < bl; k++) a.shift[k] = lde_shift[k];
+        const size_t np = 3 * (size_t)d;
+        d_abc.reserve(np * n); d_abc_lde.reserve(np * n * bl); d_deep.reserve((size_t)d * lde_n);
+        combine_polys(d_polys.p, n, w, n, coef.data(), 2 * d, d_abc.p, n, scratch2, st);
+        combine_polys(d_cpolys.p, n, cw, n, ccoef.data(), d, d_abc.p + 2 * (size_t)d * n, n, scratch, st);
+        coset_ntt_columns(roots, ntt, d_abc.p, n, d_abc_lde.p, n, np * n, np, logn, lde_shift.data(), bl, st);
+        if (G == 1) deep_quotients_ext(d_abc_lde.p, roots.W.p, n, a, d_deep.p, lde_n, st);
+        else {
+            d_gather.reserve((size_t)d * lde_n);
+            deep_quotients_ext(d_abc_lde.p, roots.W.p, n, a, (fe *)d_gather.p + rank * bl * n, lde_n, st);
+            for (int j = 0; j < d; j++) {
+                gather(d_gather.p + (size_t)j * lde_n, bl * n * sizeof(fe));
+                interleave_slices(d_gather.p + (size_t)j * lde_n, (uint64_t *)d_deep.p + (size_t)j * lde_n, n, (unsigned)bl, (unsigned)G, 1, st);
+            }
+        }
+        if (fri.empty()) fri.emplace_back(new FriLayer());
+        nfri = 1;
+        fri[0]->evals = d_deep.p; fri[0]->m = lde_n; fri[0]->committed = false;
+        tm.ood_deep += t.stop(st);
+        tm.fri = 0;
+        stage = S_DEEP;
+    }
+
     // ------------------------------------------------------------------------------------------ stage 7
     void fri_commit_layer(uint8_t root[32]) {
         need(S_DEEP, "the DEEP composition must be computed first");
@@ -478,13 +589,15 @@ struct csg_ctx {
         t.start(st);
         const size_t q = L.m / 4;
         L.nodes.reserve(16 * q);
-        hash_rows(L.evals, 4, q, 1, 0, q, (int)opt.hash_fn, L.nodes.p + 8 * q, st);
+        if (d == 1) hash_rows(L.evals, 4, q, 1, 0, q, (int)opt.hash_fn, L.nodes.p + 8 * q, st);
+        else hash_rows(L.evals, 4 * d, q, 1, 0, q, (int)opt.hash_fn, L.nodes.p + 8 * q, st, (unsigned)d, L.m);   // rows of 4 elements of E; planes of stride m
         merkle_build(L.nodes.p, q, (int)opt.hash_fn, st);
         download_root(L.nodes, root);
         L.committed = true;
         tm.fri += t.stop(st);
     }
-    void fri_fold(fe alpha) {
+    void fri_fold(fe alpha) { fri_fold_x(x_from(alpha)); }
+    void fri_fold_x(const xe &alpha) {
         need(S_DEEP, "the DEEP composition must be computed first");
         FriLayer &L = *fri[nfri - 1];
         if (!L.committed) throw StateError("the current FRI layer must be committed before it is folded");
@@ -493,7 +606,7 @@ struct csg_ctx {
         const size_t m = L.m, q = m / 4;
         const unsigned logm = ilog2(m);
         FoldArgs a{};
-        a.alpha = alpha; a.offset_inv = inv(to_mont(GENERATOR));
+        a.alpha = alpha.c[0]; a.offset_inv = inv(to_mont(GENERATOR));
         const fe w_inv = inv(root_of_unity(logm));
         a.zeta_inv = f63::pow(w_inv, q); a.quarter = inv(to_mont(4));
         a.logm = logm; a.logW = roots.logn;
@@ -503,8 +616,9 @@ struct csg_ctx {
         }
         if (fri.size() == nfri) fri.emplace_back(new FriLayer());
         FriLayer &N = *fri[nfri];
-        N.owned.reserve(q);
-        csg::fri_fold4(L.evals, m, roots.W.p, a, N.owned.p, st);
+        N.owned.reserve(q * d);
+        if (d == 1) csg::fri_fold4(L.evals, m, roots.W.p, a, N.owned.p, st);
+        else { FoldArgsX ax{a, alpha, d}; fri_fold4_ext(L.evals, m, m, roots.W.p, ax, N.owned.p, q, st); }
         N.evals = N.owned.p; N.m = q; N.committed = false;
         nfri++;
         tm.fri += t.stop(st);
@@ -521,7 +635,7 @@ struct csg_ctx {
     // sharded (the LDE matrices of a split proof): every context gathers the rows of its own cosets, zeros elsewhere, and the
     // row buffers are summed across the ranks
     std::vector<uint64_t> open_rows(const fe *data, unsigned width, unsigned ncosets, size_t coset_stride, size_t col_stride, const std::vector<size_t> &pos,
-                                    bool sharded = false) {
+                                    bool sharded = false, unsigned sub = 1, size_t sub_stride = 0) {
         std::vector<uint32_t> p32(pos.begin(), pos.end());
         sharded = sharded && G > 1;
         if (sharded) {
@@ -535,7 +649,7 @@ struct csg_ctx {
         std::vector<uint64_t> rows(pos.size() * width);
         // d_io still holds the resident trace for re-proving; rows go through a separate small buffer
         d_rows.reserve(std::max<size_t>(rows.size(), 1 << 16));
-        gather_rows(data, width, ncosets, coset_stride, col_stride, d_idx.p, pos.size(), d_rows.p, st);
+        gather_rows(data, width, ncosets, coset_stride, col_stride, d_idx.p, pos.size(), d_rows.p, st, sub, sub_stride);
         if (sharded) reduce_rows(d_rows.p, rows.size());
         CSG_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, rows.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st.s));
         CSG_CUDA(cudaStreamSynchronize(st.s));
@@ -579,6 +693,12 @@ struct csg_ctx {
         w.u8((uint8_t)opt.hash_fn); w.u8((uint8_t)opt.field_extension);
         w.u8((uint8_t)ilog2(opt.fri_folding_factor)); w.u8((uint8_t)ilog2(opt.fri_max_remainder_size));
     }
+    // flattened components of E elements (serialisation / hashing order)
+    std::vector<fe> flat(const std::vector<xe> &v) const {
+        std::vector<fe> out;
+        for (const xe &e : v) for (int j = 0; j < d; j++) out.push_back(e.c[j]);
+        return out;
+    }
     void prove_loaded(uint8_t **proof, size_t *proof_len, const uint64_t *host = nullptr) {
         if (!host) need(S_TRACE, "csg_load_trace must be called first");
         auto t0 = std::chrono::steady_clock::now();
@@ -590,36 +710,46 @@ struct csg_ctx {
         for (uint64_t v : air.pub_inputs) seed.u64(v);
         write_context(seed);
         Coin coin(hf, seed.v.data(), seed.v.size());
+        auto base = [](const std::vector<xe> &v) { std::vector<fe> o; for (const xe &e : v) o.push_back(e.c[0]); return o; };
 
         uint8_t trace_root[32], comp_root[32];
         extend_and_commit_trace(trace_root, host);
         coin.reseed(trace_root);
-        std::vector<fe> t_ab(2 * nc), b_ab(2 * na + 2);
-        for (size_t i = 0; i < 2 * nc; i++) t_ab[i] = coin.draw();
-        for (size_t i = 0; i < 2 * na; i++) b_ab[i] = coin.draw();
-        eval_constraints(t_ab.data(), b_ab.data());
+        std::vector<xe> t_ab(2 * nc), b_ab(2 * na + 2, x_zero());
+        for (size_t i = 0; i < 2 * nc; i++) t_ab[i] = coin.draw_x(d);
+        for (size_t i = 0; i < 2 * na; i++) b_ab[i] = coin.draw_x(d);
+        if (d == 1) eval_constraints(base(t_ab).data(), base(b_ab).data());
+        else eval_constraints_x(t_ab.data(), b_ab.data());
         commit_composition(comp_root);
         coin.reseed(comp_root);
 
-        ood(coin.draw());
-        uint8_t d[32];
-        hash_elements_host(hf, ood_cur.data(), w, d); coin.reseed(d);
-        hash_elements_host(hf, ood_next.data(), w, d); coin.reseed(d);
-        hash_elements_host(hf, ood_comp.data(), ce, d); coin.reseed(d);
+        const xe zz = coin.draw_x(d);
+        if (d == 1) {
+            ood(zz.c[0]);
+            xood_cur.clear(); xood_next.clear(); xood_comp.clear();
+            for (fe v : ood_cur) xood_cur.push_back(x_from(v));
+            for (fe v : ood_next) xood_next.push_back(x_from(v));
+            for (fe v : ood_comp) xood_comp.push_back(x_from(v));
+        } else ood_x(zz);
+        uint8_t dg[32];
+        hash_elements_host(hf, flat(xood_cur).data(), w * d, dg); coin.reseed(dg);
+        hash_elements_host(hf, flat(xood_next).data(), w * d, dg); coin.reseed(dg);
+        hash_elements_host(hf, flat(xood_comp).data(), ce * d, dg); coin.reseed(dg);
 
-        std::vector<fe> dab(2 * w), dd(ce);
-        for (size_t c = 0; c < w; c++) { dab[2 * c] = coin.draw(); dab[2 * c + 1] = coin.draw(); (void)coin.draw(); }
-        for (size_t r = 0; r < ce; r++) dd[r] = coin.draw();
-        const fe lambda = coin.draw(), mu = coin.draw();
-        deep(dab.data(), dd.data(), lambda, mu);
+        std::vector<xe> dab(2 * w), dd(ce);
+        for (size_t c = 0; c < w; c++) { dab[2 * c] = coin.draw_x(d); dab[2 * c + 1] = coin.draw_x(d); (void)coin.draw_x(d); }
+        for (size_t r = 0; r < ce; r++) dd[r] = coin.draw_x(d);
+        const xe lambda = coin.draw_x(d), mu = coin.draw_x(d);
+        if (d == 1) deep(base(dab).data(), base(dd).data(), lambda.c[0], mu.c[0]);
+        else deep_x(dab.data(), dd.data(), lambda, mu);
 
         const size_t nlayers = num_fri_folds() + 1;
         std::vector<std::vector<uint8_t>> fri_roots(nlayers, std::vector<uint8_t>(32));
         for (size_t l = 0; l < nlayers; l++) {
             fri_commit_layer(fri_roots[l].data());
             coin.reseed(fri_roots[l].data());
-            const fe alpha = coin.draw();
-            if (l + 1 < nlayers) fri_fold(alpha);
+            const xe alpha = coin.draw_x(d);
+            if (l + 1 < nlayers) fri_fold_x(alpha);
         }
 
         Timer &tq = query_timer;
@@ -642,17 +772,18 @@ struct csg_ctx {
             pf.u32((uint32_t)paths.size()); pf.put(paths.data(), paths.size());
         }
         {
-            std::vector<uint64_t> rows = open_rows(d_clde.p, (unsigned)ce, (unsigned)b, ce * n, n, pos, true);
+            const size_t cw = ce * d;
+            std::vector<uint64_t> rows = open_rows(d_clde.p, (unsigned)cw, (unsigned)b, cw * n, n, pos, true);
             pf.u32((uint32_t)(rows.size() * 8));
             for (uint64_t v : rows) pf.u64(v);
             std::vector<uint8_t> paths = open_paths(d_cnodes, lde_n, pos);
             pf.u32((uint32_t)paths.size()); pf.put(paths.data(), paths.size());
         }
-        pf.u16((uint16_t)(w * 8));
-        for (fe v : ood_cur) pf.element(v);
-        for (fe v : ood_next) pf.element(v);
-        pf.u16((uint16_t)(ce * 8));
-        for (fe v : ood_comp) pf.element(v);
+        pf.u16((uint16_t)(w * d * 8));
+        for (fe v : flat(xood_cur)) pf.element(v);
+        for (fe v : flat(xood_next)) pf.element(v);
+        pf.u16((uint16_t)(ce * d * 8));
+        for (fe v : flat(xood_comp)) pf.element(v);
         {
             pf.u8((uint8_t)(nlayers - 1));
             std::vector<size_t> fp = pos;
@@ -660,20 +791,15 @@ struct csg_ctx {
             for (size_t l = 0; l + 1 < nlayers; l++) {
                 fp = fold_positions(fp, domain);
                 const size_t q = domain / 4;
-                std::vector<uint64_t> rows = open_rows(fri[l]->evals, 4, 1, 0, q, fp);
+                std::vector<uint64_t> rows = open_fri_rows(*fri[l], fp);
                 pf.u32((uint32_t)(rows.size() * 8));
                 for (uint64_t v : rows) pf.u64(v);
                 std::vector<uint8_t> paths = open_paths(fri[l]->nodes, q, fp);
                 pf.u32((uint32_t)paths.size()); pf.put(paths.data(), paths.size());
                 domain = q;
             }
-            const FriLayer &last = *fri[nlayers - 1];
-            std::vector<uint64_t> rem(last.m);
-            d_rows.reserve(std::max<size_t>(last.m, 1 << 16));
-            from_montgomery(last.evals, d_rows.p, last.m, st);
-            CSG_CUDA(cudaMemcpyAsync(rem.data(), d_rows.p, last.m * 8, cudaMemcpyDeviceToHost, st.s));
-            CSG_CUDA(cudaStreamSynchronize(st.s));
-            pf.u16((uint16_t)(last.m * 8));
+            std::vector<uint64_t> rem = remainder();
+            pf.u16((uint16_t)(rem.size() * 8));
             for (uint64_t v : rem) pf.u64(v);
             pf.u8(1);
         }
@@ -688,6 +814,23 @@ struct csg_ctx {
         memcpy(*proof, pf.v.data(), pf.v.size());
         *proof_len = pf.v.size();
         stage = S_TRACE;   // the resident trace (d_io) can be proved again
+    }
+    // opened rows of a FRI layer: 4 elements per row, each d components (planes of stride m)
+    std::vector<uint64_t> open_fri_rows(const FriLayer &L, const std::vector<size_t> &pos) {
+        const size_t q = L.m / 4;
+        if (d == 1) return open_rows(L.evals, 4, 1, 0, q, pos);
+        return open_rows(L.evals, 4 * d, 1, 0, q, pos, false, (unsigned)d, L.m);
+    }
+    // the last layer in natural order, canonical, components of an element adjacent
+    std::vector<uint64_t> remainder() {
+        const FriLayer &last = *fri[nfri - 1];
+        std::vector<uint64_t> rem(last.m * d);
+        d_rows.reserve(std::max<size_t>(rem.size(), 1 << 16));
+        if (d == 1) from_montgomery(last.evals, d_rows.p, last.m, st);
+        else planes_to_canonical(last.evals, last.m, last.m, d, d_rows.p, st);
+        CSG_CUDA(cudaMemcpyAsync(rem.data(), d_rows.p, rem.size() * 8, cudaMemcpyDeviceToHost, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+        return rem;
     }
 };
 
@@ -706,6 +849,12 @@ int guarded(csg_ctx *ctx, F f) {
     catch (const std::exception &e) { ctx->err = e.what(); return CSG_ERR_UNSUPPORTED; }
 }
 std::vector<fe> mont_vec(const uint64_t *v, size_t n) { std::vector<fe> r(n); for (size_t i = 0; i < n; i++) r[i] = to_mont(v[i] % P); return r; }
+// n elements of E, d canonical words each
+std::vector<xe> mont_xvec(const uint64_t *v, size_t n, int d) {
+    std::vector<xe> r(n, x_zero());
+    for (size_t i = 0; i < n; i++) for (int j = 0; j < d; j++) r[i].c[j] = to_mont(v[i * d + j] % P);
+    return r;
+}
 }  // namespace
 
 extern "C" {
@@ -762,14 +911,33 @@ int csg_extend_and_commit_trace(csg_ctx *ctx, uint8_t root[32]) { return guarded
 int csg_eval_constraints(csg_ctx *ctx, const uint64_t *t_coeffs, const uint64_t *b_coeffs) {
     return guarded(ctx, [&] {
         ctx->need(S_AIR, "csg_set_air must be called first");
+        if (ctx->d > 1) {
+            std::vector<xe> t = mont_xvec(t_coeffs, 2 * ctx->air.num_constraints(), ctx->d), bb = mont_xvec(b_coeffs, 2 * ctx->air.assertions.size(), ctx->d);
+            bb.push_back(x_zero());
+            ctx->eval_constraints_x(t.data(), bb.data());
+            return;
+        }
         std::vector<fe> t = mont_vec(t_coeffs, 2 * ctx->air.num_constraints()), bb = mont_vec(b_coeffs, 2 * ctx->air.assertions.size());
         bb.push_back(0);
         ctx->eval_constraints(t.data(), bb.data());
     });
 }
 int csg_commit_composition(csg_ctx *ctx, uint8_t root[32]) { return guarded(ctx, [&] { ctx->commit_composition(root); }); }
+int csg_ood_ext(csg_ctx *ctx, const uint64_t *z, uint64_t *frame_cur, uint64_t *frame_next, uint64_t *comp) {
+    return guarded(ctx, [&] {
+        if (!z || !frame_cur || !frame_next || !comp) throw ArgError("null argument");
+        const int d = ctx->d;
+        if (d == 1) { csg_ctx *c = ctx; c->ood(to_mont(z[0] % P)); for (size_t i = 0; i < c->air.width; i++) { frame_cur[i] = from_mont(c->ood_cur[i]); frame_next[i] = from_mont(c->ood_next[i]); }
+                      for (size_t r = 0; r < c->ce; r++) comp[r] = from_mont(c->ood_comp[r]); return; }
+        ctx->ood_x(mont_xvec(z, 1, d)[0]);
+        for (size_t c = 0; c < ctx->air.width; c++)
+            for (int j = 0; j < d; j++) { frame_cur[c * d + j] = from_mont(ctx->xood_cur[c].c[j]); frame_next[c * d + j] = from_mont(ctx->xood_next[c].c[j]); }
+        for (size_t r = 0; r < ctx->ce; r++) for (int j = 0; j < d; j++) comp[r * d + j] = from_mont(ctx->xood_comp[r].c[j]);
+    });
+}
 int csg_ood(csg_ctx *ctx, uint64_t z, uint64_t *frame_cur, uint64_t *frame_next, uint64_t *comp) {
     return guarded(ctx, [&] {
+        if (ctx->d != 1) throw ArgError("with a field extension the out-of-domain point has several words: use csg_ood_ext");
         ctx->ood(to_mont(z % P));
         for (size_t c = 0; c < ctx->air.width; c++) { frame_cur[c] = from_mont(ctx->ood_cur[c]); frame_next[c] = from_mont(ctx->ood_next[c]); }
         for (size_t r = 0; r < ctx->ce; r++) comp[r] = from_mont(ctx->ood_comp[r]);
@@ -778,23 +946,30 @@ int csg_ood(csg_ctx *ctx, uint64_t z, uint64_t *frame_cur, uint64_t *frame_next,
 int csg_deep(csg_ctx *ctx, const uint64_t *trace_ab, const uint64_t *comp_d, const uint64_t lambda_mu[2]) {
     return guarded(ctx, [&] {
         ctx->need(S_AIR, "csg_set_air must be called first");
+        if (ctx->d > 1) {
+            std::vector<xe> ab = mont_xvec(trace_ab, 2 * ctx->air.width, ctx->d), dd = mont_xvec(comp_d, ctx->ce, ctx->d), lm = mont_xvec(lambda_mu, 2, ctx->d);
+            ctx->deep_x(ab.data(), dd.data(), lm[0], lm[1]);
+            return;
+        }
         std::vector<fe> ab = mont_vec(trace_ab, 2 * ctx->air.width), d = mont_vec(comp_d, ctx->ce);
         ctx->deep(ab.data(), d.data(), to_mont(lambda_mu[0] % P), to_mont(lambda_mu[1] % P));
     });
 }
 int csg_fri_commit_layer(csg_ctx *ctx, uint8_t root[32]) { return guarded(ctx, [&] { ctx->fri_commit_layer(root); }); }
-int csg_fri_fold(csg_ctx *ctx, uint64_t alpha) { return guarded(ctx, [&] { ctx->fri_fold(to_mont(alpha % P)); }); }
+int csg_fri_fold(csg_ctx *ctx, uint64_t alpha) {
+    return guarded(ctx, [&] { if (ctx->d != 1) throw ArgError("with a field extension alpha has several words: use csg_fri_fold_ext"); ctx->fri_fold(to_mont(alpha % P)); });
+}
+int csg_fri_fold_ext(csg_ctx *ctx, const uint64_t *alpha) {
+    return guarded(ctx, [&] { if (!alpha) throw ArgError("null argument"); ctx->fri_fold_x(mont_xvec(alpha, 1, ctx->d)[0]); });
+}
 int csg_fri_remainder(csg_ctx *ctx, uint64_t *out, size_t cap, size_t *len) {
     return guarded(ctx, [&] {
         ctx->need(S_DEEP, "the DEEP composition must be computed first");
         const FriLayer &L = *ctx->fri[ctx->nfri - 1];
-        if (cap < L.m) throw ArgError("remainder buffer too small");
-        DBuf<uint64_t> tmp;
-        tmp.reserve(L.m);
-        from_montgomery(L.evals, tmp.p, L.m, ctx->st);
-        CSG_CUDA(cudaMemcpyAsync(out, tmp.p, L.m * 8, cudaMemcpyDeviceToHost, ctx->st.s));
-        CSG_CUDA(cudaStreamSynchronize(ctx->st.s));
-        *len = L.m;
+        if (cap < L.m * ctx->d) throw ArgError("remainder buffer too small");
+        std::vector<uint64_t> rem = ctx->remainder();
+        memcpy(out, rem.data(), rem.size() * 8);
+        *len = rem.size();
     });
 }
 static void copy_opening(const std::vector<uint64_t> &r, const std::vector<uint8_t> &p, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
@@ -815,7 +990,8 @@ int csg_open_composition(csg_ctx *ctx, const uint64_t *positions, size_t npos, u
     return guarded(ctx, [&] {
         ctx->need(S_COMPOSED, "the composition polynomial must be committed first");
         std::vector<size_t> pos(positions, positions + npos);
-        copy_opening(ctx->open_rows(ctx->d_clde.p, (unsigned)ctx->ce, (unsigned)ctx->b, ctx->ce * ctx->n, ctx->n, pos, true), ctx->open_paths(ctx->d_cnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
+        const size_t cw = ctx->ce * ctx->d;
+        copy_opening(ctx->open_rows(ctx->d_clde.p, (unsigned)cw, (unsigned)ctx->b, cw * ctx->n, ctx->n, pos, true), ctx->open_paths(ctx->d_cnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
     });
 }
 int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
@@ -824,7 +1000,7 @@ int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, si
         if (layer >= ctx->nfri || !ctx->fri[layer]->committed) throw ArgError("no such committed FRI layer");
         std::vector<size_t> pos(positions, positions + npos);
         const FriLayer &L = *ctx->fri[layer];
-        copy_opening(ctx->open_rows(L.evals, 4, 1, 0, L.m / 4, pos), ctx->open_paths(L.nodes, L.m / 4, pos), rows, paths, cap, paths_len);
+        copy_opening(ctx->open_fri_rows(L, pos), ctx->open_paths(L.nodes, L.m / 4, pos), rows, paths, cap, paths_len);
     });
 }
 // debugging aid: number of elements >= p in an internal device buffer (0 = trace polys, 1 = LDE, 2 = periodic tables,

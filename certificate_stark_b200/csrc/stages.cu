@@ -23,7 +23,8 @@ unsigned grid_for(size_t count, unsigned threads) {
 }
 
 struct CrossMat { fe m[16 * 16]; };
-__global__ void composition_columns_kernel(const fe *__restrict__ e, fe *__restrict__ cols, unsigned long long n, unsigned ce, CrossMat M) {
+__global__ void composition_columns_kernel(const fe *__restrict__ e, fe *__restrict__ cols, unsigned long long n, unsigned ce, CrossMat M,
+                                           unsigned long long col_stride) {
     unsigned long long m = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (m >= n) return;
     fe v[16];
@@ -32,7 +33,7 @@ __global__ void composition_columns_kernel(const fe *__restrict__ e, fe *__restr
     for (unsigned t = 0; t < ce; t++) {
         acc192 s;
         for (unsigned k = 0; k < ce; k++) s.mac(M.m[t * ce + k], v[k]);
-        cols[r * n + q0 + qs * t] = s.reduce();
+        cols[r * col_stride + q0 + qs * t] = s.reduce();
     }
 }
 
@@ -163,13 +164,14 @@ __global__ void fri_fold4_kernel(const fe *__restrict__ e, unsigned long long q,
 }
 
 __global__ void gather_rows_kernel(const fe *__restrict__ data, unsigned width, unsigned ncosets, unsigned long long coset_stride,
-                                   unsigned long long col_stride, const uint32_t *__restrict__ pos, unsigned npos, uint64_t *__restrict__ rows) {
+                                   unsigned long long col_stride, const uint32_t *__restrict__ pos, unsigned npos, uint64_t *__restrict__ rows,
+                                   unsigned sub, unsigned long long sub_stride) {
     unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= npos * width) return;
     unsigned r = t / width, c = t % width;
     if (pos[r] == 0xFFFFFFFFu) { rows[t] = 0; return; }   // a row another context of a sharded proof owns
     unsigned long long j = pos[r], k = j % ncosets, i = j / ncosets;
-    rows[t] = from_mont(data[k * coset_stride + c * col_stride + i]);
+    rows[t] = from_mont(data[k * coset_stride + (c / sub) * col_stride + (c % sub) * sub_stride + i]);
 }
 
 __global__ void coset_to_natural_kernel(const fe *__restrict__ lde, unsigned width, unsigned ncosets, unsigned long long n, uint64_t *__restrict__ out) {
@@ -224,11 +226,12 @@ void from_montgomery(const fe *in, uint64_t *out, size_t count, Stream &st) {
     CSG_LAUNCH(st, from_mont_kernel, grid_for(count, 256), 256, 0, in, out, (unsigned long long)count);
 }
 
-void composition_columns(const fe *e, fe *cols, size_t n, unsigned ce, const fe *mat_host, Stream &st) {
+void composition_columns(const fe *e, fe *cols, size_t n, unsigned ce, const fe *mat_host, Stream &st, size_t col_stride) {
     if (ce > 16) throw std::runtime_error("constraint blowup above 16 is not supported");
     CrossMat M;
     for (unsigned i = 0; i < ce * ce; i++) M.m[i] = mat_host[i];
-    CSG_LAUNCH(st, composition_columns_kernel, (unsigned)((n + 255) / 256), 256, 0, e, cols, (unsigned long long)n, ce, M);
+    CSG_LAUNCH(st, composition_columns_kernel, (unsigned)((n + 255) / 256), 256, 0, e, cols, (unsigned long long)n, ce, M,
+               (unsigned long long)(col_stride ? col_stride : n));
 }
 
 void coset_mix(const fe *in, fe *out, size_t n, unsigned L, size_t npolys, const fe *mat_host, Stream &st) {
@@ -267,9 +270,16 @@ void combine_polys(const fe *polys, size_t stride, size_t ncols, size_t n, const
     scratch.reserve(ncomb * ncols);
     CSG_CUDA(cudaMemcpyAsync(scratch.p, coef_host, ncomb * ncols * sizeof(fe), cudaMemcpyHostToDevice, st.s));
     const unsigned grid = (unsigned)((n + 255) / 256);
-    if (ncomb == 1) CSG_LAUNCH(st, combine_polys_kernel<1>, grid, 256, 0, polys, (unsigned long long)stride, (unsigned)ncols, (unsigned long long)n, scratch.p, out, (unsigned long long)out_stride);
-    else if (ncomb == 2) CSG_LAUNCH(st, combine_polys_kernel<2>, grid, 256, 0, polys, (unsigned long long)stride, (unsigned)ncols, (unsigned long long)n, scratch.p, out, (unsigned long long)out_stride);
-    else throw std::runtime_error("combine_polys: 1 or 2 combinations per call");
+#define CSG_COMBINE(N) CSG_LAUNCH(st, combine_polys_kernel<N>, grid, 256, 0, polys, (unsigned long long)stride, (unsigned)ncols, (unsigned long long)n, scratch.p, out, (unsigned long long)out_stride)
+    switch (ncomb) {
+    case 1: CSG_COMBINE(1); break;
+    case 2: CSG_COMBINE(2); break;
+    case 3: CSG_COMBINE(3); break;
+    case 4: CSG_COMBINE(4); break;
+    case 6: CSG_COMBINE(6); break;
+    default: throw std::runtime_error("combine_polys: 1, 2, 3, 4 or 6 combinations per call");
+    }
+#undef CSG_COMBINE
 }
 
 void deep_quotients(const fe *abc, const fe *W, size_t n, const DeepArgs &a, fe *deep, Stream &st) {
@@ -283,11 +293,11 @@ void fri_fold4(const fe *evals, size_t m, const fe *W, const FoldArgs &a, fe *ou
 }
 
 void gather_rows(const fe *data, unsigned width, unsigned ncosets, size_t coset_stride, size_t col_stride, const uint32_t *pos_dev,
-                 size_t npos, uint64_t *rows_dev, Stream &st) {
+                 size_t npos, uint64_t *rows_dev, Stream &st, unsigned sub, size_t sub_stride) {
     if (!npos) return;
     const size_t total = npos * width;
     CSG_LAUNCH(st, gather_rows_kernel, (unsigned)((total + 255) / 256), 256, 0, data, width, ncosets, (unsigned long long)coset_stride,
-               (unsigned long long)col_stride, pos_dev, (unsigned)npos, rows_dev);
+               (unsigned long long)col_stride, pos_dev, (unsigned)npos, rows_dev, sub ? sub : 1u, (unsigned long long)sub_stride);
 }
 
 }  // namespace csg

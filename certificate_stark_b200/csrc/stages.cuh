@@ -13,7 +13,8 @@ void to_montgomery(const uint64_t *in, fe *out, size_t count, Stream &st);
 // e[k][m] (k < ce): coefficient m of the size-n interpolant of C on ce coset k, already divided by s_k^m.
 // cols[r][q] = coefficient q*ce + r of the degree < ce*n composition polynomial (CompositionPoly::new's transposition).
 // mat[t*ce + k] = offset^(-n t) / ce * w_ce^(-k t)
-void composition_columns(const fe *e, fe *cols, size_t n, unsigned ce, const fe *mat_host, Stream &st);
+// col_stride: distance between consecutive output columns (0: n)
+void composition_columns(const fe *e, fe *cols, size_t n, unsigned ce, const fe *mat_host, Stream &st, size_t col_stride = 0);
 
 // out[p][j'][m] = sum_j mat[j'*L + j] * in[p][j][m] for npolys blocks of L x n elements; out[e] = sum_k in[k*stride + e]
 void coset_mix(const fe *in, fe *out, size_t n, unsigned L, size_t npolys, const fe *mat_host, Stream &st);
@@ -49,8 +50,9 @@ struct FoldArgs {
 void fri_fold4(const fe *evals, size_t m, const fe *W, const FoldArgs &a, fe *out, Stream &st);
 
 // rows[t][c] (canonical) = element (c, position[t]) of a coset-major matrix; position j = k + ncosets*i
+// sub > 1: column c lives at (c / sub) * col_stride + (c % sub) * sub_stride (planes of extension-field elements)
 void gather_rows(const fe *data, unsigned width, unsigned ncosets, size_t coset_stride, size_t col_stride, const uint32_t *pos_dev,
-                 size_t npos, uint64_t *rows_dev, Stream &st);
+                 size_t npos, uint64_t *rows_dev, Stream &st, unsigned sub = 1, size_t sub_stride = 0);
 void from_montgomery(const fe *in, uint64_t *out, size_t count, Stream &st);
 // coset-major lde[(k*width + c)*n + i] -> canonical natural-order columns out[c*(n*ncosets) + k + ncosets*i]
 void coset_major_to_natural(const fe *lde, unsigned width, unsigned ncosets, size_t n, uint64_t *out, Stream &st);

@@ -39,7 +39,10 @@ enum {
     CSG_AIR_RESCUE = 5         /* RescueAir        benches/rescue.rs:163-268    14 cols,  14 constraints */
 };
 enum { CSG_HASH_BLAKE3_256 = 2, CSG_HASH_SHA3_256 = 3 }; /* HashFunction (src/lib.rs:82, examples/state-transition.rs:67-71) */
-enum { CSG_FIELD_EXT_NONE = 1 };                          /* FieldExtension::None (src/lib.rs:83) */
+/* FieldExtension (src/lib.rs:83; the example binary takes 1/2/3, examples/state-transition.rs:62-66).  With Quadratic or Cubic
+ * the challenges, composition columns, out-of-domain frame, DEEP composition and FRI layers are elements of the degree-2 / 3
+ * extension: such an element crosses the ABI (and is serialised) as its 2 / 3 canonical words in order. */
+enum { CSG_FIELD_EXT_NONE = 1, CSG_FIELD_EXT_QUADRATIC = 2, CSG_FIELD_EXT_CUBIC = 3 };
 
 /* ProofOptions::new(num_queries, blowup_factor, grinding_factor, hash_fn, field_extension, fri_folding_factor,
  * fri_max_remainder_size)  -- src/lib.rs:78-86 */
@@ -88,7 +91,11 @@ int csg_commit_composition(csg_ctx *ctx, uint8_t root[32]);                  /* 
 /* OOD frame at z: trace polys at z and z*g (width each), composition columns at z^m (m = ce blowup) */
 int csg_ood(csg_ctx *ctx, uint64_t z, uint64_t *frame_cur, uint64_t *frame_next, uint64_t *comp);
 /* DEEP coefficients: per trace column (alpha, beta), per composition column delta, then (lambda, mu) */
-int csg_deep(csg_ctx *ctx, const uint64_t *trace_ab, const uint64_t *comp_d, const uint64_t lambda_mu[2]);
+int csg_deep(csg_ctx *ctx, const uint64_t *trace_ab, const uint64_t *comp_d, const uint64_t *lambda_mu /* 2 elements */);
+/* with a field extension every challenge / frame entry of the level-2 calls is d words (t_coeffs, b_coeffs, trace_ab, comp_d,
+ * lambda_mu, opened composition and FRI rows, the remainder); the two calls that take a challenge by value have pointer forms: */
+int csg_ood_ext(csg_ctx *ctx, const uint64_t *z, uint64_t *frame_cur, uint64_t *frame_next, uint64_t *comp);
+int csg_fri_fold_ext(csg_ctx *ctx, const uint64_t *alpha);
 int csg_fri_commit_layer(csg_ctx *ctx, uint8_t root[32]);                    /* transpose/4, hash, Merkle */
 int csg_fri_fold(csg_ctx *ctx, uint64_t alpha);                              /* degree-respecting projection */
 int csg_fri_remainder(csg_ctx *ctx, uint64_t *out, size_t cap, size_t *len);

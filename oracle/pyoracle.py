@@ -53,6 +53,12 @@ def lib():
         L.stark_verify.argtypes = [C.c_int, u64p, C.c_size_t, u8p, C.c_size_t]
         L.stark_verify.restype = C.c_int
         L.stark_free.argtypes = [C.c_void_p]
+        L.stark_prove_generic.argtypes = [C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.POINTER(StarkOptions), C.c_int, C.POINTER(u8p), szp]
+        L.stark_prove_generic.restype = C.c_int
+        L.stark_verify_generic.argtypes = [C.c_int, u64p, C.c_size_t, u8p, C.c_size_t]
+        L.stark_verify_generic.restype = C.c_int
+        L.ext_mul_canonical.argtypes = [C.c_int, u64p, u64p, u64p]
+        L.ext_inv_canonical.argtypes = [C.c_int, u64p, u64p]
         L.blake3_256.argtypes = [C.c_char_p, C.c_size_t, u8p]
         L.sha3_256.argtypes = [C.c_char_p, C.c_size_t, u8p]
         L.ntt_natural.argtypes = [u64p, C.c_size_t, C.c_int]
@@ -129,6 +135,37 @@ def prove(air_id, trace, pub, opt, want_debug=False):
     proof = bytes(C.cast(out, C.POINTER(C.c_uint8 * n.value)).contents)
     lib().stark_free(out)
     return (proof, dbg) if want_debug else proof
+
+
+def prove_generic(air_id, trace, pub, opt):
+    """the extension-field code path of the oracle at degree d = opt.field_extension (1 included: must equal prove())"""
+    trace = np.ascontiguousarray(trace, dtype=np.uint64)
+    pub = np.ascontiguousarray(pub, dtype=np.uint64)
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    rc = lib().stark_prove_generic(air_id, _p64(trace), trace.shape[1], _p64(pub), pub.size, C.byref(opt), int(opt.field_extension), C.byref(out), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"oracle stark_prove_generic failed: {rc}")
+    proof = bytes(C.cast(out, C.POINTER(C.c_uint8 * n.value)).contents)
+    lib().stark_free(out)
+    return proof
+
+
+def verify_generic(air_id, pub, proof):
+    pub = np.ascontiguousarray(pub, dtype=np.uint64)
+    buf = np.frombuffer(proof, dtype=np.uint8)
+    return lib().stark_verify_generic(air_id, _p64(pub), pub.size, _p8(buf), buf.size)
+
+
+def ext_mul(d, a, b):
+    a, b, out = np.array(a, dtype=np.uint64), np.array(b, dtype=np.uint64), np.zeros(d, dtype=np.uint64)
+    lib().ext_mul_canonical(d, _p64(a), _p64(b), _p64(out))
+    return [int(v) for v in out]
+
+
+def ext_inv(d, a):
+    a, out = np.array(a, dtype=np.uint64), np.zeros(d, dtype=np.uint64)
+    lib().ext_inv_canonical(d, _p64(a), _p64(out))
+    return [int(v) for v in out]
 
 
 def verify(air_id, pub, proof):

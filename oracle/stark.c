@@ -233,7 +233,7 @@ static void write_context(buf_t *b, uint32_t width, size_t n, const stark_option
 #define CONTEXT_BYTES 20
 static size_t num_fri_layers(const stark_options *o, size_t domain) { size_t r = 0; while (domain > o->fri_max_remainder_size) { domain /= o->fri_folding_factor; r++; } return r; }
 static int options_ok(const stark_options *o) {
-    return o->field_extension == 1 && o->fri_folding_factor == 4 && o->num_queries > 0 && o->num_queries < 256 && o->blowup_factor >= 2 &&
+    return o->field_extension >= 1 && o->field_extension <= 3 && o->fri_folding_factor == 4 && o->num_queries > 0 && o->num_queries < 256 && o->blowup_factor >= 2 &&
            (o->blowup_factor & (o->blowup_factor - 1)) == 0 && (o->hash_fn == HASH_BLAKE3_256 || o->hash_fn == HASH_SHA3_256) &&
            o->fri_max_remainder_size >= 4 && (o->fri_max_remainder_size & (o->fri_max_remainder_size - 1)) == 0 && o->grinding_factor < 32;
 }
@@ -264,13 +264,13 @@ static int cons_init(cons_t *k, const air_t *a, coin_t *coin) {
     k->g = fe_root_of_unity(ilog2(k->n)); k->g_inv_last = fe_exp(k->g, k->n - 1);
     uint32_t nc = a->num_constraints;
     k->t_alpha = malloc(nc * sizeof(fe)); k->t_beta = malloc(nc * sizeof(fe)); k->t_group = malloc(nc * sizeof(uint32_t));
-    for (uint32_t i = 0; i < nc; i++) if (coin_draw(coin, &k->t_alpha[i]) || coin_draw(coin, &k->t_beta[i])) return 1;
+    for (uint32_t i = 0; coin && i < nc; i++) if (coin_draw(coin, &k->t_alpha[i]) || coin_draw(coin, &k->t_beta[i])) return 1;
     k->na = a->num_assertions;
     k->sa = malloc((k->na ? k->na : 1) * sizeof(air_assertion));
     memcpy(k->sa, a->assertions, k->na * sizeof(air_assertion));
     qsort(k->sa, k->na, sizeof(air_assertion), cmp_assert);
     k->b_alpha = malloc((k->na + 1) * sizeof(fe)); k->b_beta = malloc((k->na + 1) * sizeof(fe));
-    for (uint32_t i = 0; i < k->na; i++) if (coin_draw(coin, &k->b_alpha[i]) || coin_draw(coin, &k->b_beta[i])) return 1;
+    for (uint32_t i = 0; coin && i < k->na; i++) if (coin_draw(coin, &k->b_alpha[i]) || coin_draw(coin, &k->b_beta[i])) return 1;
     /* transition groups keyed by evaluation degree, ascending */
     size_t comp_degree = k->ce_n - 1, target = comp_degree + (k->n - 1);
     k->tgroups = malloc(nc * sizeof(tgroup_t));
@@ -376,10 +376,14 @@ static size_t fold_positions(const size_t *pos, size_t np, size_t domain, size_t
 
 /* ================================================================== PROVER */
 typedef struct { uint8_t *nodes; fe *evals; size_t m; } fri_layer_t;
+static int stark_prove_ext(int air_id, const uint64_t *trace, size_t n, const uint64_t *pub, size_t npub, const stark_options *opt, int d,
+                           uint8_t **proof_out, size_t *proof_len, stark_debug *dbg);
+static int stark_verify_ext(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len);
 
 int stark_prove(int air_id, const uint64_t *trace, size_t n, const uint64_t *pub, size_t npub, const stark_options *opt,
                 uint8_t **proof_out, size_t *proof_len, stark_debug *dbg) {
     if (!options_ok(opt) || n < 8 || (n & (n - 1))) return -1;
+    if (opt->field_extension != 1) return stark_prove_ext(air_id, trace, n, pub, npub, opt, (int)opt->field_extension, proof_out, proof_len, dbg);
     air_t *air = air_new(air_id, n, pub, npub);
     if (!air) return -2;
     const uint32_t w = air->width;
@@ -631,6 +635,7 @@ static uint64_t rd_uint(rd_t *r, int bytes) { const uint8_t *q = rd_take(r, byte
 static int rd_fe(rd_t *r, fe *out) { uint64_t v = rd_uint(r, 8); if (r->err || v >= F63_P) { r->err = 1; return 1; } *out = fe_from_u64(v); return 0; }
 
 int stark_verify(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len) {
+    if (proof_len > 18 && proof[2] == 0 && proof[3] == 0 && proof[17] != 1) return stark_verify_ext(air_id, pub, npub, proof, proof_len);   /* field_extension byte */
     rd_t R = {proof, proof_len, 0, 0};
     /* context */
     uint32_t w = (uint32_t)rd_uint(&R, 1); unsigned logn = (unsigned)rd_uint(&R, 1);
@@ -795,3 +800,5 @@ done:
     air_free(air);
     return rc;
 }
+
+#include "stark_ext.inc"

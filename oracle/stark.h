@@ -23,7 +23,7 @@ typedef struct {
     uint32_t blowup_factor;     /* 8 */
     uint32_t grinding_factor;   /* 0 */
     uint32_t hash_fn;           /* HASH_BLAKE3_256 / HASH_SHA3_256 */
-    uint32_t field_extension;   /* 1 = None (only None is implemented) */
+    uint32_t field_extension;   /* 1 = None, 2 = Quadratic, 3 = Cubic (ext.h) */
     uint32_t fri_folding_factor;/* 4 */
     uint32_t fri_max_remainder_size; /* 256 */
 } stark_options;
@@ -47,6 +47,12 @@ int stark_prove(int air_id, const uint64_t *trace, size_t n, const uint64_t *pub
 /* 0 = accepted; negative = malformed proof; positive = the verification step that failed */
 int stark_verify(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len);
 void stark_free(void *p);
+/* the extension-field code path at any degree d = field_extension in {1,2,3}; d = 1 must reproduce stark_prove (self-check) */
+int stark_prove_generic(int air_id, const uint64_t *trace, size_t n, const uint64_t *pub, size_t npub, const stark_options *opt, int d,
+                        uint8_t **proof, size_t *proof_len);
+int stark_verify_generic(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len);
+void ext_mul_canonical(int d, const uint64_t *a, const uint64_t *b, uint64_t *out);
+void ext_inv_canonical(int d, const uint64_t *a, uint64_t *out);
 
 /* ---- building blocks, exported for kernel-level parity tests ---- */
 void ntt_natural(fe *a, size_t n, int inverse);                       /* in place; inverse includes the 1/n scaling */

@@ -235,7 +235,7 @@ def test_degenerate_shapes_fail_cleanly(ctx, csg):
     with pytest.raises(csg.CsgError):
         ctx.prove(csg.AIR_RESCUE, trace[:, :6], pub, csg.ProofOptions(blowup_factor=4))  # not a power of two
     with pytest.raises(csg.CsgError):
-        ctx.prove(csg.AIR_RANGE, *csg.build_range_trace(1), csg.ProofOptions(field_extension=3))   # cubic extension: not implemented
+        ctx.prove(csg.AIR_RANGE, *csg.build_range_trace(1), csg.ProofOptions(field_extension=4))   # FieldExtension is None / Quadratic / Cubic
     with pytest.raises(csg.CsgError, match="remainder"):
         ctx.prove(csg.AIR_RESCUE, *csg.build_rescue_trace(np.arange(42, 49, dtype=np.uint64), 32), csg.ProofOptions(blowup_factor=32, fri_max_remainder_size=4))
     # the context stays usable after errors
