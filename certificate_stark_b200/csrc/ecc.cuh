@@ -29,22 +29,56 @@ CSG_HD fp2 sqr(fp2 a) { return mul(a, a); }
 CSG_HD fp6 add(const fp6 &a, const fp6 &b) { fp6 r; for (int i = 0; i < 6; i++) r.c[i] = f63::add(a.c[i], b.c[i]); return r; }
 CSG_HD fp6 sub(const fp6 &a, const fp6 &b) { fp6 r; for (int i = 0; i < 6; i++) r.c[i] = f63::sub(a.c[i], b.c[i]); return r; }
 CSG_HD fp6 dbl(const fp6 &a) { fp6 r; for (int i = 0; i < 6; i++) r.c[i] = f63::dbl(a.c[i]); return r; }
-// (a + b v + c v^2)(d + e v + f v^2) with v^3 = -v - 1: six Fp2 products (ecc.rs:506-548).
-// Not inlined on the device: the curve formulas call it ~40 times per row and the body is ~700 instructions.
+// (a + b v + c v^2)(d + e v + f v^2) with v^3 = -v - 1 (ecc.rs:506-548):
+//     r0 = ad - bf - ce        r1 = ae + bd - bf - ce - cf        r2 = af + be + cd - cf
+// Schoolbook over Fp with lazily reduced 128-bit sums: an Fp2 product (x0 + x1 u)(y0 + y1 u) is
+//     (x0 y0 + x1 (2 y1))  +  (x0 y1 + x1 (y0 + 2 y1)) u
+// so with 2 y1 and y0 + 2 y1 prepared per right operand it is four multiply-accumulates, and every output coefficient is ONE
+// Montgomery reduction of a sum of at most 10 products (15 fit in 128 bits).  The subtractions become additions of products
+// with p - b, p - c.  36 multiply-accumulates + 6 reductions instead of 18 modular multiplications + ~70 modular
+// additions: half the ALU-pipe instructions, and the work is split evenly between the ALU and FMA pipes (IMAD.WIDE).
+// Not inlined on the device: the curve formulas call it ~40 times per row.
+struct fp2acc {
+    f63::acc128 c0, c1;
+    // += (x0 + x1 u) * y, y given as (y0, y1, 2 y1, y0 + 2 y1)
+    CSG_HD void mac(fe x0, fe x1, fe y0, fe y1, fe y1d, fe ys) { c0.mac(x0, y0); c0.mac(x1, y1d); c1.mac(x0, y1); c1.mac(x1, ys); }
+    CSG_HD void add(const fp2acc &o) {
+#if defined(__CUDA_ARCH__)
+        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(c0.lo), "+l"(c0.hi) : "l"(o.c0.lo), "l"(o.c0.hi));
+        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(c1.lo), "+l"(c1.hi) : "l"(o.c1.lo), "l"(o.c1.hi));
+#else
+        c0.lo += o.c0.lo; c0.hi += o.c0.hi + (c0.lo < o.c0.lo ? 1 : 0);
+        c1.lo += o.c1.lo; c1.hi += o.c1.hi + (c1.lo < o.c1.lo ? 1 : 0);
+#endif
+    }
+};
 #if defined(__CUDACC__)
 static __host__ __device__ __noinline__ fp6 mul(fp6 x, fp6 y) {   // by value: operands travel in registers, not through local memory
 #else
 inline fp6 mul(const fp6 &x, const fp6 &y) {
 #endif
-    fp2 a = {x.c[0], x.c[1]}, b = {x.c[2], x.c[3]}, c = {x.c[4], x.c[5]};
-    fp2 d = {y.c[0], y.c[1]}, e = {y.c[2], y.c[3]}, f = {y.c[4], y.c[5]};
-    fp2 ad = mul(a, d), be = mul(b, e), cf = mul(c, f);
-    fp2 s_ab = mul(add(a, b), add(d, e)), s_ac = mul(add(a, c), add(d, f)), s_bc = mul(add(b, c), add(e, f));
-    fp2 sum = add(add(ad, be), cf);
-    fp2 r0 = sub(sum, s_bc);
-    fp2 r1 = sub(sub(s_ab, s_bc), ad);
-    fp2 r2 = add(sub(sub(s_ac, sum), cf), dbl(be));
-    return {{r0.c0, r0.c1, r1.c0, r1.c1, r2.c0, r2.c1}};
+    const fe a0 = x.c[0], a1 = x.c[1], b0 = x.c[2], b1 = x.c[3], c0 = x.c[4], c1 = x.c[5];
+    // p - b, p - c: operands only need to be below 2^64 and at most p for the product bound; p - 0 = p is fine
+    const fe nb0 = f63::P - b0, nb1 = f63::P - b1, nc0 = f63::P - c0, nc1 = f63::P - c1;
+    const fe d0 = y.c[0], d1 = y.c[1], e0 = y.c[2], e1 = y.c[3], f0 = y.c[4], f1 = y.c[5];
+    const fe d1d = f63::dbl(d1), e1d = f63::dbl(e1), f1d = f63::dbl(f1);
+    const fe ds = f63::add(d0, d1d), es = f63::add(e0, e1d), fs = f63::add(f0, f1d);
+    fp2acc t;                                   // -(bf + ce), shared by r0 and r1
+    t.mac(nb0, nb1, f0, f1, f1d, fs);
+    t.mac(nc0, nc1, e0, e1, e1d, es);
+    fp2acc r0 = t;
+    r0.mac(a0, a1, d0, d1, d1d, ds);
+    fp2acc r1 = t;
+    r1.mac(a0, a1, e0, e1, e1d, es);
+    r1.mac(b0, b1, d0, d1, d1d, ds);
+    fp2acc u;                                   // -cf, shared by r1 and r2
+    u.mac(nc0, nc1, f0, f1, f1d, fs);
+    r1.add(u);
+    fp2acc r2 = u;
+    r2.mac(a0, a1, f0, f1, f1d, fs);
+    r2.mac(b0, b1, e0, e1, e1d, es);
+    r2.mac(c0, c1, d0, d1, d1d, ds);
+    return {{r0.c0.reduce(), r0.c1.reduce(), r1.c0.reduce(), r1.c1.reduce(), r2.c0.reduce(), r2.c1.reduce()}};
 }
 CSG_HD fp6 sqr(const fp6 &a) { return mul(a, a); }
 CSG_HD fp6 b3() { const uint64_t *t = CSG_TABLE(CSG_B3); return {{t[0], t[1], t[2], t[3], t[4], t[5]}}; }
