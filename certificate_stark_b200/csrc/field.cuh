@@ -52,7 +52,9 @@ CSG_HD u128 mul_wide(uint64_t a, uint64_t b) {
 // two 32x32->64 multiply-adds (IMAD.WIDE.U32 on the device) and a handful of adds: no 64-bit multiplications at all.
 constexpr uint64_t P_HI = P >> 32;   // 0x41800000
 CSG_HD fe redc_reference(uint64_t lo, uint64_t hi);
-CSG_HD fe redc(uint64_t lo, uint64_t hi) {
+// the reduction without its final conditional subtraction: t * 2^-64 mod p as a value in [0, t / 2^64 + p], i.e. below 2p
+// whenever t < p * 2^64 (lazy butterflies of the NTT keep their operands in [0, 2p))
+CSG_HD uint64_t redc_raw(uint64_t lo, uint64_t hi) {
 #if defined(CSG_REDC_REFERENCE)
     return redc_reference(lo, hi);
 #endif
@@ -85,7 +87,7 @@ CSG_HD fe redc(uint64_t lo, uint64_t hi) {
         "mov.b64 %0, {r0, r1};\n\t"
         "}"
         : "=l"(u) : "l"(lo), "l"(hi));
-    return u >= P ? u - P : u;
+    return u;
 #else
     const uint32_t t0 = (uint32_t)lo, m1 = 0u - t0;
     const uint64_t mp1 = (uint64_t)m1 * P_HI;                                   // < 2^63
@@ -93,9 +95,10 @@ CSG_HD fe redc(uint64_t lo, uint64_t hi) {
     const uint32_t t1 = (uint32_t)s, m2 = 0u - t1;
     const uint64_t rest = hi + (mp1 >> 32) + (s >> 32);                         // (t + m1*p) >> 64, at most p
     const uint64_t u = (uint64_t)m2 * P_HI + rest + (t1 != 0 ? 1 : 0);           // < 2p
-    return u >= P ? u - P : u;
+    return u;
 #endif
 }
+CSG_HD fe redc(uint64_t lo, uint64_t hi) { const uint64_t u = redc_raw(lo, hi); return u >= P ? u - P : u; }
 // the same value computed the long way (one 64-bit Montgomery step with -p^-1 = p - 2); kept for the unit tests
 CSG_HD fe redc_reference(uint64_t lo, uint64_t hi) {
     uint64_t m = lo * NPRIME;
@@ -106,6 +109,13 @@ CSG_HD fe redc_reference(uint64_t lo, uint64_t hi) {
 
 CSG_HD fe mul(fe a, fe b) { u128 t = mul_wide(a, b); return redc(t.lo, t.hi); }
 CSG_HD fe sqr(fe a) { return mul(a, a); }
+// lazy arithmetic on values in [0, 2p) (2p < 2^64; 4p is not, so sums are brought back below 2p at once):
+//   mul_2p: a < 2p, b < p  ->  a*b*2^-64 mod p, below 1.52 p, no conditional subtraction
+//   add_2p / sub_2p: operands and result in [0, 2p)
+CSG_HD uint64_t mul_2p(uint64_t a, fe b) { u128 t = mul_wide(a, b); return redc_raw(t.lo, t.hi); }
+CSG_HD uint64_t add_2p(uint64_t a, uint64_t b) { uint64_t s = a + b; return s >= 2 * P ? s - 2 * P : s; }
+CSG_HD uint64_t sub_2p(uint64_t a, uint64_t b) { return a >= b ? a - b : a + 2 * P - b; }
+CSG_HD fe reduce_2p(uint64_t a) { return a >= P ? a - P : a; }
 CSG_HD fe add(fe a, fe b) { uint64_t s = a + b; return s >= P ? s - P : s; }
 CSG_HD fe sub(fe a, fe b) { return a >= b ? a - b : a + P - b; }
 CSG_HD fe neg(fe a) { return a ? P - a : 0; }

@@ -63,9 +63,9 @@ __device__ __forceinline__ void dit_round(fe *sm, const fe *tw, unsigned logS, u
                 if (j & h) continue;
                 const unsigned k = k0 + ((j & (h - 1)) << s);
                 const fe w = tw[k << (logS - 1 - s - t)];
-                const fe x = v[j], y = mul(v[j + h], w);
-                v[j] = add(x, y);
-                v[j + h] = sub(x, y);
+                const fe x = v[j], y = mul_2p(v[j + h], w);   // lazy butterfly: values stay in [0, 2p) between the rounds
+                v[j] = add_2p(x, y);
+                v[j + h] = sub_2p(x, y);
             }
         }
 #pragma unroll
@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
         unsigned e, l;
         if (lane_fast_out) { l = idx & (T - 1); e = idx >> a.logT; } else { e = idx & (S - 1); l = idx >> a.logS; }
         if (lane0 + l >= a.nlanes) continue;
-        fe v = sm[l * SP + pad(e)];
+        fe v = sm[l * SP + pad(e)];   // in [0, 2p): a multiplication below brings it under p, otherwise one subtraction does
+        if (!(a.tw_logn || postA || postB || a.use_scalar)) v = reduce_2p(v);
         if (a.tw_logn) v = mul(v, root_pow(a.W, a.logW, a.tw_logn, (unsigned long long)e * (lane0 + l), a.inverse));
         if (postA) v = mul(v, postA[e]);
         if (postB) v = mul(v, postB[lane0 + l]);
