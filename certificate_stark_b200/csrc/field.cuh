@@ -113,7 +113,8 @@ CSG_HD fe sqr(fe a) { return mul(a, a); }
 //   mul_2p: a < 2p, b < p  ->  a*b*2^-64 mod p, below 1.52 p, no conditional subtraction
 //   add_2p / sub_2p: operands and result in [0, 2p)
 CSG_HD uint64_t mul_2p(uint64_t a, fe b) { u128 t = mul_wide(a, b); return redc_raw(t.lo, t.hi); }
-CSG_HD uint64_t add_2p(uint64_t a, uint64_t b) { uint64_t s = a + b; return s >= 2 * P ? s - 2 * P : s; }
+CSG_HD uint64_t add_2p(uint64_t a, uint64_t b) { uint64_t s = a + b; return s >= 2 * P ? s - 2 * P : s; }   // needs a + b < 2^64: one operand from mul_2p
+CSG_HD uint64_t add_2p_any(uint64_t a, uint64_t b) { const uint64_t t = 2 * P - b; return a >= t ? a - t : a + b; }   // any a, b < 2p (4p > 2^64)
 CSG_HD uint64_t sub_2p(uint64_t a, uint64_t b) { return a >= b ? a - b : a + 2 * P - b; }
 CSG_HD fe reduce_2p(uint64_t a) { return a >= P ? a - P : a; }
 CSG_HD fe add(fe a, fe b) { uint64_t s = a + b; return s >= P ? s - P : s; }

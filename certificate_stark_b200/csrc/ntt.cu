@@ -1,4 +1,5 @@
 // See ntt.cuh for the design.  Hand-written for sm_100a: no library FFT exists for this field.
+#include <cstdlib>
 #include <vector>
 
 #include "ntt.cuh"
@@ -135,7 +136,178 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------- 1024-point passes, one warp per lane
+// The two-pass sizes that matter most (n = 2^19 .. 2^21: trace lengths of 512-2048 transactions) have 1024-point
+// sub-transforms.  For those a warp owns one lane and does the whole sub-transform as 32 x 32 (four-step inside the warp):
+//     i = 32a + b,  k = c + 32d:   X[c + 32d] = sum_b w32^(bd) * ( w1024^(bc) * sum_a w32^(ac) x[32a + b] )
+// thread b runs a 32-point transform over a entirely in registers (decimation in frequency, lazy butterflies, the 31 unit
+// twiddles skipped), multiplies by w1024^(bc), the warp transposes through its own 8 KB of shared memory (XOR swizzle,
+// conflict free, __syncwarp only), thread c runs the second 32-point transform over b and the warp leaves X in natural order
+// in its lane of the tile.  Two block-wide barriers and three trips through shared memory per pass instead of five and five;
+// 4 modular multiplications per element instead of 5.  Lanes whose elements are contiguous in memory (pass B) are read
+// straight from global memory; strided lanes (pass A) are staged as a tile of 8 adjacent lanes, as are all outputs.
+struct Fft32Tw { fe w[16]; };   // w32^j, j < 16 (forward or inverse)
+
+// 32-point transform in registers, decimation in time: v[r] = x[brev5(r)] on entry, v[k] = X[k] on exit; values in [0, 2p)
+__device__ __forceinline__ void fft32_dit(uint64_t (&v)[32], const Fft32Tw &tw) {
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+        const int h = 1 << t;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (j & h) continue;
+            const int ti = (j & (h - 1)) << (4 - t);
+            const uint64_t x = v[j];
+            if (ti) {
+                const uint64_t y = mul_2p(v[j + h], tw.w[ti]);
+                v[j] = add_2p(x, y);
+                v[j + h] = sub_2p(x, y);
+            } else {   // unit twiddle: no multiplication, so the sum of two values below 2p needs the overflow-safe form
+                const uint64_t y = v[j + h];
+                v[j] = add_2p_any(x, y);
+                v[j + h] = sub_2p(x, y);
+            }
+        }
+    }
+}
+__device__ __forceinline__ constexpr int brev5(int r) { return ((r & 1) << 4) | ((r & 2) << 2) | (r & 4) | ((r & 8) >> 2) | ((r & 16) >> 4); }
+
+// F_LANES lanes (= warps) per CTA; lane pitch chosen so that the staged accesses (lane fastest) of a half-warp hit distinct banks
+template <int F_LANES> struct FastShape { static constexpr unsigned SP = F_LANES == 8 ? 1024 + 2 : 1024 + 4, THREADS = 32 * F_LANES, LOG = F_LANES == 8 ? 3 : 2; };
+
+template <bool STAGE_IN, int F_LANES>
+__global__ void __launch_bounds__(32 * F_LANES, 512 / (32 * F_LANES)) ntt1024_kernel(PassArgs a, Fft32Tw tw32) {
+    constexpr unsigned F_SP = FastShape<F_LANES>::SP, NTH = FastShape<F_LANES>::THREADS, LLOG = FastShape<F_LANES>::LOG;
+    extern __shared__ fe sm[];
+    fe *T2 = sm + (size_t)F_LANES * F_SP;          // w1024^(+-b c) at [c*32 + b]
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned lane0 = blockIdx.x * F_LANES;
+    const fe *in = a.in + blockIdx.y * a.in_by + blockIdx.z * a.in_bz;
+    fe *out = a.out + blockIdx.y * a.out_by + blockIdx.z * a.out_bz;
+    const fe *preA = a.preA ? a.preA + blockIdx.z * a.pre_bz : nullptr;
+    const fe *preB = a.preB ? a.preB + blockIdx.z * a.pre_bz : nullptr;
+
+    for (unsigned j = tid; j < 1024; j += NTH) T2[j] = root_pow(a.W, a.logW, 10, ((j >> 5) * (j & 31)) & 1023, a.inverse);
+
+    // The coset pre-scale s^m of element m = e*n2 + lane factors as preA[e] * preB[lane].  A per-lane factor commutes with the
+    // transform along the lane, so in a staged pass with an output twiddle (pass A) only preA[e] (a 1024-entry table that
+    // stays in L1) is applied on the way in and preB[lane] joins the twiddle on the way out: the data are then the only
+    // stream read from HBM (the full per-coset table and the twiddle gather of the generic kernel are not needed).
+    const bool fold = STAGE_IN && a.tw_logn && preA && preB;
+    auto load_scaled = [&](unsigned e, unsigned l) -> fe {
+        const unsigned long long m = e * a.in_se + (lane0 + l) * a.in_sl;
+        fe v = in[m];
+        if (fold) return mul(v, preA[e]);
+        if (a.preFull) v = mul(v, a.preFull[blockIdx.z * a.pre_full_bz + m]);
+        else {
+            if (preA) v = mul(v, preA[e]);
+            if (preB) v = mul(v, preB[lane0 + l]);
+        }
+        return v;
+    };
+    if (STAGE_IN) {
+#pragma unroll 8
+        for (unsigned idx = tid; idx < 1024 * F_LANES; idx += NTH) {
+            const unsigned l = idx & (F_LANES - 1), e = idx >> LLOG;
+            sm[l * F_SP + e] = lane0 + l < a.nlanes ? load_scaled(e, l) : 0;
+        }
+    }
+    __syncthreads();
+
+    fe *mine = sm + warp * F_SP;
+    if (lane0 + warp < a.nlanes) {
+        uint64_t v[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = STAGE_IN ? mine[32 * brev5(k) + lane] : load_scaled(32 * brev5(k) + lane, warp);   // register r: a = brev5(r)
+        __syncwarp();
+#pragma unroll 1
+        for (int phase = 0; phase < 2; phase++) {
+            fft32_dit(v, tw32);
+            if (phase == 0) {
+                // register c holds Y_b[c], b = lane: twiddle, then hand element (b, c) to thread c
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const uint64_t val = c ? mul_2p(v[c], T2[c * 32 + lane]) : v[c];
+                    mine[lane * 32 + (c ^ lane)] = val;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 32; r++) v[r] = mine[brev5(r) * 32 + (lane ^ brev5(r))];   // register r: b = brev5(r)
+                __syncwarp();
+            }
+        }
+        // register d holds X[c + 32 d], c = lane
+#pragma unroll
+        for (int dd = 0; dd < 32; dd++) mine[lane + 32 * dd] = v[dd];
+    }
+    __syncthreads();
+
+    const fe *postA = a.postA ? a.postA + blockIdx.z * a.post_bz : nullptr;
+    const fe *postB = a.postB ? a.postB + blockIdx.z * a.post_bz : nullptr;
+    if (a.tw_logn && !postA && !postB && !a.use_scalar) {
+        // pass A: element e of lane L is multiplied by w_n^(+-e L) (times preB[L] when folded).  A thread keeps one lane and
+        // walks e in steps of 32: the factors form a geometric sequence, two interleaved chains, no table gather
+        const unsigned l = tid & (F_LANES - 1), e0 = tid >> LLOG, L = lane0 + l;
+        if (L < a.nlanes) {
+            const fe step = root_pow(a.W, a.logW, a.tw_logn, 32ULL * L, a.inverse), step2 = sqr(step);
+            fe g0 = root_pow(a.W, a.logW, a.tw_logn, (unsigned long long)e0 * L, a.inverse);
+            if (fold) g0 = mul(g0, preB[L]);
+            fe g1 = mul(g0, step);
+            fe *o = out + L * a.out_sl;
+            const fe *src = sm + l * F_SP;
+#pragma unroll 4
+            for (unsigned k = 0; k < 32; k += 2) {
+                const unsigned ea = e0 + 32 * k, eb = ea + 32;
+                o[ea * a.out_se] = mul(src[ea], g0);
+                o[eb * a.out_se] = mul(src[eb], g1);
+                g0 = mul(g0, step2); g1 = mul(g1, step2);
+            }
+        }
+        return;
+    }
+#pragma unroll 4
+    for (unsigned idx = tid; idx < 1024 * F_LANES; idx += NTH) {
+        const unsigned l = idx & (F_LANES - 1), e = idx >> LLOG;
+        if (lane0 + l >= a.nlanes) continue;
+        fe v = sm[l * F_SP + e];   // in [0, 2p)
+        if (!(a.tw_logn || postA || postB || a.use_scalar)) v = reduce_2p(v);
+        if (a.tw_logn) v = mul(v, root_pow(a.W, a.logW, a.tw_logn, (unsigned long long)e * (lane0 + l), a.inverse));
+        if (postA) v = mul(v, postA[e]);
+        if (postB) v = mul(v, postB[lane0 + l]);
+        if (a.use_scalar) v = mul(v, a.scalar);
+        out[e * a.out_se + (lane0 + l) * a.out_sl] = v;
+    }
+}
+
+// the warp-per-lane kernel applies when the sub-transform has 1024 points, adjacent lanes are adjacent in the output
+// (tile store), and the input is either a tile of adjacent lanes too (pass A) or contiguous per lane (pass B)
+bool fast1024_applies(const PassArgs &a) {
+    static const bool off = getenv("CSG_NTT_GENERIC") != nullptr;   // A/B testing against the generic kernel
+    if (off || a.logS != 10 || a.out_sl != 1 || a.nlanes < 8) return false;
+    return a.in_sl == 1 || a.in_se == 1;
+}
+template <bool STAGE_IN, int F_LANES>
+void launch_fast1024_as(const PassArgs &a, const Fft32Tw &tw, unsigned ncols, unsigned ncosets, Stream &st) {
+    const size_t smem = ((size_t)F_LANES * FastShape<F_LANES>::SP + 1024) * sizeof(fe);
+    dim3 grid((a.nlanes + F_LANES - 1) / F_LANES, ncols, ncosets);
+    CSG_CUDA(cudaFuncSetAttribute(ntt1024_kernel<STAGE_IN, F_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CSG_LAUNCH(st, (ntt1024_kernel<STAGE_IN, F_LANES>), grid, FastShape<F_LANES>::THREADS, smem, a, tw);
+}
+void launch_fast1024(const PassArgs &a, unsigned ncols, unsigned ncosets, Stream &st) {
+    Fft32Tw tw;
+    fe w32 = root_of_unity(5);
+    if (a.inverse) w32 = inv(w32);
+    fe acc = ONE;
+    for (int j = 0; j < 16; j++) { tw.w[j] = acc; acc = mul(acc, w32); }
+    static const int lanes_a = getenv("CSG_NTT_LANES_A") ? atoi(getenv("CSG_NTT_LANES_A")) : 4;   // tuning knobs (A/B runs)
+    static const int lanes_b = getenv("CSG_NTT_LANES_B") ? atoi(getenv("CSG_NTT_LANES_B")) : 8;
+    if (a.in_sl == 1) { if (lanes_a == 8) launch_fast1024_as<true, 8>(a, tw, ncols, ncosets, st); else launch_fast1024_as<true, 4>(a, tw, ncols, ncosets, st); }
+    else { if (lanes_b == 8) launch_fast1024_as<false, 8>(a, tw, ncols, ncosets, st); else launch_fast1024_as<false, 4>(a, tw, ncols, ncosets, st); }
+}
+
 void launch_pass(const PassArgs &a, unsigned ncols, unsigned ncosets, Stream &st) {
+    if (fast1024_applies(a)) { launch_fast1024(a, ncols, ncosets, st); return; }
     const unsigned S = 1u << a.logS, T = 1u << a.logT;
     size_t smem = ((size_t)T * lane_pitch(S) + S / 2 + 1) * sizeof(fe);
     if (smem > 48 * 1024)   // per device and cheap: set whenever a launch needs more than the default 48 KB

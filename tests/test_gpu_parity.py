@@ -14,7 +14,8 @@ def rand_field(rng, shape):
 
 
 # ---------------------------------------------------------------------------------------------- kernels
-@pytest.mark.parametrize("logn,width,blowup", [(1, 3, 2), (3, 5, 4), (6, 2, 8), (10, 14, 4), (11, 3, 8), (12, 7, 8), (13, 2, 2), (16, 3, 8), (20, 1, 2)])
+@pytest.mark.parametrize("logn,width,blowup", [(1, 3, 2), (3, 5, 4), (6, 2, 8), (10, 14, 4), (11, 3, 8), (12, 7, 8), (13, 2, 2), (16, 3, 8), (20, 1, 2),
+                                               (19, 2, 4), (20, 3, 8), (21, 1, 2)])   # 2^19..2^21: the warp-per-lane 1024-point passes
 def test_lde_matches_oracle(ctx, oracle, logn, width, blowup):
     rng = np.random.default_rng(logn * 100 + width)
     n = 1 << logn
