@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(32 * F_LANES, 512 / (32 * F_LANES)) ntt1024_ke
     // transform along the lane, so in a staged pass with an output twiddle (pass A) only preA[e] (a 1024-entry table that
     // stays in L1) is applied on the way in and preB[lane] joins the twiddle on the way out: the data are then the only
     // stream read from HBM (the full per-coset table and the twiddle gather of the generic kernel are not needed).
-    const bool fold = STAGE_IN && a.tw_logn && preA && preB;
+    const bool fold = a.tw_logn && preA && preB;
     auto load_scaled = [&](unsigned e, unsigned l) -> fe {
         const unsigned long long m = e * a.in_se + (lane0 + l) * a.in_sl;
         fe v = in[m];
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(32 * F_LANES, 512 / (32 * F_LANES)) ntt1024_ke
         return v;
     };
     if (STAGE_IN) {
-#pragma unroll 8
+#pragma unroll 8   // 16 in flight was slower (registers); reading strided lanes straight from global memory was no faster either
         for (unsigned idx = tid; idx < 1024 * F_LANES; idx += NTH) {
             const unsigned l = idx & (F_LANES - 1), e = idx >> LLOG;
             sm[l * F_SP + e] = lane0 + l < a.nlanes ? load_scaled(e, l) : 0;
@@ -300,7 +300,7 @@ void launch_fast1024(const PassArgs &a, unsigned ncols, unsigned ncosets, Stream
     if (a.inverse) w32 = inv(w32);
     fe acc = ONE;
     for (int j = 0; j < 16; j++) { tw.w[j] = acc; acc = mul(acc, w32); }
-    static const int lanes_a = getenv("CSG_NTT_LANES_A") ? atoi(getenv("CSG_NTT_LANES_A")) : 4;   // tuning knobs (A/B runs)
+    static const int lanes_a = getenv("CSG_NTT_LANES_A") ? atoi(getenv("CSG_NTT_LANES_A")) : 8;   // tuning knobs (A/B runs)
     static const int lanes_b = getenv("CSG_NTT_LANES_B") ? atoi(getenv("CSG_NTT_LANES_B")) : 8;
     if (a.in_sl == 1) { if (lanes_a == 8) launch_fast1024_as<true, 8>(a, tw, ncols, ncosets, st); else launch_fast1024_as<true, 4>(a, tw, ncols, ncosets, st); }
     else { if (lanes_b == 8) launch_fast1024_as<false, 8>(a, tw, ncols, ncosets, st); else launch_fast1024_as<false, 4>(a, tw, ncols, ncosets, st); }
