@@ -78,10 +78,16 @@ fe slot_coefficient(const fe *alpha, const fe *beta, const uint8_t *group, const
 // Split mode exists for the constraints whose degree stays below half the composition degree (Rescue rounds, Merkle and
 // copy logic: < 4n for the transaction and Schnorr AIRs): A and the B_g are then polynomials of degree < 4n, evaluated on
 // half of the constraint-evaluation cosets only and extended to the other half with two small transforms.
+// Extension fields (DEG = 2, 3): the coefficients alpha_s, beta_s are elements of E while the constraint values stay in the
+// base field, so component j of T(x) is the same combination with component j of every coefficient.  `sum` accumulates
+// component 0 and sum_x[j-1] component j; the extra components live at alpha_x[(j-1) * coef_stride + slot].  One evaluation
+// of the constraints feeds all DEG accumulators (combined mode only).
 constexpr int MAX_SPLIT_GROUPS = 6;
-template <bool SPLIT>
+template <bool SPLIT, int DEG = 1>
 struct CombT {
     static constexpr bool split = SPLIT;
+    static constexpr int D = DEG;
+    static_assert(!SPLIT || DEG == 1, "the low-degree split is implemented for base-field coefficients");
     const fe *alpha, *beta;
     const uint8_t *group;
     const fe *xp;        // x^adj per degree group, element g at xp[g * xp_stride]   (combined mode only)
@@ -91,9 +97,20 @@ struct CombT {
     // part[(3 * g + k) * part_stride] -- the group of a slot is only known at run time, and a register file cannot be indexed
     uint64_t *part;
     size_t part_stride;
+    const fe *alpha_x = nullptr, *beta_x = nullptr;
+    size_t coef_stride = 0;
+    f63::acc192 sum_x[DEG > 1 ? DEG - 1 : 1];
     CSG_HD fe coef(int slot) const { return slot_coefficient(alpha, beta, group, xp, xp_stride, slot); }
+    CSG_HD fe coef_x(int j, int slot) const { return slot_coefficient(alpha_x + (j - 1) * coef_stride, beta_x + (j - 1) * coef_stride, group, xp, xp_stride, slot); }
     CSG_HD void add(int slot, fe v) {
-        if (!SPLIT) { sum.mac(coef(slot), v); return; }
+        if (!SPLIT) {
+            sum.mac(coef(slot), v);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int j = 1; j < DEG; j++) sum_x[j - 1].mac(coef_x(j, slot), v);
+            return;
+        }
         sum.mac(alpha[slot], v);
         uint64_t *q = part + (size_t)group[slot] * 3 * part_stride;
         f63::acc192 t;
@@ -113,13 +130,27 @@ using SplitComb = CombT<true>;
 // contributions that share one flag.  Combined mode: sum_k coef(slot_k) * v_k, multiplied by the flag once at flush time;
 // split mode: the flag is multiplied into every value (there is no single coefficient to factor it out of).
 struct FlagAcc {
-    f63::acc192 s;
+    f63::acc192 s, sx[2];   // sx: components 1, 2 of E-valued coefficients (untouched, hence free, in the base field)
     fe flag;
     CSG_HD explicit FlagAcc(fe f) : flag(f) {}
     template <class CB> CSG_HD void add(CB &C, int slot, fe v) {
-        if (!CB::split) s.mac(C.coef(slot), v); else C.add(slot, f63::mul(flag, v));
+        if (!CB::split) {
+            s.mac(C.coef(slot), v);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int j = 1; j < CB::D; j++) sx[j - 1].mac(C.coef_x(j, slot), v);
+        } else C.add(slot, f63::mul(flag, v));
     }
-    template <class CB> CSG_HD void flush(CB &C) { if (!CB::split) C.sum.mac(flag, s.reduce()); }
+    template <class CB> CSG_HD void flush(CB &C) {
+        if (!CB::split) {
+            C.sum.mac(flag, s.reduce());
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int j = 1; j < CB::D; j++) C.sum_x[j - 1].mac(flag, sx[j - 1].reduce());
+        }
+    }
 };
 
 CSG_HD fe f_not(fe a) { return f63::sub(f63::ONE, a); }

@@ -46,6 +46,10 @@ struct ConsArgs {
     unsigned a_poly_len[CONS_MAX_ASSERTIONS];            // > 1: value polynomial of that many coefficients at a_poly_off
     unsigned long long a_poly_off[CONS_MAX_ASSERTIONS];
     fe a_xoff[CONS_MAX_ASSERTIONS];                      // the polynomial is evaluated at x * a_xoff
+    // FieldExtension::Quadratic / Cubic: components 1 (and 2) of the E-valued coefficients; component 0 is alpha / beta above
+    unsigned ext_degree;
+    fe alpha_x[2][CONS_MAX_CONSTRAINTS], beta_x[2][CONS_MAX_CONSTRAINTS];
+    fe a_alpha_x[2][CONS_MAX_ASSERTIONS], a_beta_x[2][CONS_MAX_ASSERTIONS];
 };
 
 // lde: coset-major extended trace; W: root table of size n; ptab / apoly: periodic tables and assertion value
@@ -54,6 +58,10 @@ void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &args
                       const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr,   // ev: 5 events bracketing the 4 phases
                       const RootTable *rt = nullptr, NttScratch *sc = nullptr);   // given: low-degree constraints use half of the cosets (TX, Schnorr)
 size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets);
+// the same with E-valued coefficients (args.ext_degree = 2 or 3): one pass over the rows, component j of the merged column
+// written to out[(j * ncosets + kc) * n + i]; part: ext_degree times the scratch of the base-field call
+void eval_constraints_ext(int air_id, const ConsArgs *args_dev, const ConsArgs &args_host, const fe *lde, const fe *W, const fe *ptab,
+                          const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr);
 
 unsigned long long redc_violations();   // debug builds (-DCSG_REDC_CHECK): reductions entered with an out-of-range operand
 

@@ -322,13 +322,14 @@ struct csg_ctx {
     // ------------------------------------------------------------------------------------------ stage 3
     // plane: which component of the E-valued coefficients these are (0 for the base field); the merged column of component j
     // lands in d_comb[j][ce coset][row]
-    void eval_constraints(const fe *t_ab, const fe *b_ab, int plane = 0) {
+    void eval_constraints(const fe *t_ab, const fe *b_ab, int plane = 0, bool all_components = false) {
         need(S_COMMITTED, "the trace must be committed first");
         Timer &t = stage_timer;
         t.start(st);
         ConsArgs &A = *h_cargs;
         const fe g = root_of_unity(logn);
         A.logn = logn; A.ncosets = (unsigned)cel; A.col_stride = n; A.width = air.width;
+        A.ext_degree = all_components ? (unsigned)d : 1;
         A.g_last = f63::pow(g, n - 1);
         A.nconstraints = (unsigned)air.num_constraints(); A.ngroups = (unsigned)tg.adj.size();
         for (size_t i = 0; i < air.num_constraints(); i++) { A.alpha[i] = t_ab[2 * i]; A.beta[i] = t_ab[2 * i + 1]; A.group[i] = tg.group_of[i]; }
@@ -368,29 +369,42 @@ struct csg_ctx {
         CSG_CUDA(cudaMemcpyAsync(d_cargs.p, &A, sizeof A, cudaMemcpyHostToDevice, st.s));
         const size_t comb_plane = (cel ? cel : 1) * n;
         d_comb.reserve(comb_plane * d);
-        d_parts.reserve(constraint_scratch_elements(air.id, n, cel ? cel : 1));
+        d_parts.reserve(constraint_scratch_elements(air.id, n, cel ? cel : 1) * (all_components ? d : 1));
         if (!cons_ev[0]) for (auto &e : cons_ev) CSG_CUDA(cudaEventCreate(&e));
         // the low-degree split interpolates across the even cosets: only when this context owns all of them
         const bool split = split_low_degree && G == 1;
-        if (cel) csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p + plane * comb_plane, st, cons_ev,
-                                       split ? &roots : nullptr, split ? &ntt : nullptr);
+        if (cel && all_components) csg::eval_constraints_ext(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st, cons_ev);
+        else if (cel) csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p + plane * comb_plane, st, cons_ev,
+                                            split ? &roots : nullptr, split ? &ntt : nullptr);
         else for (auto &e : cons_ev) CSG_CUDA(cudaEventRecord(e, st.s));
         const float ms = t.stop(st);   // also keeps `polys` alive until the copy has completed
         tm.constraints = plane ? tm.constraints + ms : ms;
         float *parts_ms[4] = {&tm.cons_rescue, &tm.cons_ecc_banks, &tm.cons_ecc_final, &tm.cons_rest};
         for (int k = 0; k < 4; k++) { float pm = 0; CSG_CUDA(cudaEventElapsedTime(&pm, cons_ev[k], cons_ev[k + 1])); *parts_ms[k] = plane ? *parts_ms[k] + pm : pm; }
-        if (plane + 1 == d) stage = S_EVALUATED;
+        if (plane + 1 == d || all_components) stage = S_EVALUATED;
     }
     // E-valued coefficients: the constraint values are base-field elements, so component j of the merged column is the same
     // combination with component j of every coefficient -- d passes of the base-field evaluation
     void eval_constraints_x(const xe *t_ab, const xe *b_ab) {
         const size_t nc = air.num_constraints(), na = air.assertions.size();
         std::vector<fe> tj(2 * nc), bj(2 * na + 2);
-        for (int j = 0; j < d; j++) {
-            for (size_t i = 0; i < 2 * nc; i++) tj[i] = t_ab[i].c[j];
-            for (size_t i = 0; i < 2 * na; i++) bj[i] = b_ab[i].c[j];
-            eval_constraints(tj.data(), bj.data(), j);
+        if (getenv("CSG_EXT_PASSES")) {   // A/B: one pass of the base-field kernels per component
+            for (int j = 0; j < d; j++) {
+                for (size_t i = 0; i < 2 * nc; i++) tj[i] = t_ab[i].c[j];
+                for (size_t i = 0; i < 2 * na; i++) bj[i] = b_ab[i].c[j];
+                eval_constraints(tj.data(), bj.data(), j);
+            }
+            return;
         }
+        // one pass: every thread accumulates all d components (constraints_ext.cu)
+        ConsArgs &A = *h_cargs;
+        for (int j = 1; j < d; j++) {
+            for (size_t i = 0; i < nc; i++) { A.alpha_x[j - 1][i] = t_ab[2 * i].c[j]; A.beta_x[j - 1][i] = t_ab[2 * i + 1].c[j]; }
+            for (size_t i = 0; i < na; i++) { A.a_alpha_x[j - 1][i] = b_ab[2 * i].c[j]; A.a_beta_x[j - 1][i] = b_ab[2 * i + 1].c[j]; }
+        }
+        for (size_t i = 0; i < 2 * nc; i++) tj[i] = t_ab[i].c[0];
+        for (size_t i = 0; i < 2 * na; i++) bj[i] = b_ab[i].c[0];
+        eval_constraints(tj.data(), bj.data(), 0, true);
     }
     // coefficients of the polynomial taking the given values on <w_len> (host, tiny: one value per signature)
     static std::vector<fe> host_interpolate(const std::vector<fe> &vals) {
