@@ -41,6 +41,11 @@ class ProofOptions(C.Structure):
         super().__init__(num_queries, blowup_factor, grinding_factor, hash_fn, field_extension, fri_folding_factor, fri_max_remainder_size)
 
 
+class ShardPlan(C.Structure):
+    """csg_shard_plan: what one rank of a coset-sharded proof owns"""
+    _fields_ = [(n, C.c_uint32) for n in ("first_coset", "num_cosets", "first_ce_coset", "num_ce_cosets", "first_column", "num_columns", "columns_per_rank")]
+
+
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d", "lde", "commit_trace", "constraints", "composition", "ood_deep", "fri", "queries", "total")] + \
                [("kernel_launches", C.c_uint64)] + [(n, C.c_float) for n in ("cons_rescue", "cons_ecc_banks", "cons_ecc_final", "cons_rest", "comm")]
@@ -88,6 +93,7 @@ def lib() -> C.CDLL:
         "csg_verify": (C.c_int, [C.c_int, _u64p, C.c_size_t, _u8p, C.c_size_t]),
         "csg_get_timings": (C.c_int, [vp, C.POINTER(Timings)]),
         "csg_dist_unique_id": (C.c_int, [_u8p]), "csg_dist_init": (C.c_int, [vp, C.c_int, C.c_int, _u8p]),
+        "csg_dist_plan": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ShardPlan)]),
         "csg_dist_init_local": (C.c_int, [C.POINTER(vp), C.c_int]), "csg_dist_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "csg_timer_start": (C.c_int, [vp]), "csg_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "csg_tx_batch_new": (vp, [C.c_uint64, C.c_size_t, C.c_uint]), "csg_tx_batch_free": (None, [vp]), "csg_tx_batch_size": (C.c_size_t, [vp]),
@@ -274,6 +280,14 @@ class Context:
         ms = (C.c_float * 4)()
         self._check(lib().csg_k_sweep(self._h, width, n, blowup, hash_fn, iters, ms))
         return dict(zip(("lde_ms", "hash_rows_ms", "merkle_ms", "fri_fold_ms"), [float(v) for v in ms]))
+
+
+def dist_plan(rank: int, world: int, blowup: int, ce_blowup: int, width: int) -> ShardPlan:
+    """ownership of rank `rank` in a `world`-way sharded proof (csg_dist_plan); host-only"""
+    p = ShardPlan()
+    if lib().csg_dist_plan(rank, world, blowup, ce_blowup, width, C.byref(p)):
+        raise CsgError("world must be a power of two dividing the blowup factor, rank below it")
+    return p
 
 
 def dist_unique_id() -> bytes:

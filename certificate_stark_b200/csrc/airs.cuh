@@ -285,6 +285,35 @@ CSG_HD void scalar_mult_bank(const Frame &f, CB &C, int o, const fe (&q)[12], fe
         a.flush(C);
     }
 }
+// ---- the same bank for the low-degree split of the curve constraints.  The outputs of either formula are polynomials of
+// degree 4(n-1) in the trace polynomials; only their products with the row's bit and the periodic flags exceed 4n.  So
+//     T_bank = doubling * (sum_i c_i next_i + c_b bit(bit-1) - Cd)  +  addition * (sum_i c_i (next_i - (1-bit) cur_i) + c_b (bit - bit') - bit * Cm)
+// with Cd = sum_i c_i d_i, Cm = sum_i c_i m_i the merged outputs of the doubling / mixed-addition formula: Cd and Cm (alpha
+// part and per-group beta parts, split mode) are evaluated on the even cosets only and extended by NTT, the rest is cheap.
+template <class CB>
+CSG_HD void scalar_mult_bank_outputs(const Frame &f, CB &C, int o, const fe (&q)[12], int formula) {
+    ecc::point p;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; i++) { p.x.c[i] = f.cur(o + i); p.y.c[i] = f.cur(o + 6 + i); p.z.c[i] = f.cur(o + 12 + i); }
+    const ecc::point r = formula == 0 ? ecc::double_point(p) : ecc::add_mixed(p, ecc::load6(q), ecc::load6(q + 6));
+    for (int i = 0; i < 6; i++) { C.add(o + i, r.x.c[i]); C.add(o + 6 + i, r.y.c[i]); C.add(o + 12 + i, r.z.c[i]); }
+}
+template <class CB>
+CSG_HD fe scalar_mult_bank_merge(const Frame &f, const CB &C, int o, fe doubling, fe addition, fe Cd, fe Cm) {
+    const fe bit = f.cur(o + PPW), nbit = f_not(bit);
+    f63::acc192 sd, sa;
+    for (int i = 0; i < PPW; i++) {
+        const fe c = C.coef(o + i), nx = f.next(o + i);
+        sd.mac(c, nx);
+        sa.mac(c, f63::sub(nx, f63::mul(nbit, f.cur(o + i))));
+    }
+    const fe cb = C.coef(o + PPW);
+    const fe td = f63::sub(f63::add(sd.reduce(), f63::mul(cb, f_bin(bit))), Cd);
+    const fe ta = f63::sub(f63::add(sa.reduce(), f63::mul(cb, f63::sub(bit, f.next(o + PPW)))), f63::mul(bit, Cm));
+    return f63::add(f63::mul(doubling, td), f63::mul(addition, ta));
+}
 // last step of a signature: S + h.P, x reduced to affine, and h must equal the hash output
 // (src/schnorr/air.rs:506-530, src/utils/ecc.rs:146-172)
 template <class CB>
@@ -376,6 +405,21 @@ CSG_HD void eval_ecc_bank(int bank, const Frame &f, const PV &pv, CB &C) {
     const uint64_t *gen = CSG_TABLE(CSG_GENERATOR);
     for (int j = 0; j < 12; j++) q[j] = bank == 0 ? gen[j] : (AIR == TRANSACTION ? f.next(SENDER_KEY + j) : pv(7 + j));
     scalar_mult_bank(f, C, bank * (PPW + 1), q, doubling, addition);
+}
+template <int AIR, class PV, class CB>
+CSG_HD void eval_ecc_bank_outputs(int bank, int formula, const Frame &f, const PV &pv, CB &C) {
+    if (AIR != TRANSACTION && AIR != SCHNORR) return;
+    fe q[12];
+    const uint64_t *gen = CSG_TABLE(CSG_GENERATOR);
+    for (int j = 0; j < 12; j++) q[j] = bank == 0 ? gen[j] : (AIR == TRANSACTION ? f.next(SENDER_KEY + j) : pv(7 + j));
+    scalar_mult_bank_outputs(f, C, bank * (PPW + 1), q, formula);
+}
+template <int AIR, class PV, class CB>
+CSG_HD fe eval_ecc_bank_merge(int bank, const Frame &f, const PV &pv, const CB &C, fe Cd, fe Cm) {
+    if (AIR != TRANSACTION && AIR != SCHNORR) return 0;
+    const fe scalar_mult = pv(AIR == TRANSACTION ? TX_SCALAR_MULT : 1);
+    const fe doubling = pv(AIR == TRANSACTION ? TX_DOUBLING : 2), addition = f63::mul(f_not(doubling), scalar_mult);
+    return scalar_mult_bank_merge(f, C, bank * (PPW + 1), doubling, addition, Cd, Cm);
 }
 template <int AIR, class PV, class CB>
 CSG_HD void eval_ecc_final(const Frame &f, const PV &pv, CB &C) {

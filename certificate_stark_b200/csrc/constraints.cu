@@ -5,6 +5,7 @@
 // adds the cheap linear constraints, sums the partials, applies the divisors and the boundary constraints and writes the
 // merged column.  Splitting the row's work this way keeps each kernel's code and register footprint small (the
 // monolithic version ran at 8 warps/SM with 20 % of its stalls on instruction fetch) and multiplies the parallelism.
+#include <cstdlib>
 #include <vector>
 
 #include "airs.cuh"
@@ -38,6 +39,56 @@ cons_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, cons
     fe *dst = low + (((unsigned long long)item * NP) * L + j) * n + i;
     dst[0] = C.sum.reduce();
     for (unsigned g = 0; g + 1 < NP; g++) dst[(unsigned long long)(1 + g) * L * n] = C.part_value((int)g);
+}
+
+// ---- low-degree split of the scalar-multiplication banks (airs.cuh, scalar_mult_bank_outputs): the merged outputs of the
+// doubling and the mixed-addition formula of each bank -- 4 variants -- on the even cosets, as an alpha polynomial and one
+// beta polynomial per degree group the bank's slots fall into.
+constexpr unsigned ECC_SPLIT_MAX_POLYS = 16;
+struct EccSplitMap {
+    unsigned npolys[2];                                // bank b: 1 + number of groups among its point slots
+    unsigned char groups[2][airs::MAX_SPLIT_GROUPS];   // those groups
+    unsigned base[4];                                  // first polynomial of variant v = 2*bank + formula
+    unsigned total;
+};
+template <int AIR>
+__global__ void __launch_bounds__(CONS_THREADS, CSG_ECC_MINBLOCKS)
+cons_ecc_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ ptab, EccSplitMap M, fe *__restrict__ eccl) {
+    const unsigned j = blockIdx.y, kc = 2 * j, v = blockIdx.z, bank = v >> 1, L = A->ncosets / 2, NP = 1 + A->ngroups;
+    const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long inext = (i + 1) & (n - 1);
+    const fe *base = lde + A->lde_coset_stride[kc];
+    airs::Frame f{base + i, base + inext, (size_t)A->col_stride};
+    airs::Periodic pv{ptab + kc * A->ptab_coset_stride, A->poff, A->pmask, (uint32_t)i};
+    __shared__ uint64_t part_s[3 * airs::MAX_SPLIT_GROUPS][CONS_THREADS];
+    for (unsigned k = 0; k < 3 * (NP - 1); k++) part_s[k][threadIdx.x] = 0;
+    airs::SplitComb C{A->alpha, A->beta, A->group, nullptr, 0, acc192(), &part_s[0][threadIdx.x], (size_t)CONS_THREADS};
+    airs::eval_ecc_bank_outputs<AIR>((int)bank, (int)(v & 1), f, pv, C);
+    fe *dst = eccl + ((unsigned long long)M.base[v] * L + j) * n + i;
+    dst[0] = C.sum.reduce();
+    for (unsigned q = 0; q + 1 < M.npolys[bank]; q++) dst[(unsigned long long)(1 + q) * L * n] = C.part_value((int)M.groups[bank][q]);
+}
+// the banks' contribution to T(x) on every ce coset from the extended formula values; hi[(bank * ncosets + kc) * n + i]
+template <int AIR>
+__global__ void __launch_bounds__(CONS_THREADS)
+cons_ecc_merge_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W, const fe *__restrict__ ptab, EccSplitMap M,
+                      const fe *__restrict__ even, const fe *__restrict__ odd, fe *__restrict__ hi) {
+    __shared__ fe xp_s[airs::MAX_GROUPS][CONS_THREADS];
+    const unsigned kc = blockIdx.y, bank = blockIdx.z, L = A->ncosets / 2;
+    const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
+    if (i >= n) return;
+    RowCtx r = row_setup(A, lde, W, ptab, kc, i, xp_s);
+    airs::Comb C{A->alpha, A->beta, A->group, &xp_s[0][threadIdx.x], (size_t)CONS_THREADS, acc192(), nullptr, 0};
+    const fe *low = ((kc & 1) ? odd : even) + (unsigned long long)(kc >> 1) * n + i;
+    fe merged[2];
+    for (unsigned formula = 0; formula < 2; formula++) {
+        const fe *p = low + (unsigned long long)M.base[2 * bank + formula] * L * n;
+        acc192 s;
+        for (unsigned q = 0; q + 1 < M.npolys[bank]; q++) s.mac(xp_s[M.groups[bank][q]][threadIdx.x], p[(unsigned long long)(1 + q) * L * n]);
+        merged[formula] = add(s.reduce(), p[0]);
+    }
+    hi[((unsigned long long)bank * A->ncosets + kc) * n + i] = airs::eval_ecc_bank_merge<AIR>((int)bank, r.f, r.pv, C, merged[0], merged[1]);
 }
 
 // T(x) from its pieces on every ce coset, then divisors and boundary constraints.
@@ -91,21 +142,10 @@ void launch_split(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, co
     const size_t slab = (size_t)NP * L * n;
     fe *low_parts = part, *low_sum = low_parts + (size_t)(NR + 1) * slab, *low_coef = low_sum + slab, *low_mix = low_coef + slab,
        *low_odd = low_mix + slab, *hi = low_odd + slab, *binv = hi + (size_t)NE * ce * n;
-    auto mark = [&](int k) { if (ev) CSG_CUDA(cudaEventRecord(ev[k], st.s)); };
-    mark(0);
-    CSG_LAUNCH(st, (cons_low_kernel<AIR, 0>), dim3(gx, L, NR), CONS_THREADS, 0, args_dev, lde, W, ptab, low_parts, 0u);
-    mark(1);
-    CSG_LAUNCH(st, (cons_item_kernel<AIR, 1>), dim3(gx, ce, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, hi, 0u);
-    mark(2);
-    CSG_LAUNCH(st, (cons_item_kernel<AIR, 2>), dim3(gx, ce, 1), CONS_THREADS, 0, args_dev, lde, W, ptab, hi, 0u);
-    mark(3);
-    CSG_LAUNCH(st, (cons_low_kernel<AIR, 3>), dim3(gx, L, 1), CONS_THREADS, 0, args_dev, lde, W, ptab, low_parts, (unsigned)NR);
-    sum_slices(low_parts, low_sum, slab, NR + 1, st);
-    // interpolate on the even cosets, evaluate on the odd ones
-    std::vector<fe> sinv(NP * L), sodd(NP * L), mix(L * L);
-    for (unsigned p = 0; p < NP; p++)
-        for (unsigned j = 0; j < L; j++) { sinv[p * L + j] = inv(h.shift[2 * j]); sodd[p * L + j] = h.shift[2 * j + 1]; }
+    // interpolation on the even cosets, L x L mix of the per-coset coefficient sets, evaluation on the odd cosets, for `np`
+    // polynomials laid out [p][L][n]
     const fe w2l = root_of_unity(ilog2(2 * L)), linv = inv(to_mont(L));
+    std::vector<fe> mix(L * L);
     for (unsigned jo = 0; jo < L; jo++)
         for (unsigned je = 0; je < L; je++) {
             const unsigned e = (2 * (jo + L - je) + 1) % (2 * L);   // 2 (j' - j) + 1 mod 2L
@@ -113,16 +153,52 @@ void launch_split(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, co
             for (unsigned t = 0; t < L; t++) { acc = add(acc, cur); cur = mul(cur, step); }
             mix[jo * L + je] = mul(acc, linv);
         }
-    coset_intt_columns(rt, sc, low_sum, n, low_coef, n, h.logn, sinv.data(), (size_t)NP * L, st);
-    coset_mix(low_coef, low_mix, n, L, NP, mix.data(), st);
-    coset_ntt_entries(rt, sc, low_mix, low_odd, (size_t)NP * L, h.logn, sodd.data(), st);
+    auto extend = [&](const fe *even, fe *coef, fe *mixed, fe *odd, unsigned np) {
+        std::vector<fe> sinv(np * L), sodd(np * L);
+        for (unsigned p = 0; p < np; p++)
+            for (unsigned j = 0; j < L; j++) { sinv[p * L + j] = inv(h.shift[2 * j]); sodd[p * L + j] = h.shift[2 * j + 1]; }
+        coset_intt_columns(rt, sc, even, n, coef, n, h.logn, sinv.data(), (size_t)np * L, st);
+        coset_mix(coef, mixed, n, L, np, mix.data(), st);
+        coset_ntt_entries(rt, sc, mixed, odd, (size_t)np * L, h.logn, sodd.data(), st);
+        CSG_CUDA(cudaStreamSynchronize(st.s));   // the staging vectors are read by async copies
+    };
+    // the banks' formula outputs in split mode: which degree groups the point slots of each bank fall into
+    static const bool ecc_split = getenv("CSG_NO_ECC_SPLIT") == nullptr;
+    EccSplitMap M{};
+    for (unsigned b = 0; b < 2; b++) {
+        unsigned cnt = 0;
+        for (unsigned sl = b * (airs::PPW + 1); sl < b * (airs::PPW + 1) + airs::PPW; sl++) {
+            bool seen = false;
+            for (unsigned q = 0; q < cnt; q++) seen = seen || M.groups[b][q] == h.group[sl];
+            if (!seen) M.groups[b][cnt++] = h.group[sl];
+        }
+        M.npolys[b] = 1 + cnt;
+    }
+    for (unsigned v = 0; v < 4; v++) { M.base[v] = M.total; M.total += M.npolys[v >> 1]; }
+    if (M.total > ECC_SPLIT_MAX_POLYS) throw std::runtime_error("too many degree groups for the curve split");
+    const size_t eslab = (size_t)M.total * L * n;
+    fe *eccl_even = binv + (size_t)CONS_MAX_BGROUPS * ce * n, *eccl_coef = eccl_even + eslab, *eccl_mix = eccl_coef + eslab, *eccl_odd = eccl_mix + eslab;
+    auto mark = [&](int k) { if (ev) CSG_CUDA(cudaEventRecord(ev[k], st.s)); };
+    mark(0);
+    CSG_LAUNCH(st, (cons_low_kernel<AIR, 0>), dim3(gx, L, NR), CONS_THREADS, 0, args_dev, lde, W, ptab, low_parts, 0u);
+    mark(1);
+    if (ecc_split) {
+        CSG_LAUNCH(st, cons_ecc_low_kernel<AIR>, dim3(gx, L, 4), CONS_THREADS, 0, args_dev, lde, ptab, M, eccl_even);
+        extend(eccl_even, eccl_coef, eccl_mix, eccl_odd, M.total);
+        CSG_LAUNCH(st, cons_ecc_merge_kernel<AIR>, dim3(gx, ce, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, M, (const fe *)eccl_even, (const fe *)eccl_odd, hi);
+    } else CSG_LAUNCH(st, (cons_item_kernel<AIR, 1>), dim3(gx, ce, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, hi, 0u);
+    mark(2);
+    CSG_LAUNCH(st, (cons_item_kernel<AIR, 2>), dim3(gx, ce, 1), CONS_THREADS, 0, args_dev, lde, W, ptab, hi, 0u);
+    mark(3);
+    CSG_LAUNCH(st, (cons_low_kernel<AIR, 3>), dim3(gx, L, 1), CONS_THREADS, 0, args_dev, lde, W, ptab, low_parts, (unsigned)NR);
+    sum_slices(low_parts, low_sum, slab, NR + 1, st);
+    extend(low_sum, low_coef, low_mix, low_odd, NP);   // interpolate on the even cosets, evaluate on the odd ones
     if (h.nbgroups > 0)
         CSG_LAUNCH(st, boundary_inverse_kernel, dim3((unsigned)((n + INV_CHUNK * INV_THREADS - 1) / (INV_CHUNK * INV_THREADS)), ce, h.nbgroups),
                    INV_THREADS, 0, args_dev, W, binv);
     CSG_LAUNCH(st, cons_final_kernel, dim3(gx, ce), CONS_THREADS, 0, args_dev, lde, W, apoly, (const fe *)low_sum, (const fe *)low_odd, (const fe *)hi,
                (unsigned)NE, (const fe *)binv, out);
     mark(4);
-    CSG_CUDA(cudaStreamSynchronize(st.s));   // the host staging vectors above are read by async copies
 }
 }  // namespace
 
@@ -148,7 +224,7 @@ size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets) {
     default: break;
     }
     // split path: (rescue items + rest) x (1 + groups) x ce/2 partial slabs, 4 more slabs for the extension, curve items, divisors
-    const size_t split = ((items + 1 + 4) * (1 + CONS_MAX_GROUPS) / 2 + 3 + CONS_MAX_BGROUPS) * n * ncosets;
+    const size_t split = ((items + 1 + 4) * (1 + CONS_MAX_GROUPS) / 2 + 3 + CONS_MAX_BGROUPS + 4 * 16 / 2) * n * ncosets;   // + 4 slabs of <= 16 curve polynomials on half of the cosets
     const size_t plain = (items + CONS_MAX_BGROUPS) * n * ncosets;
     return split > plain ? split : plain;
 }

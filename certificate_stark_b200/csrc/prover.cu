@@ -59,6 +59,21 @@ class Timer {   // device time of a stage, CUDA events on the proving stream; th
 
 using namespace csg;
 
+// which part of a sharded proof a rank owns: a contiguous block of LDE cosets (and the ce cosets among them), and the block
+// of trace columns it interpolates.  The one place this geometry is defined; csg_dist_plan exposes it to callers.
+static bool shard_plan(size_t rank, size_t world, size_t b, size_t ce, size_t w, csg_shard_plan *out) {
+    if (world < 1 || rank >= world || b < world || b % world || ce < 1 || ce > b || b % ce) return false;
+    const size_t bl = b / world, k0 = rank * bl, cpr = (w + world - 1) / world;
+    size_t kc0 = 0, cel = 0;
+    for (size_t kc = 0; kc < ce; kc++) {
+        const size_t k = kc * (b / ce);
+        if (k >= k0 && k < k0 + bl) { if (!cel) kc0 = kc; cel++; }
+    }
+    const size_t c_lo = std::min(w, rank * cpr), c_hi = std::min(w, c_lo + cpr);
+    *out = csg_shard_plan{(uint32_t)k0, (uint32_t)bl, (uint32_t)kc0, (uint32_t)cel, (uint32_t)c_lo, (uint32_t)(c_hi - c_lo), (uint32_t)cpr};
+    return true;
+}
+
 struct csg_ctx {
     int device = 0;
     Stream st;
@@ -129,8 +144,9 @@ struct csg_ctx {
         n = trace_len; logn = ilog2(n); b = o->blowup_factor; ce = air.ce_blowup(); lde_n = n * b;
         if (ce > b) throw ArgError("blowup factor is smaller than the constraint evaluation blowup of this AIR");
         G = comm ? (size_t)comm->world : 1; rank = comm ? (size_t)comm->rank : 0;
-        if (G > b || b % G) throw ArgError("the number of ranks of a sharded proof must divide the blowup factor");
-        bl = b / G; k0 = rank * bl;
+        csg_shard_plan plan;
+        if (!shard_plan(rank, G, b, ce, air.width, &plan)) throw ArgError("the number of ranks of a sharded proof must divide the blowup factor");
+        bl = plan.num_cosets; k0 = plan.first_coset;
         if (logn > 22) throw ArgError("trace length above 2^22 is not supported");
         {   // the FRI remainder layer is committed as rows of 4: it needs at least 2 rows
             size_t m = lde_n;
@@ -150,12 +166,8 @@ struct csg_ctx {
         for (size_t k = 0; k < b; k++) { all_shift[k] = acc; acc = mul(acc, w_lde); }
         lde_shift.assign(all_shift.begin() + k0, all_shift.begin() + k0 + bl);
         ce_shift.clear();
-        kc0 = 0;
-        for (size_t kc = 0; kc < ce; kc++) {
-            const size_t k = kc * (b / ce);
-            if (k >= k0 && k < k0 + bl) { if (ce_shift.empty()) kc0 = kc; ce_shift.push_back(all_shift[k]); }
-        }
-        cel = ce_shift.size();
+        kc0 = plan.first_ce_coset; cel = plan.num_ce_cosets;
+        for (size_t kc = kc0; kc < kc0 + cel; kc++) ce_shift.push_back(all_shift[kc * (b / ce)]);
         build_periodic_tables();
         lde_tables.build(lde_shift.data(), bl, logn, st);
         nfri = 0;
@@ -235,7 +247,9 @@ struct csg_ctx {
         const size_t w = air.width;
         // sharded proof: this context interpolates the column block [c_lo, c_hi), the coefficient blocks are all-gathered,
         // and every context extends all columns onto its own cosets
-        const size_t cpr = (w + G - 1) / G, c_lo = std::min(w, rank * cpr), c_hi = std::min(w, c_lo + cpr), wpad = cpr * G;
+        csg_shard_plan plan;
+        shard_plan(rank, G, b, ce, w, &plan);
+        const size_t cpr = plan.columns_per_rank, c_lo = plan.first_column, c_hi = c_lo + plan.num_columns, wpad = cpr * G;
         const size_t CHUNK = host ? 8 : cpr;   // nothing to overlap when the trace is already resident: one chunk
         Timer &t = stage_timer;
         t.start(st);
@@ -1116,6 +1130,10 @@ int csg_dist_init_local(csg_ctx **ctxs, int world) {
             ctxs[r]->stage = S_NONE;
         }
     });
+}
+int csg_dist_plan(int rank, int world, uint32_t blowup, uint32_t ce_blowup, uint32_t width, csg_shard_plan *out) {
+    if (!out || rank < 0 || world < 1 || (world & (world - 1))) return CSG_ERR_ARG;
+    return shard_plan((size_t)rank, (size_t)world, blowup, ce_blowup, width, out) ? CSG_OK : CSG_ERR_ARG;
 }
 int csg_dist_info(const csg_ctx *ctx, int *rank, int *world) {
     if (!ctx || !rank || !world) return CSG_ERR_ARG;

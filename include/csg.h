@@ -120,6 +120,11 @@ int csg_dist_unique_id(uint8_t id[128]);
 int csg_dist_init(csg_ctx *ctx, int rank, int world, const uint8_t id[128]);
 int csg_dist_init_local(csg_ctx **ctxs, int world);
 int csg_dist_info(const csg_ctx *ctx, int *rank, int *world);
+/* what rank `rank` of `world` owns for an AIR of `width` columns and constraint-evaluation blowup `ce_blowup` (<= blowup): a
+ * contiguous block of LDE cosets, the constraint-evaluation cosets among them (possibly none), and the block of trace columns
+ * it interpolates -- the only columns csg_prove / csg_prove_trace read from the caller's trace on that rank.  Needs no GPU. */
+typedef struct { uint32_t first_coset, num_cosets, first_ce_coset, num_ce_cosets, first_column, num_columns, columns_per_rank; } csg_shard_plan;
+int csg_dist_plan(int rank, int world, uint32_t blowup, uint32_t ce_blowup, uint32_t width, csg_shard_plan *out);
 
 /* per-stage device times of the last proof, milliseconds (CUDA events on the proving stream) */
 typedef struct {

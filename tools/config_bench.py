@@ -26,6 +26,9 @@ def cases():
     seed = np.arange(42, 49, dtype=np.uint64)
     for tx in (1, 4):
         yield f"configs[0] state-transition {tx} tx", csg.AIR_TRANSACTION, csg.TransactionBatch(seed=1, num_tx=tx).transaction_trace(), 8
+    # the example binary's own defaults: 4 transactions, cubic extension (examples/state-transition.rs:58-66); and quadratic
+    for ext in (3, 2):
+        yield f"configs[0] state-transition 4 tx, field extension {ext}", csg.AIR_TRANSACTION, csg.TransactionBatch(seed=1, num_tx=4).transaction_trace(), 8, ext
     for chain in (128, 256, 512, 1024):
         yield f"configs[1] rescue chain {chain}", csg.AIR_RESCUE, csg.build_rescue_trace(seed, chain), 4
     for tx in (1, 16, 128):
@@ -35,6 +38,9 @@ def cases():
     yield "configs[2] range 64-bit", csg.AIR_RANGE, csg.build_range_trace(2**63 - 1), 8
     for tx in (16, 128, 1024):
         yield f"configs[3] state-transition {tx} tx", csg.AIR_TRANSACTION, csg.TransactionBatch(seed=4, num_tx=tx).transaction_trace(), 8
+    for ext in (2, 3):
+        yield f"configs[3] state-transition 1024 tx, field extension {ext}", csg.AIR_TRANSACTION, csg.TransactionBatch(seed=4, num_tx=1024).transaction_trace(), 8, ext
+    yield "configs[3] state-transition 128 tx, field extension 3", csg.AIR_TRANSACTION, csg.TransactionBatch(seed=4, num_tx=128).transaction_trace(), 8, 3
 
 
 def main():
@@ -44,8 +50,9 @@ def main():
     args = ap.parse_args()
     rows = []
     with csg.Context(0) as ctx:
-        for name, air, (trace, pub), blowup in cases():
-            opt = csg.ProofOptions(blowup_factor=blowup)
+        for name, air, (trace, pub), blowup, *rest in cases():
+            ext = rest[0] if rest else 1
+            opt = csg.ProofOptions(blowup_factor=blowup, field_extension=ext)
             ctx.set_air(air, trace.shape[1], pub, opt)
             ctx.load_trace(trace)
             proof = ctx.prove_loaded()
@@ -60,11 +67,12 @@ def main():
                    "kernel_launches": int(t["kernel_launches"])}
             if trace.shape[1] <= args.cpu_max_rows:
                 t0 = time.perf_counter()
-                want = O.prove(air, trace, pub, O.options(blowup=blowup))
+                want = O.prove(air, trace, pub, O.options(blowup=blowup, field_extension=ext))
                 rec["cpu_port_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
                 rec["proof_identical_to_oracle"] = bool(want == proof)
                 rec["oracle_verifier_accepts"] = O.verify(air, pub, proof) == 0
                 rec["speedup"] = round(rec["cpu_port_ms"] / gpu_ms, 1)
+            rec["host_verifier_accepts"] = csg.verify(air, pub, proof) == 0
             rows.append(rec)
             print(json.dumps(rec), flush=True)
     Path(args.out).write_text(json.dumps(rows, indent=1))

@@ -15,3 +15,14 @@ with csg.Context(0) as ctx:
     tr, pub = csg.TransactionBatch(seed=3, num_tx=2).merkle_update_trace()
     ctx.prove(csg.AIR_MERKLE_UPDATE, tr, pub, csg.ProofOptions())
     print("sanitizer workload done")
+    # extension fields, the sharded path (4 ranks on this device) and the warp-per-lane 1024-point NTT passes (n = 2^19: pass A)
+    b = csg.TransactionBatch(seed=4, num_tx=2); tr, pub = b.transaction_trace()
+    for ext in (2, 3):
+        assert csg.verify(csg.AIR_TRANSACTION, pub, ctx.prove(csg.AIR_TRANSACTION, tr, pub, csg.ProofOptions(field_extension=ext))) == 0
+    with csg.LocalGroup(4) as grp:
+        ps = grp.prove(csg.AIR_TRANSACTION, tr, pub, csg.ProofOptions(field_extension=3))
+        assert all(p == ps[0] for p in ps)
+    rng = np.random.default_rng(1)
+    cols = (rng.integers(0, 2**63, size=(2, 1 << 19), dtype=np.uint64) % np.uint64(csg.P)).astype(np.uint64)
+    ctx.lde(cols, 2)
+    print("sanitizer workload (extension, sharded, 1024-point passes) done")
