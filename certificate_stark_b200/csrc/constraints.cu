@@ -51,8 +51,11 @@ struct EccSplitMap {
     unsigned base[4];                                  // first polynomial of variant v = 2*bank + formula
     unsigned total;
 };
+#ifndef CSG_ECC_LOW_MINBLOCKS
+#define CSG_ECC_LOW_MINBLOCKS 3
+#endif
 template <int AIR>
-__global__ void __launch_bounds__(CONS_THREADS, CSG_ECC_MINBLOCKS)
+__global__ void __launch_bounds__(CONS_THREADS, CSG_ECC_LOW_MINBLOCKS)
 cons_ecc_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ ptab, EccSplitMap M, fe *__restrict__ eccl) {
     const unsigned j = blockIdx.y, kc = 2 * j, v = blockIdx.z, bank = v >> 1, L = A->ncosets / 2, NP = 1 + A->ngroups;
     const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
