@@ -35,20 +35,23 @@ CONSTRAINT_BYTES_PER_ROW = 8 * TRACE_WIDTH + 8      # every LDE row read once, o
 MODMUL_PER_ROW = 5922                               # instrumented count of src/air.rs:383-610
 # The constraint stage is four kernels (csrc/constraints.cu).  Algorithmic bytes per ce row of each: the columns it has to
 # read once (8 B each) plus the partial sums it writes / reads (8 B each); DESIGN.md section 3.
-CONS_KERNELS = {   # name: (description, algorithmic bytes per ce row, fraction of the ce rows the kernel visits)
-    "cons_rescue": ("cons_low_kernel<TRANSACTION,0> (5 Rescue residuals per row, even ce cosets, split mode)", 5 * 14 * 8 + 5 * 6 * 8, 0.5),
-    "cons_ecc_banks": ("cons_item_kernel<TRANSACTION,1> (2 scalar-multiplication banks per row)", 2 * 19 * 8 + 12 * 8 + 2 * 8, 1.0),
-    "cons_ecc_final": ("cons_item_kernel<TRANSACTION,2> (final point addition)", 36 * 8 + 4 * 8 + 8, 1.0),
-    "cons_rest": ("phase: cons_low_kernel<TRANSACTION,3> (linear constraints, even cosets) + extension transforms + cons_final_kernel", 8 * TRACE_WIDTH + 8 * 8 + 8, 1.0),
+CONS_KERNELS = {   # name: (description, algorithmic bytes per ce row, fraction of the ce rows visited, one kernel launch?)
+    "cons_rescue": ("cons_low_kernel<TRANSACTION,0> (5 Rescue residuals per row, even ce cosets, split mode)", 5 * 14 * 8 + 5 * 6 * 8, 0.5, True),
+    "cons_ecc_banks": ("phase: cons_ecc_low_kernel<TRANSACTION> (2 banks x 2 curve formulas, even ce cosets) + extension transforms + "
+                       "cons_ecc_merge_kernel", 2 * 19 * 8 + 12 * 8 + 2 * 8, 1.0, False),
+    "cons_ecc_final": ("cons_item_kernel<TRANSACTION,2> (final point addition)", 36 * 8 + 4 * 8 + 8, 1.0, True),
+    "cons_rest": ("phase: cons_low_kernel<TRANSACTION,3> (linear constraints, even cosets) + extension transforms + cons_final_kernel",
+                  8 * TRACE_WIDTH + 8 * 8 + 8, 1.0, False),
 }
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu capture of this same command (profiles/README.md);
 # null for kernels that were not captured
-TRAFFIC = {}
+TRAFFIC, PIPES = {}, {}
 _t = ROOT / "profiles" / "traffic.json"
 if _t.exists():
     TRAFFIC = json.loads(_t.read_text())
+    PIPES = TRAFFIC.get("_pipes", {})     # ALU / FMA pipe utilisation and issue-slot use of the same launches (ncu): the binding resource
 
 
 def measured_peaks():
@@ -299,7 +302,8 @@ def main():
                        "algorithmic_bytes_per_launch": int(rows * CONS_KERNELS[k][2]) * CONS_KERNELS[k][1]} for k in CONS_KERNELS}
         for v in kernels.values():
             v["achieved_gbs"] = v["algorithmic_bytes_per_launch"] / (v["launch_ms"] / 1e3) / 1e9 if v["launch_ms"] > 0 else None
-        top = max(kernels, key=lambda k: kernels[k]["launch_ms"])      # the dominant kernel of the proof
+        # the dominant single kernel of the proof (the two "phase" entries are several launches each: extension transforms included)
+        top = max((k for k in kernels if CONS_KERNELS[k][3]), key=lambda k: kernels[k]["launch_ms"])
         top_ms, alg_bytes = kernels[top]["launch_ms"], kernels[top]["algorithmic_bytes_per_launch"]
         achieved = kernels[top]["achieved_gbs"]
         line = {
@@ -315,7 +319,7 @@ def main():
                                               "2.2 KB per transaction H2D, then the proof; the host builder needs ~0.4 s for the same batch"},
             "gpu_launches": launches,
             "clocks": clock_summary,
-            "roofline": {"kernel": kernels[top]["kernel"] + ", 1 launch per proof", "bound": "hbm",
+            "roofline": {"kernel": kernels[top]["kernel"] + ", 1 launch per proof", "bound": "hbm", "pipes": PIPES.get(top),
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
                          "peak_source": peak_src, "traffic": TRAFFIC.get(top), "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": top_ms,
                          "constraint_stage": {"ms": cons_ms, "kernels": kernels,
