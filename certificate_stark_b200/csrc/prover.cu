@@ -97,6 +97,8 @@ struct csg_ctx {
     DBuf<uint64_t> d_gather;               // slices under exchange
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> comm_ev;
     size_t comm_used = 0;
+    Stream comm_stream;                    // the coefficient all-gather overlaps the extension of the own columns
+    cudaEvent_t ev_intt = nullptr, ev_gathered = nullptr;
 
     DBuf<uint64_t> d_io, d_wit_in;
     DBuf<fe> d_wit_finals;
@@ -274,8 +276,18 @@ struct csg_ctx {
             if (G == 1) coset_ntt_columns(roots, ntt, scratch.p + c0 * n, n, d_lde.p + c0 * n, n, w * n, nc, logn, lde_tables, st);
         }
         if (G > 1) {
-            gather(scratch.p, cpr * n * sizeof(fe));
-            coset_ntt_columns(roots, ntt, scratch.p, n, d_lde.p, n, w * n, w, logn, lde_tables, st);
+            // The coefficient all-gather (the largest exchange) runs on its own stream while this context already extends the
+            // columns it interpolated itself; the other ranks' columns follow once they have arrived.
+            if (!comm_stream.s) CSG_CUDA(cudaStreamCreateWithFlags(&comm_stream.s, cudaStreamNonBlocking));
+            if (!ev_intt) { CSG_CUDA(cudaEventCreateWithFlags(&ev_intt, cudaEventDisableTiming)); CSG_CUDA(cudaEventCreateWithFlags(&ev_gathered, cudaEventDisableTiming)); }
+            CSG_CUDA(cudaEventRecord(ev_intt, st.s));
+            if (c_hi > c_lo) coset_ntt_columns(roots, ntt, scratch.p + c_lo * n, n, d_lde.p + c_lo * n, n, w * n, c_hi - c_lo, logn, lde_tables, st);
+            CSG_CUDA(cudaStreamWaitEvent(comm_stream.s, ev_intt, 0));
+            gather(scratch.p, cpr * n * sizeof(fe), &comm_stream);
+            CSG_CUDA(cudaEventRecord(ev_gathered, comm_stream.s));
+            CSG_CUDA(cudaStreamWaitEvent(st.s, ev_gathered, 0));
+            if (c_lo > 0) coset_ntt_columns(roots, ntt, scratch.p, n, d_lde.p, n, w * n, c_lo, logn, lde_tables, st);
+            if (c_hi < w) coset_ntt_columns(roots, ntt, scratch.p + c_hi * n, n, d_lde.p + c_hi * n, n, w * n, w - c_hi, logn, lde_tables, st);
         }
         std::swap(d_polys.p, scratch.p); std::swap(d_polys.n, scratch.n);   // d_polys = coefficients
         if (host) { nfri = 0; tm.h2d = 0; }
@@ -295,11 +307,12 @@ struct csg_ctx {
             comm_ev.emplace_back(a, e);
         }
     }
-    void gather(void *buf, size_t bytes) {
+    void gather(void *buf, size_t bytes, Stream *on = nullptr) {
+        Stream &cs = on ? *on : st;
         comm_events();
-        CSG_CUDA(cudaEventRecord(comm_ev[comm_used].first, st.s));
-        comm->all_gather(buf, bytes, st);
-        CSG_CUDA(cudaEventRecord(comm_ev[comm_used++].second, st.s));
+        CSG_CUDA(cudaEventRecord(comm_ev[comm_used].first, cs.s));
+        comm->all_gather(buf, bytes, cs);
+        CSG_CUDA(cudaEventRecord(comm_ev[comm_used++].second, cs.s));
     }
     void reduce_rows(uint64_t *buf, size_t count) {
         comm_events();
@@ -792,45 +805,51 @@ struct csg_ctx {
         pf.u16((uint16_t)((2 + nlayers) * 32));
         pf.put(trace_root, 32); pf.put(comp_root, 32);
         for (auto &r : fri_roots) pf.put(r.data(), 32);
+        // every opening of the proof -- trace rows, composition rows, FRI layer rows, their Merkle paths, the remainder -- is
+        // planned on the host first and fetched in ONE round trip (one index upload, a handful of gather launches, one download)
+        OpenBatch B;
+        const size_t cw = ce * d;
+        const Opening o_trace = plan_opening(B, d_lde.p, (unsigned)w, (unsigned)b, w * n, n, 1, 0, true, d_tnodes.p, lde_n, pos);
+        const Opening o_comp = plan_opening(B, d_clde.p, (unsigned)cw, (unsigned)b, cw * n, n, 1, 0, true, d_cnodes.p, lde_n, pos);
+        std::vector<Opening> o_fri;
         {
-            std::vector<uint64_t> rows = open_rows(d_lde.p, (unsigned)w, (unsigned)b, w * n, n, pos, true);
-            pf.u32((uint32_t)(rows.size() * 8));
-            for (uint64_t v : rows) pf.u64(v);
-            std::vector<uint8_t> paths = open_paths(d_tnodes, lde_n, pos);
-            pf.u32((uint32_t)paths.size()); pf.put(paths.data(), paths.size());
-        }
-        {
-            const size_t cw = ce * d;
-            std::vector<uint64_t> rows = open_rows(d_clde.p, (unsigned)cw, (unsigned)b, cw * n, n, pos, true);
-            pf.u32((uint32_t)(rows.size() * 8));
-            for (uint64_t v : rows) pf.u64(v);
-            std::vector<uint8_t> paths = open_paths(d_cnodes, lde_n, pos);
-            pf.u32((uint32_t)paths.size()); pf.put(paths.data(), paths.size());
-        }
-        pf.u16((uint16_t)(w * d * 8));
-        for (fe v : flat(xood_cur)) pf.element(v);
-        for (fe v : flat(xood_next)) pf.element(v);
-        pf.u16((uint16_t)(ce * d * 8));
-        for (fe v : flat(xood_comp)) pf.element(v);
-        {
-            pf.u8((uint8_t)(nlayers - 1));
             std::vector<size_t> fp = pos;
             size_t domain = lde_n;
             for (size_t l = 0; l + 1 < nlayers; l++) {
                 fp = fold_positions(fp, domain);
                 const size_t q = domain / 4;
-                std::vector<uint64_t> rows = open_fri_rows(*fri[l], fp);
-                pf.u32((uint32_t)(rows.size() * 8));
-                for (uint64_t v : rows) pf.u64(v);
-                std::vector<uint8_t> paths = open_paths(fri[l]->nodes, q, fp);
-                pf.u32((uint32_t)paths.size()); pf.put(paths.data(), paths.size());
+                const FriLayer &L = *fri[l];
+                o_fri.push_back(plan_opening(B, L.evals, 4 * (unsigned)d, 1, 0, q, (unsigned)d, d == 1 ? 0 : L.m, false, L.nodes.p, q, fp));
                 domain = q;
             }
-            std::vector<uint64_t> rem = remainder();
-            pf.u16((uint16_t)(rem.size() * 8));
-            for (uint64_t v : rem) pf.u64(v);
-            pf.u8(1);
         }
+        const FriLayer &last = *fri[nlayers - 1];
+        const size_t rem_off = B.rows_words, rem_len = last.m * d;
+        B.rows_words += rem_len;
+        std::vector<uint64_t> rows;
+        std::vector<uint8_t> digs;
+        run_openings(B, rows, digs, last, rem_off);
+        auto emit = [&](const Opening &o) {
+            pf.u32((uint32_t)(o.rows_len * 8));
+            for (size_t k = 0; k < o.rows_len; k++) pf.u64(rows[o.rows_off + k]);
+            Bytes paths;
+            paths.u8((uint8_t)o.slots.size());
+            size_t at = o.dig_off;
+            for (auto &sl : o.slots) { paths.u8((uint8_t)sl.size()); paths.put(digs.data() + at * 32, sl.size() * 32); at += sl.size(); }
+            pf.u32((uint32_t)paths.v.size()); pf.put(paths.v.data(), paths.v.size());
+        };
+        emit(o_trace);
+        emit(o_comp);
+        pf.u16((uint16_t)(w * d * 8));
+        for (fe v : flat(xood_cur)) pf.element(v);
+        for (fe v : flat(xood_next)) pf.element(v);
+        pf.u16((uint16_t)(ce * d * 8));
+        for (fe v : flat(xood_comp)) pf.element(v);
+        pf.u8((uint8_t)(nlayers - 1));
+        for (const Opening &o : o_fri) emit(o);
+        pf.u16((uint16_t)(rem_len * 8));
+        for (size_t k = 0; k < rem_len; k++) pf.u64(rows[rem_off + k]);
+        pf.u8(1);
         pf.u64(nonce);
         tm.queries = tq.stop(st);
         tm.kernel_launches = st.launches - launches0;
@@ -842,6 +861,56 @@ struct csg_ctx {
         memcpy(*proof, pf.v.data(), pf.v.size());
         *proof_len = pf.v.size();
         stage = S_TRACE;   // the resident trace (d_io) can be proved again
+    }
+    // ---- batched openings
+    struct Opening { size_t rows_off = 0, rows_len = 0, dig_off = 0; std::vector<std::vector<uint32_t>> slots; };
+    struct OpenBatch {
+        struct Rows { const fe *data; unsigned width, ncosets; size_t coset_stride, col_stride; unsigned sub; size_t sub_stride, idx_off, npos, rows_off; };
+        struct Digs { const uint32_t *nodes; size_t idx_off, count, dig_off; };
+        std::vector<uint32_t> idx;   // row positions and node indices of every job, concatenated
+        std::vector<Rows> rows;
+        std::vector<Digs> digs;
+        size_t rows_words = 0, dig_count = 0, sharded_words = 0;
+    };
+    // rows of `data` at `pos` (sharded matrices first: their rows are summed across the ranks in one go) and the batch opening
+    // of the same positions in the tree `nodes`
+    Opening plan_opening(OpenBatch &B, const fe *data, unsigned width, unsigned ncosets, size_t coset_stride, size_t col_stride, unsigned sub, size_t sub_stride,
+                         bool sharded, const uint32_t *nodes, size_t nleaves, const std::vector<size_t> &pos) {
+        Opening o;
+        sharded = sharded && G > 1;
+        OpenBatch::Rows r{data, width, sharded ? (unsigned)bl : ncosets, coset_stride, col_stride, sub ? sub : 1, sub_stride, B.idx.size(), pos.size(), B.rows_words};
+        for (size_t p : pos) {
+            uint32_t v = (uint32_t)p;
+            if (sharded) { const size_t k = p % b, i = p / b; v = (k >= k0 && k < k0 + bl) ? (uint32_t)((k - k0) + bl * i) : 0xFFFFFFFFu; }
+            B.idx.push_back(v);
+        }
+        o.rows_off = B.rows_words; o.rows_len = pos.size() * width;
+        B.rows_words += o.rows_len;
+        if (sharded) { if (B.sharded_words != o.rows_off) throw StateError("sharded openings must be planned first"); B.sharded_words = B.rows_words; }
+        B.rows.push_back(r);
+        o.slots = batch_opening_nodes(nleaves, pos);
+        OpenBatch::Digs dj{nodes, B.idx.size(), 0, B.dig_count};
+        for (auto &sl : o.slots) { B.idx.insert(B.idx.end(), sl.begin(), sl.end()); dj.count += sl.size(); }
+        o.dig_off = B.dig_count;
+        B.dig_count += dj.count;
+        B.digs.push_back(dj);
+        return o;
+    }
+    void run_openings(OpenBatch &B, std::vector<uint64_t> &rows, std::vector<uint8_t> &digs, const FriLayer &last, size_t rem_off) {
+        d_idx.reserve(std::max<size_t>(B.idx.size(), 1 << 16));
+        d_rows.reserve(std::max<size_t>(B.rows_words, 1 << 17));
+        d_dig.reserve(std::max<size_t>(B.dig_count * 8, 8 << 16));
+        CSG_CUDA(cudaMemcpyAsync(d_idx.p, B.idx.data(), B.idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st.s));
+        for (auto &r : B.rows)
+            gather_rows(r.data, r.width, r.ncosets, r.coset_stride, r.col_stride, d_idx.p + r.idx_off, r.npos, d_rows.p + r.rows_off, st, r.sub, r.sub_stride);
+        if (B.sharded_words) reduce_rows(d_rows.p, B.sharded_words);
+        for (auto &g : B.digs) gather_digests(g.nodes, d_idx.p + g.idx_off, g.count, d_dig.p + 8 * g.dig_off, st);
+        if (d == 1) from_montgomery(last.evals, d_rows.p + rem_off, last.m, st);
+        else planes_to_canonical(last.evals, last.m, last.m, d, d_rows.p + rem_off, st);
+        rows.resize(B.rows_words); digs.resize(B.dig_count * 32);
+        CSG_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, rows.size() * 8, cudaMemcpyDeviceToHost, st.s));
+        if (!digs.empty()) CSG_CUDA(cudaMemcpyAsync(digs.data(), d_dig.p, digs.size(), cudaMemcpyDeviceToHost, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
     }
     // opened rows of a FRI layer: 4 elements per row, each d components (planes of stride m)
     std::vector<uint64_t> open_fri_rows(const FriLayer &L, const std::vector<size_t> &pos) {
@@ -905,6 +974,8 @@ void csg_destroy(csg_ctx *ctx) {
     for (auto e : ctx->cons_ev) if (e) cudaEventDestroy(e);
     for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
     for (auto &e : ctx->comm_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (ctx->ev_intt) { cudaEventDestroy(ctx->ev_intt); cudaEventDestroy(ctx->ev_gathered); }
+    if (ctx->comm_stream.s) { cudaStreamSynchronize(ctx->comm_stream.s); cudaStreamDestroy(ctx->comm_stream.s); }
     ctx->comm.reset();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;

@@ -11,6 +11,6 @@ cap() {  # name, kernel regex, extra ncu args
     ncu -i $D/$1.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_summary.py > gpurun_out/ncu_$1_summary_$TAG.txt
 }
 cap cons "cons_" "-c 6"
-cap ntt "ntt_pass" "-s 8 -c 6"
+cap ntt "ntt" "-s 8 -c 6"
 cap hash "hash_rows|merkle_level" "-c 3"
 ls -la $D gpurun_out | tail -20
