@@ -44,10 +44,14 @@ class Coin {
     }
     // an element of the degree-d extension: the first 8*d bytes of one output as d canonical words, the whole output
     // rejected unless every word is below p (coin.draw::<E>())
+    // For d = 3 only 1.7 % of the outputs pass (each word is below p with probability 0.26), about 60 hashes per draw and
+    // ~30k per proof: the outputs H(seed || counter) are independent, so they are computed a block at a time on all host threads.
     f63::xe draw_x(int d) {
         for (int i = 0; i < 1000; i++) {
-            uint8_t t[32];
-            counter_++; merge_with_int(counter_, t);
+            counter_++;
+            const uint8_t *t = d > 1 ? output(counter_) : nullptr;
+            uint8_t t1[32];
+            if (!t) { merge_with_int(counter_, t1); t = t1; }
             f63::xe r = f63::x_zero();
             bool ok = true;
             for (int j = 0; j < d && ok; j++) { uint64_t v; memcpy(&v, t + 8 * j, 8); if (v >= f63::P) ok = false; else r.c[j] = f63::to_mont(v); }
@@ -73,6 +77,23 @@ class Coin {
     int hash_fn_;
     uint8_t seed_[32];
     uint64_t counter_ = 0;
+    // outputs for the counters block_first_ .. block_first_ + block_.size()/32 - 1 under the seed they were computed for
+    std::vector<uint8_t> block_;
+    uint64_t block_first_ = 0;
+    uint8_t block_seed_[32];
+    const uint8_t *output(uint64_t ctr) {
+        const bool same_seed = !block_.empty() && memcmp(block_seed_, seed_, 32) == 0;
+        if (!same_seed || ctr < block_first_ || ctr >= block_first_ + block_.size() / 32) {
+            // a seed that serves one draw (a FRI layer's alpha) needs ~60 outputs, one that serves hundreds keeps asking: grow
+            const size_t K = same_seed ? std::min<size_t>(4 * (block_.size() / 32), 2048) : 128;
+            block_.resize(K * 32);
+            block_first_ = ctr;
+            memcpy(block_seed_, seed_, 32);
+#pragma omp parallel for schedule(static)
+            for (long k = 0; k < (long)K; k++) merge_with_int(ctr + (uint64_t)k, &block_[(size_t)k * 32]);
+        }
+        return &block_[(size_t)(ctr - block_first_) * 32];
+    }
     void merge_with_int(uint64_t v, uint8_t out[32]) const {
         uint8_t t[40];
         memcpy(t, seed_, 32);
