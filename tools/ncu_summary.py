@@ -24,7 +24,8 @@ def main():
     for r in rows[hdr + 2:]:
         if len(r) != len(names):
             continue
-        parts = [r[idx["Kernel Name"]][-48:]]
+        name = r[idx["Kernel Name"]].split("(")[0]          # function name with its template arguments, parameter list dropped
+        parts = [name.split("::")[-1][-60:]]
         for label, metric in COLS:
             if metric in idx:
                 parts.append(f"{label} {r[idx[metric]]} {units[idx[metric]]}".rstrip())
