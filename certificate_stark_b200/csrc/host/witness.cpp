@@ -106,6 +106,21 @@ struct AccountTree {
         size_t i = ((size_t)1 << depth) + idx; nodes[i] = leaf;
         for (i >>= 1; i >= 1; i >>= 1) rescue::merge(nodes[2 * i].data(), nodes[2 * i + 1].data(), nodes[i].data());
     }
+    // bulk form for the initial accounts: leaves are written first, then every touched interior node is recomputed once, level
+    // by level, on all host threads (thousands of independent Rescue permutations instead of 15 dependent ones per account)
+    std::vector<size_t> dirty;
+    void set_leaf(size_t idx, const Hash7 &leaf) { size_t i = ((size_t)1 << depth) + idx; nodes[i] = leaf; dirty.push_back(i); }
+    void rebuild() {
+        std::vector<size_t> cur;
+        cur.swap(dirty);
+        for (unsigned l = depth; l-- > 0;) {
+            for (auto &i : cur) i >>= 1;
+            std::sort(cur.begin(), cur.end());
+            cur.erase(std::unique(cur.begin(), cur.end()), cur.end());
+#pragma omp parallel for schedule(static)
+            for (long k = 0; k < (long)cur.size(); k++) rescue::merge(nodes[2 * cur[k]].data(), nodes[2 * cur[k] + 1].data(), nodes[cur[k]].data());
+        }
+    }
     std::vector<Hash7> prove(size_t idx) const {  // [leaf, sibling leaf, sibling nodes ... up to below the root]
         std::vector<Hash7> p; size_t i = ((size_t)1 << depth) + idx;
         p.push_back(nodes[i]);
@@ -268,12 +283,13 @@ csg_tx_batch *csg_tx_batch_new(uint64_t seed, size_t num_tx, unsigned tree_depth
     std::vector<unsigned> skeys(tree_size, 0);
     std::vector<Account> values(tree_size); for (auto &v : values) v.fill(0);
     AccountTree tree(tree_depth);
-    auto new_account = [&](size_t idx) {
+    std::vector<size_t> created;
+    auto new_account = [&](size_t idx) {   // the leaf hashes and their paths are computed in bulk below
         unsigned sk = 1 + rng.next() % 3; skeys[idx] = sk;
         Account a;
         for (int i = 0; i < 12; i++) a[i] = pk[sk][i];
         a[12] = f63::to_mont(rng.next() % f63::P); a[13] = f63::to_mont(rng.next() % f63::P);
-        values[idx] = a; tree.update_leaf(idx, account_leaf(a));
+        values[idx] = a; created.push_back(idx);
     };
     B->s_idx.resize(num_tx); B->r_idx.resize(num_tx);
     for (size_t t = 0; t < num_tx; t++) { B->s_idx[t] = rng.next() % tree_size; new_account(B->s_idx[t]); }
@@ -282,6 +298,13 @@ csg_tx_batch *csg_tx_batch_new(uint64_t seed, size_t num_tx, unsigned tree_depth
         while (r == B->s_idx[t]) r = rng.next() % tree_size;
         B->r_idx[t] = r;
         if (!skeys[r]) new_account(r);
+    }
+    {   // a slot drawn twice keeps its last account, as with one update per draw
+        std::vector<Hash7> leaves(created.size());
+#pragma omp parallel for schedule(static)
+        for (long k = 0; k < (long)created.size(); k++) leaves[k] = account_leaf(values[created[k]]);
+        for (size_t k = 0; k < created.size(); k++) tree.set_leaf(created[k], leaves[k]);
+        tree.rebuild();
     }
     std::vector<unsigned> s_sk(num_tx);
     for (size_t t = 0; t < num_tx; t++) {
