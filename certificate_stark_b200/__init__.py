@@ -180,8 +180,15 @@ class Context:
         """attach to the torch.distributed world: rank 0 creates the NCCL id, broadcast through the default process group"""
         import torch.distributed as dist
         rank, world = dist.get_rank(), dist.get_world_size()
-        box = [dist_unique_id() if rank == 0 else None]
+        box = [None]
+        if rank == 0:
+            try:
+                box = [dist_unique_id()]
+            except CsgError:
+                pass                      # every rank learns about it through the broadcast and raises together
         dist.broadcast_object_list(box, src=0)
+        if box[0] is None:
+            raise CsgError("NCCL is not available on rank 0 (libnccl.so.2 could not be loaded)")
         self.dist_init(rank, world, box[0])
 
     def dist_info(self):
