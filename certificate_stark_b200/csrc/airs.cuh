@@ -87,7 +87,7 @@ template <bool SPLIT, int DEG = 1>
 struct CombT {
     static constexpr bool split = SPLIT;
     static constexpr int D = DEG;
-    static_assert(!SPLIT || DEG == 1, "the low-degree split is implemented for base-field coefficients");
+
     const fe *alpha, *beta;
     const uint8_t *group;
     const fe *xp;        // x^adj per degree group, element g at xp[g * xp_stride]   (combined mode only)
@@ -111,15 +111,27 @@ struct CombT {
             for (int j = 1; j < DEG; j++) sum_x[j - 1].mac(coef_x(j, slot), v);
             return;
         }
+        const int g = group[slot];
         sum.mac(alpha[slot], v);
-        uint64_t *q = part + (size_t)group[slot] * 3 * part_stride;
+        part_mac(0, g, beta[slot], v);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 1; j < DEG; j++) {
+            sum_x[j - 1].mac(alpha_x[(j - 1) * coef_stride + slot], v);
+            part_mac(j, g, beta_x[(j - 1) * coef_stride + slot], v);
+        }
+    }
+    // the accumulator of B_g of component j: words at part[((j * MAX_SPLIT_GROUPS + g) * 3 + k) * part_stride]
+    CSG_HD void part_mac(int j, int g, fe b, fe v) {
+        uint64_t *q = part + (size_t)(j * MAX_SPLIT_GROUPS + g) * 3 * part_stride;
         f63::acc192 t;
         t.lo = q[0]; t.mid = q[part_stride]; t.hi = q[2 * part_stride];
-        t.mac(beta[slot], v);
+        t.mac(b, v);
         q[0] = t.lo; q[part_stride] = t.mid; q[2 * part_stride] = t.hi;
     }
-    CSG_HD fe part_value(int g) const {   // split mode: B_g, reduced
-        const uint64_t *q = part + (size_t)g * 3 * part_stride;
+    CSG_HD fe part_value(int g, int j = 0) const {   // split mode: B_g of component j, reduced
+        const uint64_t *q = part + (size_t)(j * MAX_SPLIT_GROUPS + g) * 3 * part_stride;
         f63::acc192 t;
         t.lo = q[0]; t.mid = q[part_stride]; t.hi = q[2 * part_stride];
         return t.reduce();
@@ -301,15 +313,15 @@ CSG_HD void scalar_mult_bank_outputs(const Frame &f, CB &C, int o, const fe (&q)
     for (int i = 0; i < 6; i++) { C.add(o + i, r.x.c[i]); C.add(o + 6 + i, r.y.c[i]); C.add(o + 12 + i, r.z.c[i]); }
 }
 template <class CB>
-CSG_HD fe scalar_mult_bank_merge(const Frame &f, const CB &C, int o, fe doubling, fe addition, fe Cd, fe Cm) {
+CSG_HD fe scalar_mult_bank_merge(const Frame &f, const CB &C, int comp, int o, fe doubling, fe addition, fe Cd, fe Cm) {   // comp: component of E-valued coefficients
     const fe bit = f.cur(o + PPW), nbit = f_not(bit);
     f63::acc192 sd, sa;
     for (int i = 0; i < PPW; i++) {
-        const fe c = C.coef(o + i), nx = f.next(o + i);
+        const fe c = comp ? C.coef_x(comp, o + i) : C.coef(o + i), nx = f.next(o + i);
         sd.mac(c, nx);
         sa.mac(c, f63::sub(nx, f63::mul(nbit, f.cur(o + i))));
     }
-    const fe cb = C.coef(o + PPW);
+    const fe cb = comp ? C.coef_x(comp, o + PPW) : C.coef(o + PPW);
     const fe td = f63::sub(f63::add(sd.reduce(), f63::mul(cb, f_bin(bit))), Cd);
     const fe ta = f63::sub(f63::add(sa.reduce(), f63::mul(cb, f63::sub(bit, f.next(o + PPW)))), f63::mul(bit, Cm));
     return f63::add(f63::mul(doubling, td), f63::mul(addition, ta));
@@ -415,11 +427,11 @@ CSG_HD void eval_ecc_bank_outputs(int bank, int formula, const Frame &f, const P
     scalar_mult_bank_outputs(f, C, bank * (PPW + 1), q, formula);
 }
 template <int AIR, class PV, class CB>
-CSG_HD fe eval_ecc_bank_merge(int bank, const Frame &f, const PV &pv, const CB &C, fe Cd, fe Cm) {
+CSG_HD fe eval_ecc_bank_merge(int bank, const Frame &f, const PV &pv, const CB &C, int comp, fe Cd, fe Cm) {
     if (AIR != TRANSACTION && AIR != SCHNORR) return 0;
     const fe scalar_mult = pv(AIR == TRANSACTION ? TX_SCALAR_MULT : 1);
     const fe doubling = pv(AIR == TRANSACTION ? TX_DOUBLING : 2), addition = f63::mul(f_not(doubling), scalar_mult);
-    return scalar_mult_bank_merge(f, C, bank * (PPW + 1), doubling, addition, Cd, Cm);
+    return scalar_mult_bank_merge(f, C, comp, bank * (PPW + 1), doubling, addition, Cd, Cm);
 }
 template <int AIR, class PV, class CB>
 CSG_HD void eval_ecc_final(const Frame &f, const PV &pv, CB &C) {

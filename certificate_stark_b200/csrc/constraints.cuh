@@ -61,7 +61,8 @@ size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets);
 // the same with E-valued coefficients (args.ext_degree = 2 or 3): one pass over the rows, component j of the merged column
 // written to out[(j * ncosets + kc) * n + i]; part: ext_degree times the scratch of the base-field call
 void eval_constraints_ext(int air_id, const ConsArgs *args_dev, const ConsArgs &args_host, const fe *lde, const fe *W, const fe *ptab,
-                          const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr);
+                          const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr,
+                          const RootTable *rt = nullptr, NttScratch *sc = nullptr);   // given: the low-degree split, per component
 
 unsigned long long redc_violations();   // debug builds (-DCSG_REDC_CHECK): reductions entered with an out-of-range operand
 

@@ -400,7 +400,8 @@ struct csg_ctx {
         if (!cons_ev[0]) for (auto &e : cons_ev) CSG_CUDA(cudaEventCreate(&e));
         // the low-degree split interpolates across the even cosets: only when this context owns all of them
         const bool split = split_low_degree && G == 1;
-        if (cel && all_components) csg::eval_constraints_ext(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st, cons_ev);
+        if (cel && all_components) csg::eval_constraints_ext(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st, cons_ev,
+                                                             split ? &roots : nullptr, split ? &ntt : nullptr);
         else if (cel) csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p + plane * comb_plane, st, cons_ev,
                                             split ? &roots : nullptr, split ? &ntt : nullptr);
         else for (auto &e : cons_ev) CSG_CUDA(cudaEventRecord(e, st.s));
