@@ -43,21 +43,21 @@ size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets) {
 }
 
 void eval_constraints_ext2(int air_id, const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab, const fe *apoly,
-                           fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc);   // constraints_ext.cu, compiled once per degree
+                           fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc, const SplitExchange *xch);   // constraints_ext.cu, compiled once per degree
 void eval_constraints_ext3(int air_id, const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab, const fe *apoly,
-                           fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc);
+                           fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc, const SplitExchange *xch);
 void eval_constraints_ext(int air_id, const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab,
-                          const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc) {
-    if (h.ext_degree == 2) eval_constraints_ext2(air_id, args_dev, h, lde, W, ptab, apoly, part, out, st, ev, rt, sc);
-    else if (h.ext_degree == 3) eval_constraints_ext3(air_id, args_dev, h, lde, W, ptab, apoly, part, out, st, ev, rt, sc);
+                          const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc, const SplitExchange *xch) {
+    if (h.ext_degree == 2) eval_constraints_ext2(air_id, args_dev, h, lde, W, ptab, apoly, part, out, st, ev, rt, sc, xch);
+    else if (h.ext_degree == 3) eval_constraints_ext3(air_id, args_dev, h, lde, W, ptab, apoly, part, out, st, ev, rt, sc, xch);
     else throw std::runtime_error("extension degree must be 2 or 3");
 }
 
 void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab,
-                      const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc) {
-    const bool split = rt && sc && h.ncosets == 8 && h.ngroups <= (unsigned)airs::MAX_SPLIT_GROUPS;
-    if (split && air_id == airs::TRANSACTION) { launch_split<airs::TRANSACTION>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev, *rt, *sc); return; }
-    if (split && air_id == airs::SCHNORR) { launch_split<airs::SCHNORR>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev, *rt, *sc); return; }
+                      const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc, const SplitExchange *xch) {
+    const bool split = rt && sc && split_applies(h, xch);
+    if (split && air_id == airs::TRANSACTION) { launch_split<airs::TRANSACTION>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev, *rt, *sc, xch); return; }
+    if (split && air_id == airs::SCHNORR) { launch_split<airs::SCHNORR>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev, *rt, *sc, xch); return; }
     switch (air_id) {
     case airs::TRANSACTION: launch<airs::TRANSACTION>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;
     case airs::MERKLE_UPDATE: launch<airs::MERKLE_UPDATE>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;

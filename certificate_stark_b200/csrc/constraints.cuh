@@ -52,17 +52,29 @@ struct ConsArgs {
     fe a_alpha_x[2][CONS_MAX_ASSERTIONS], a_beta_x[2][CONS_MAX_ASSERTIONS];
 };
 
+// A sharded proof (comm.cuh) can still use the low-degree splits when every rank owns whole even/odd coset pairs: each rank
+// interpolates on its own even cosets, the coefficient sets are all-gathered, and each rank mixes and evaluates its own odd cosets.
+struct SplitExchange {
+    unsigned world, rank;
+    void (*gather)(void *self, void *buf, size_t bytes);   // in-place all-gather of equal slices on the proving stream
+    void *self;
+    fe *buf;                                              // world slices of the largest polynomial set
+    size_t buf_elems;
+};
+
 // lde: coset-major extended trace; W: root table of size n; ptab / apoly: periodic tables and assertion value
 // polynomials; part: scratch of constraint_scratch_elements() for the per-item partial sums; out[kc * n + i] receives C(x)
 void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &args_host, const fe *lde, const fe *W, const fe *ptab,
                       const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr,   // ev: 5 events bracketing the 4 phases
-                      const RootTable *rt = nullptr, NttScratch *sc = nullptr);   // given: low-degree constraints use half of the cosets (TX, Schnorr)
+                      const RootTable *rt = nullptr, NttScratch *sc = nullptr,   // given: low-degree constraints use half of the cosets (TX, Schnorr)
+                      const SplitExchange *xch = nullptr);                      // given: args describe the cosets of one rank of a sharded proof
 size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets);
 // the same with E-valued coefficients (args.ext_degree = 2 or 3): one pass over the rows, component j of the merged column
 // written to out[(j * ncosets + kc) * n + i]; part: ext_degree times the scratch of the base-field call
 void eval_constraints_ext(int air_id, const ConsArgs *args_dev, const ConsArgs &args_host, const fe *lde, const fe *W, const fe *ptab,
                           const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr,
-                          const RootTable *rt = nullptr, NttScratch *sc = nullptr);   // given: the low-degree split, per component
+                          const RootTable *rt = nullptr, NttScratch *sc = nullptr,   // given: the low-degree split, per component
+                          const SplitExchange *xch = nullptr);
 
 unsigned long long redc_violations();   // debug builds (-DCSG_REDC_CHECK): reductions entered with an out-of-range operand
 

@@ -14,12 +14,12 @@
 namespace csg {
 
 void CSG_CAT(eval_constraints_ext, CSG_EXT_DEG)(int air_id, const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab,
-                                                const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc) {
+                                                const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev, const RootTable *rt, NttScratch *sc, const SplitExchange *xch) {
     constexpr int D = CSG_EXT_DEG;
     // the low-degree split (rescue residuals, linear rest, curve formulas on the even cosets only), per component
-    const bool split = rt && sc && h.ncosets == 8 && h.ngroups <= (unsigned)airs::MAX_SPLIT_GROUPS;
-    if (split && air_id == airs::TRANSACTION) { launch_split<airs::TRANSACTION, D>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev, *rt, *sc); return; }
-    if (split && air_id == airs::SCHNORR) { launch_split<airs::SCHNORR, D>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev, *rt, *sc); return; }
+    const bool split = rt && sc && split_applies(h, xch);
+    if (split && air_id == airs::TRANSACTION) { launch_split<airs::TRANSACTION, D>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev, *rt, *sc, xch); return; }
+    if (split && air_id == airs::SCHNORR) { launch_split<airs::SCHNORR, D>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev, *rt, *sc, xch); return; }
     switch (air_id) {
     case airs::TRANSACTION: launch<airs::TRANSACTION, D>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;
     case airs::MERKLE_UPDATE: launch<airs::MERKLE_UPDATE, D>(args_dev, h, lde, W, ptab, apoly, part, out, st, ev); break;

@@ -306,32 +306,48 @@ cons_final_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, co
     for (int comp = 0; comp < DEG; comp++) out[((unsigned long long)comp * A->ncosets + kc) * n + i] = res[comp];
 }
 
+// the split needs the 8 ce cosets of the transaction / Schnorr AIR; a rank of a sharded proof must own whole even/odd pairs
+inline bool split_applies(const ConsArgs &h, const SplitExchange *xch) {
+    const unsigned world = xch ? xch->world : 1;
+    return h.ncosets * world == 8 && h.ncosets % 2 == 0 && h.ngroups <= (unsigned)airs::MAX_SPLIT_GROUPS;
+}
+
 template <int AIR, int DEG = 1>
 void launch_split(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe *W, const fe *ptab, const fe *apoly, fe *part, fe *out, Stream &st,
-                  cudaEvent_t *ev, const RootTable &rt, NttScratch &sc) {
+                  cudaEvent_t *ev, const RootTable &rt, NttScratch &sc, const SplitExchange *xch = nullptr) {
     const unsigned long long n = 1ULL << h.logn;
+    // ce, L: the cosets of THIS rank (all of them without an exchange); Lg: even cosets of the whole proof
     const unsigned gx = (unsigned)((n + CONS_THREADS - 1) / CONS_THREADS), ce = h.ncosets, L = ce / 2, NP = 1 + h.ngroups, NPD = DEG * NP;
+    const unsigned G = xch ? xch->world : 1, Lg = L * G, rank = xch ? xch->rank : 0;
     constexpr int NR = airs::Items<AIR>::rescue, NE = airs::Items<AIR>::ecc;
     const size_t slab = (size_t)NPD * L * n;
     fe *low_parts = part, *low_sum = low_parts + (size_t)(NR + 1) * slab, *low_coef = low_sum + slab, *low_mix = low_coef + slab,
        *low_odd = low_mix + slab, *hi = low_odd + slab, *binv = hi + (size_t)DEG * NE * ce * n;
     // interpolation on the even cosets, L x L mix of the per-coset coefficient sets, evaluation on the odd cosets, for `np`
     // polynomials laid out [p][L][n]
-    const fe w2l = root_of_unity(ilog2(2 * L)), linv = inv(to_mont(L));
-    std::vector<fe> mix(L * L);
-    for (unsigned jo = 0; jo < L; jo++)
-        for (unsigned je = 0; je < L; je++) {
-            const unsigned e = (2 * (jo + L - je) + 1) % (2 * L);   // 2 (j' - j) + 1 mod 2L
+    const fe w2l = root_of_unity(ilog2(2 * Lg)), linv = inv(to_mont(Lg));
+    std::vector<fe> mix(L * Lg);   // the rows of the Lg x Lg map that produce this rank's odd cosets
+    for (unsigned jl = 0; jl < L; jl++)
+        for (unsigned je = 0; je < Lg; je++) {
+            const unsigned jo = rank * L + jl, e = (2 * (jo + Lg - je) + 1) % (2 * Lg);   // 2 (j' - j) + 1 mod 2L
             fe acc = 0, step = f63::pow(w2l, e), cur = ONE;
-            for (unsigned t = 0; t < L; t++) { acc = add(acc, cur); cur = mul(cur, step); }
-            mix[jo * L + je] = mul(acc, linv);
+            for (unsigned t = 0; t < Lg; t++) { acc = add(acc, cur); cur = mul(cur, step); }
+            mix[jl * Lg + je] = mul(acc, linv);
         }
     auto extend = [&](const fe *even, fe *coef, fe *mixed, fe *odd, unsigned np) {
         std::vector<fe> sinv(np * L), sodd(np * L);
         for (unsigned p = 0; p < np; p++)
             for (unsigned j = 0; j < L; j++) { sinv[p * L + j] = inv(h.shift[2 * j]); sodd[p * L + j] = h.shift[2 * j + 1]; }
-        coset_intt_columns(rt, sc, even, n, coef, n, h.logn, sinv.data(), (size_t)np * L, st);
-        coset_mix(coef, mixed, n, L, np, mix.data(), st);
+        if (xch) {   // own even cosets into this rank's slice, all-gather, then only the rows of the mix this rank needs
+            const size_t slice = (size_t)np * L * n;
+            if (slice * G > xch->buf_elems) throw std::runtime_error("exchange buffer of the sharded split is too small");
+            coset_intt_columns(rt, sc, even, n, xch->buf + rank * slice, n, h.logn, sinv.data(), (size_t)np * L, st);
+            xch->gather(xch->self, xch->buf, slice * sizeof(fe));
+            coset_mix_sharded(xch->buf, mixed, n, Lg, L, slice, np, mix.data(), st);
+        } else {
+            coset_intt_columns(rt, sc, even, n, coef, n, h.logn, sinv.data(), (size_t)np * L, st);
+            coset_mix(coef, mixed, n, L, np, mix.data(), st);
+        }
         coset_ntt_entries(rt, sc, mixed, odd, (size_t)np * L, h.logn, sodd.data(), st);
         CSG_CUDA(cudaStreamSynchronize(st.s));   // the staging vectors are read by async copies
     };

@@ -95,6 +95,7 @@ struct csg_ctx {
     std::unique_ptr<Comm> comm;
     size_t G = 1, rank = 0, bl = 0, k0 = 0, cel = 0, kc0 = 0;
     DBuf<uint64_t> d_gather;               // slices under exchange
+    DBuf<fe> d_xch;                        // coefficient sets of the low-degree splits under exchange
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> comm_ev;
     size_t comm_used = 0;
     Stream comm_stream;                    // the coefficient all-gather overlaps the extension of the own columns
@@ -398,12 +399,18 @@ struct csg_ctx {
         d_comb.reserve(comb_plane * d);
         d_parts.reserve(constraint_scratch_elements(air.id, n, cel ? cel : 1) * (all_components ? d : 1));
         if (!cons_ev[0]) for (auto &e : cons_ev) CSG_CUDA(cudaEventCreate(&e));
-        // the low-degree split interpolates across the even cosets: only when this context owns all of them
-        const bool split = split_low_degree && G == 1;
+        // the low-degree splits interpolate across the even cosets: alone, or with an exchange when every rank owns whole pairs
+        const bool split = split_low_degree && (G == 1 || (ce == b && bl % 2 == 0));
+        SplitExchange xch{(unsigned)G, (unsigned)rank, [](void *self, void *buf, size_t bytes) { static_cast<csg_ctx *>(self)->gather(buf, bytes); }, this, nullptr, 0};
+        if (split && G > 1) {
+            d_xch.reserve((size_t)16 * d * (ce / 2) * n);   // <= 16 polynomials per component on the even cosets of the whole proof
+            xch.buf = d_xch.p; xch.buf_elems = d_xch.n;
+        }
+        const SplitExchange *px = split && G > 1 ? &xch : nullptr;
         if (cel && all_components) csg::eval_constraints_ext(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p, st, cons_ev,
-                                                             split ? &roots : nullptr, split ? &ntt : nullptr);
+                                                             split ? &roots : nullptr, split ? &ntt : nullptr, px);
         else if (cel) csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p + plane * comb_plane, st, cons_ev,
-                                            split ? &roots : nullptr, split ? &ntt : nullptr);
+                                            split ? &roots : nullptr, split ? &ntt : nullptr, px);
         else for (auto &e : cons_ev) CSG_CUDA(cudaEventRecord(e, st.s));
         const float ms = t.stop(st);   // also keeps `polys` alive until the copy has completed
         tm.constraints = plane ? tm.constraints + ms : ms;

@@ -51,6 +51,22 @@ __global__ void coset_mix_kernel(const fe *__restrict__ in, fe *__restrict__ out
         dst[t * n] = s.reduce();
     }
 }
+// the same for a sharded proof: the L input cosets of polynomial p come from L / Ll ranks (coset j at
+// in[(j / Ll) * rank_stride + (p * Ll + j % Ll) * n]); only the Ll output cosets of this rank are formed (M: Ll x L), out[p][Ll][n]
+__global__ void coset_mix_sharded_kernel(const fe *__restrict__ in, fe *__restrict__ out, unsigned long long n, unsigned L, unsigned Ll,
+                                         unsigned long long rank_stride, CrossMat M) {
+    unsigned long long m = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const unsigned p = blockIdx.y;
+    fe v[16];
+    for (unsigned j = 0; j < L; j++) v[j] = in[(j / Ll) * rank_stride + ((unsigned long long)p * Ll + j % Ll) * n + m];
+    fe *dst = out + (unsigned long long)p * Ll * n + m;
+    for (unsigned t = 0; t < Ll; t++) {
+        acc192 s;
+        for (unsigned j = 0; j < L; j++) s.mac(M.m[t * L + j], v[j]);
+        dst[t * n] = s.reduce();
+    }
+}
 // out[e] = sum_k in[k * stride + e], k < count
 __global__ void sum_slices_kernel(const fe *__restrict__ in, fe *__restrict__ out, unsigned long long stride, unsigned count) {
     unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -240,6 +256,13 @@ void coset_mix(const fe *in, fe *out, size_t n, unsigned L, size_t npolys, const
     for (unsigned i = 0; i < L * L; i++) M.m[i] = mat_host[i];
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)npolys);
     CSG_LAUNCH(st, coset_mix_kernel, grid, 256, 0, in, out, (unsigned long long)n, L, M);
+}
+void coset_mix_sharded(const fe *in, fe *out, size_t n, unsigned L, unsigned Ll, size_t rank_stride, size_t npolys, const fe *mat_host, Stream &st) {
+    if (L > 16 || Ll == 0 || L % Ll) throw std::runtime_error("bad coset counts for the sharded mix");
+    CrossMat M;
+    for (unsigned i = 0; i < Ll * L; i++) M.m[i] = mat_host[i];
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)npolys);
+    CSG_LAUNCH(st, coset_mix_sharded_kernel, grid, 256, 0, in, out, (unsigned long long)n, L, Ll, (unsigned long long)rank_stride, M);
 }
 void sum_slices(const fe *in, fe *out, size_t stride, unsigned count, Stream &st) {
     CSG_LAUNCH(st, sum_slices_kernel, (unsigned)((stride + 255) / 256), 256, 0, in, out, (unsigned long long)stride, count);

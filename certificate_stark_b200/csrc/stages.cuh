@@ -19,6 +19,9 @@ void composition_columns(const fe *e, fe *cols, size_t n, unsigned ce, const fe 
 // out[p][j'][m] = sum_j mat[j'*L + j] * in[p][j][m] for npolys blocks of L x n elements; out[e] = sum_k in[k*stride + e]
 void coset_mix(const fe *in, fe *out, size_t n, unsigned L, size_t npolys, const fe *mat_host, Stream &st);
 void sum_slices(const fe *in, fe *out, size_t stride, unsigned count, Stream &st);
+// sharded form: input coset j of polynomial p at in[(j / Ll) * rank_stride + (p * Ll + j % Ll) * n] (slices gathered from L / Ll
+// ranks), mat_host: the Ll rows of the L x L map that belong to this rank; out[p][Ll][n]
+void coset_mix_sharded(const fe *in, fe *out, size_t n, unsigned L, unsigned Ll, size_t rank_stride, size_t npolys, const fe *mat_host, Stream &st);
 
 // values[p * ncols + c] = poly_c(points[p]) for ncols polynomials of n coefficients at polys[c * stride ..]; the final
 // reduction over per-CTA partial sums runs on the host (a few hundred KB)

@@ -45,7 +45,7 @@ def test_example_default_is_cubic(ctx, oracle, csg, ext, hash_fn, num_tx):
 
 
 @pytest.mark.parametrize("ext", [2, 3])
-@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_extension_proof_sharded(csg, ext, world):
     trace, pub = csg.TransactionBatch(seed=5, num_tx=2).transaction_trace()
     opt = csg.ProofOptions(field_extension=ext)

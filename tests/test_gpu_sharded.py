@@ -38,7 +38,7 @@ def test_merkle_update_sharded_with_fewer_ce_cosets_than_ranks(csg, oracle, worl
     sharded_equals_single(csg, oracle, csg.AIR_MERKLE_UPDATE, trace, pub, csg.ProofOptions(), world)
 
 
-@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("hash_fn", [2, 3])
 def test_schnorr_sharded(csg, oracle, world, hash_fn):
     trace, pub = csg.SignatureBatch(seed=5, num_sig=2).schnorr_trace()
