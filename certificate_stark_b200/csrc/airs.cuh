@@ -19,6 +19,7 @@
 #pragma once
 #include "ecc.cuh"
 #include "rescue.cuh"
+#include "rescue_tables.h"
 
 namespace airs {
 using f63::fe;
@@ -100,6 +101,7 @@ struct CombT {
     const fe *alpha_x = nullptr, *beta_x = nullptr;
     size_t coef_stride = 0;
     f63::acc192 sum_x[DEG > 1 ? DEG - 1 : 1];
+    const RescueTables *rt = nullptr;   // device, base field: the Rescue users' coefficient tables (rescue_tables.h)
     CSG_HD fe coef(int slot) const { return slot_coefficient(alpha, beta, group, xp, xp_stride, slot); }
     CSG_HD fe coef_x(int j, int slot) const { return slot_coefficient(alpha_x + (j - 1) * coef_stride, beta_x + (j - 1) * coef_stride, group, xp, xp_stride, slot); }
     CSG_HD void add(int slot, fe v) {
@@ -139,10 +141,14 @@ struct CombT {
 };
 using Comb = CombT<false>;
 using SplitComb = CombT<true>;
-// contributions that share one flag.  Combined mode: sum_k coef(slot_k) * v_k, multiplied by the flag once at flush time;
-// split mode: the flag is multiplied into every value (there is no single coefficient to factor it out of).
+// contributions that share one flag.  Combined mode: sum_k coef(slot_k) * v_k, multiplied by the flag once at flush time.
+// Split mode: the alpha part likewise; the beta part of the current degree group is accumulated in registers and handed
+// to B_g (times the flag) whenever the group of the next slot differs -- slots come in runs of equal declared degree, so
+// that is rare, and no value is multiplied by the flag on its own.
 struct FlagAcc {
     f63::acc192 s, sx[2];   // sx: components 1, 2 of E-valued coefficients (untouched, hence free, in the base field)
+    f63::acc192 sb, sbx[2]; // split mode: beta part of group `gcur`
+    int gcur = -1;
     fe flag;
     CSG_HD explicit FlagAcc(fe f) : flag(f) {}
     template <class CB> CSG_HD void add(CB &C, int slot, fe v) {
@@ -152,16 +158,36 @@ struct FlagAcc {
 #pragma unroll
 #endif
             for (int j = 1; j < CB::D; j++) sx[j - 1].mac(C.coef_x(j, slot), v);
-        } else C.add(slot, f63::mul(flag, v));
-    }
-    template <class CB> CSG_HD void flush(CB &C) {
-        if (!CB::split) {
-            C.sum.mac(flag, s.reduce());
+        } else {
+            const int g = C.group[slot];
+            if (g != gcur) { flush_beta(C); gcur = g; }
+            s.mac(C.alpha[slot], v);
+            sb.mac(C.beta[slot], v);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int j = 1; j < CB::D; j++) C.sum_x[j - 1].mac(flag, sx[j - 1].reduce());
+            for (int j = 1; j < CB::D; j++) {
+                sx[j - 1].mac(C.alpha_x[(j - 1) * C.coef_stride + slot], v);
+                sbx[j - 1].mac(C.beta_x[(j - 1) * C.coef_stride + slot], v);
+            }
         }
+    }
+    template <class CB> CSG_HD void flush_beta(CB &C) {
+        if (gcur < 0) return;
+        C.part_mac(0, gcur, flag, sb.reduce());
+        sb = f63::acc192();
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 1; j < CB::D; j++) { C.part_mac(j, gcur, flag, sbx[j - 1].reduce()); sbx[j - 1] = f63::acc192(); }
+    }
+    template <class CB> CSG_HD void flush(CB &C) {
+        if (CB::split) flush_beta(C);
+        C.sum.mac(flag, s.reduce());
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 1; j < CB::D; j++) C.sum_x[j - 1].mac(flag, sx[j - 1].reduce());
     }
 };
 
@@ -386,26 +412,102 @@ template <> struct Items<SCHNORR> { static constexpr int rescue = 1, ecc = 3; };
 template <> struct Items<RANGE> { static constexpr int rescue = 0, ecc = 0; };
 template <> struct Items<RESCUE> { static constexpr int rescue = 1, ecc = 0; };
 
-// ---- Rescue residual number s of the AIR
+// ---- Rescue residual number s of the AIR: its state columns, round-constant columns and the result slots of its users
+struct RescueItem { int col0, ark0, slot_a, slot_b; bool second; };
+CSG_HD constexpr RescueItem rescue_item(int air, int s) {
+    // transaction AIR: the four leaf/path hash states serve both the leaf-hash phase (setup flag, slots 0,14,28,42:
+    // src/merkle/init/air.rs:171-201) and the authentication paths (hash flag, slots = columns); the fifth state is the
+    // Schnorr message hash
+    return air == TRANSACTION ? (s < 4 ? RescueItem{15 * s - (s >> 1), TX_ARK, 14 * s, 15 * s - (s >> 1), true} : RescueItem{SIG_HASH, TX_ARK, SIG_HASH, 0, false})
+         : air == MERKLE_UPDATE ? RescueItem{15 * s - (s >> 1), 5, 15 * s - (s >> 1), 0, false}
+         : air == MERKLE_INIT ? RescueItem{15 * s - (s >> 1), 0, 14 * s, 0, false}
+         : air == SCHNORR ? RescueItem{SIG_HASH, APW + 15, SIG_HASH, 0, false}
+         : RescueItem{0, 1, 0, 0, false};
+}
+// compiled number of degree groups among the 14 slots of a user (the declared degrees of src/air.rs:76-108 put the slots of
+// the curve registers, their bits and the hash states in up to three groups); the host checks the actual count against it
+CSG_HD constexpr int rescue_item_ng(int air, int s, int user) {
+    return air != TRANSACTION ? 1 : s == 0 ? 2 : s == 1 ? 3 : s == 2 ? 2 : 1;
+}
+
+#if defined(__CUDA_ARCH__)
+template <int NG, class CB>
+__device__ __forceinline__ void rescue_flush(CB &C, const RescueTables &R, int use, fe flag, const f63::acc192 &a, const f63::acc192 (&b)[NG]) {
+    C.sum.mac(flag, a.reduce());
+#pragma unroll
+    for (int q = 0; q < NG; q++)
+        if (q < R.ng[use]) {
+            const int g = R.grp[use][q];
+            if (CB::split) C.part_mac(0, g, flag, b[q].reduce());
+            else C.sum.mac(f63::mul(flag, C.xp[g * C.xp_stride]), b[q].reduce());
+        }
+}
+// rescue_state with the forward MDS product folded into per-proof coefficient tables (rescue_tables.h): the alpha part and
+// the beta part of each degree group of each user are accumulated unreduced and multiplied by the user's flag once.
+template <int NGA, int NGB, class PV, class CB>
+__device__ __forceinline__ void rescue_state_t(const Frame &f, const PV &pv, CB &C, int col0, int ark0, fe flag_a, int use_a, fe flag_b, int use_b) {
+    const RescueTables &R = *C.rt;
+    constexpr int NB = NGB > 0 ? NGB : 1;
+    f63::acc192 aa, ba[NGA], ab, bb[NB];
+#pragma unroll 2
+    for (int j = 0; j < 14; j++) {
+        const fe t = rescue::cube(f.cur(col0 + j));
+        aa.mac(R.a_fwd[use_a][j], t);
+#pragma unroll
+        for (int q = 0; q < NGA; q++) ba[q].mac(R.b_fwd[use_a][q][j], t);
+        if (NGB > 0) {
+            ab.mac(R.a_fwd[use_b][j], t);
+#pragma unroll
+            for (int q = 0; q < NGB; q++) bb[q].mac(R.b_fwd[use_b][q][j], t);
+        }
+    }
+    fe tn[14];
+#pragma unroll
+    for (int j = 0; j < 14; j++) tn[j] = f63::sub(f.next(col0 + j), pv(ark0 + 14 + j));
+    // two rows of the inverse MDS product per iteration: two independent multiply-add chains in flight
+#pragma unroll 1
+    for (int i = 0; i < 14; i += 2) {
+        const uint64_t *inv_mds = CSG_TABLE(CSG_INV_MDS) + i * 14;
+        f63::acc128 bwd0, bwd1;
+#pragma unroll
+        for (int j = 0; j < 14; j++) { bwd0.mac(inv_mds[j], tn[j]); bwd1.mac(inv_mds[14 + j], tn[j]); }
+        const fe v0 = f63::sub(rescue::cube(bwd0.reduce()), pv(ark0 + i)), v1 = f63::sub(rescue::cube(bwd1.reduce()), pv(ark0 + i + 1));
+        aa.mac(R.a_bwd[use_a][i], v0); aa.mac(R.a_bwd[use_a][i + 1], v1);
+#pragma unroll
+        for (int q = 0; q < NGA; q++) { ba[q].mac(R.b_bwd[use_a][q][i], v0); ba[q].mac(R.b_bwd[use_a][q][i + 1], v1); }
+        if (NGB > 0) {
+            ab.mac(R.a_bwd[use_b][i], v0); ab.mac(R.a_bwd[use_b][i + 1], v1);
+#pragma unroll
+            for (int q = 0; q < NGB; q++) { bb[q].mac(R.b_bwd[use_b][q][i], v0); bb[q].mac(R.b_bwd[use_b][q][i + 1], v1); }
+        }
+    }
+    rescue_flush<NGA>(C, R, use_a, flag_a, aa, ba);
+    if (NGB > 0) rescue_flush<NB>(C, R, use_b, flag_b, ab, bb);
+}
+#endif
+
 template <int AIR, class PV, class CB>
 CSG_HD void eval_rescue_item(int s, const Frame &f, const PV &pv, CB &C) {
-    if (AIR == TRANSACTION) {
-        // the four leaf/path hash states serve both the leaf-hash phase (setup flag, slots 0,14,28,42:
-        // src/merkle/init/air.rs:171-201) and the authentication paths (hash flag, slots = columns); the fifth state is the
-        // Schnorr message hash
-        const int col0 = s < 4 ? 15 * s - (s >> 1) : SIG_HASH;
-        const bool path = s < 4;
-        rescue_state(f, pv, C, col0, TX_ARK, path ? pv(TX_SETUP) : pv(TX_SCHNORR_HASH), path ? 14 * s : SIG_HASH, path, path ? pv(TX_HASH) : 0, col0);
-    } else if (AIR == MERKLE_UPDATE) {
-        const int col0 = 15 * s - (s >> 1);
-        rescue_state(f, pv, C, col0, 5, pv(4), col0, false, 0, 0);
-    } else if (AIR == MERKLE_INIT) {
-        rescue_state(f, pv, C, 15 * s - (s >> 1), 0, f63::ONE, 14 * s, false, 0, 0);
-    } else if (AIR == SCHNORR) {
-        rescue_state(f, pv, C, SIG_HASH, APW + 15, pv(APW + 7), SIG_HASH, false, 0, 0);
-    } else if (AIR == RESCUE) {
-        rescue_state(f, pv, C, 0, 1, pv(0), 0, false, 0, 0);
+    const RescueItem it = rescue_item(AIR, s);
+    fe flag_a = f63::ONE, flag_b = 0;
+    if (AIR == TRANSACTION) { flag_a = s < 4 ? pv(TX_SETUP) : pv(TX_SCHNORR_HASH); flag_b = s < 4 ? pv(TX_HASH) : 0; }
+    else if (AIR == MERKLE_UPDATE) flag_a = pv(4);
+    else if (AIR == SCHNORR) flag_a = pv(APW + 7);
+    else if (AIR == RESCUE) flag_a = pv(0);
+#if defined(__CUDA_ARCH__)
+    if constexpr (CB::D == 1) {
+        if (AIR == TRANSACTION) {
+            // item 0: both users own slots 0..13 -- one user under the sum of the flags
+            if (s == 0) rescue_state_t<rescue_item_ng(TRANSACTION, 0, 0), 0>(f, pv, C, it.col0, it.ark0, f63::add(flag_a, flag_b), 0, 0, 0);
+            else if (s == 1) rescue_state_t<rescue_item_ng(TRANSACTION, 1, 0), rescue_item_ng(TRANSACTION, 1, 1)>(f, pv, C, it.col0, it.ark0, flag_a, 2, flag_b, 3);
+            else if (s == 2) rescue_state_t<rescue_item_ng(TRANSACTION, 2, 0), rescue_item_ng(TRANSACTION, 2, 1)>(f, pv, C, it.col0, it.ark0, flag_a, 4, flag_b, 5);
+            else if (s == 3) rescue_state_t<rescue_item_ng(TRANSACTION, 3, 0), rescue_item_ng(TRANSACTION, 3, 1)>(f, pv, C, it.col0, it.ark0, flag_a, 6, flag_b, 7);
+            else rescue_state_t<rescue_item_ng(TRANSACTION, 4, 0), 0>(f, pv, C, it.col0, it.ark0, flag_a, 8, 0, 0);
+        } else rescue_state_t<1, 0>(f, pv, C, it.col0, it.ark0, flag_a, 2 * s, 0, 0);
+        return;
     }
+#endif
+    rescue_state(f, pv, C, it.col0, it.ark0, flag_a, it.slot_a, it.second, flag_b, it.slot_b);
 }
 // ---- curve items: bank 0 = S (generator), bank 1 = h.P (public key); then the final addition
 template <int AIR, class PV, class CB>

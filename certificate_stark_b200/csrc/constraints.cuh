@@ -9,6 +9,7 @@
 #pragma once
 #include "dev.cuh"
 #include "ntt.cuh"
+#include "rescue_tables.h"
 
 namespace csg {
 
@@ -50,7 +51,11 @@ struct ConsArgs {
     unsigned ext_degree;
     fe alpha_x[2][CONS_MAX_CONSTRAINTS], beta_x[2][CONS_MAX_CONSTRAINTS];
     fe a_alpha_x[2][CONS_MAX_ASSERTIONS], a_beta_x[2][CONS_MAX_ASSERTIONS];
+    // base-field Rescue users: alpha / beta with the forward MDS product folded in (fill_rescue_tables)
+    airs::RescueTables rt;
 };
+// after alpha, beta and group are set: the tables of every Rescue user of the AIR
+void fill_rescue_tables(int air_id, ConsArgs &args);
 
 // A sharded proof (comm.cuh) can still use the low-degree splits when every rank owns whole even/odd coset pairs: each rank
 // interpolates on its own even cosets, the coefficient sets are all-gathered, and each rank mixes and evaluates its own odd cosets.

@@ -65,12 +65,15 @@ __global__ void __launch_bounds__(INV_THREADS) boundary_inverse_kernel(const Con
 #ifndef CSG_RESCUE_MINBLOCKS
 #define CSG_RESCUE_MINBLOCKS 6
 #endif
+#ifndef CSG_LOW_MINBLOCKS
+#define CSG_LOW_MINBLOCKS 4
+#endif
 #ifndef CSG_REST_MINBLOCKS
 #define CSG_REST_MINBLOCKS 6
 #endif
 // KIND 0: Rescue residual number blockIdx.z; KIND 1: scalar-multiplication bank blockIdx.z; KIND 2: final point addition
 template <int AIR, int KIND, int DEG = 1>
-__global__ void __launch_bounds__(CONS_THREADS, KIND == 0 ? (DEG == 1 ? CSG_RESCUE_MINBLOCKS : 4) : CSG_ECC_MINBLOCKS)
+__global__ void __launch_bounds__(CONS_THREADS, KIND == 0 ? (DEG == 1 && AIR != airs::TRANSACTION ? CSG_RESCUE_MINBLOCKS : 4) : CSG_ECC_MINBLOCKS)
 cons_item_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W, const fe *__restrict__ ptab,
                  fe *__restrict__ part, unsigned part_items) {
     __shared__ fe xp_s[airs::MAX_GROUPS][CONS_THREADS];   // x^adj of each degree group, one column per thread
@@ -80,6 +83,7 @@ cons_item_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, con
     RowCtx r = row_setup(A, lde, W, ptab, kc, i, xp_s);
     airs::CombT<false, DEG> C{A->alpha, A->beta, A->group, &xp_s[0][threadIdx.x], (size_t)CONS_THREADS, acc192(), nullptr, 0,
                               &A->alpha_x[0][0], &A->beta_x[0][0], (size_t)CONS_MAX_CONSTRAINTS};
+    C.rt = &A->rt;
     if (KIND == 0) airs::eval_rescue_item<AIR>((int)item, r.f, r.pv, C);
     else if (KIND == 1) airs::eval_ecc_bank<AIR>((int)item, r.f, r.pv, C);
     else airs::eval_ecc_final<AIR>(r.f, r.pv, C);
@@ -170,7 +174,7 @@ constexpr size_t split_smem_bytes(int deg) { return (size_t)3 * airs::MAX_SPLIT_
 // KIND 0: Rescue residual number blockIdx.z; KIND 3: the linear rest.
 // low[(((item * DEG + comp) * NP + p) * L + j) * n + i], p = 0 the alpha part, p = 1 + g the beta part of degree group g, j = kc / 2.
 template <int AIR, int KIND, int DEG>
-__global__ void __launch_bounds__(CONS_THREADS, 4)
+__global__ void __launch_bounds__(CONS_THREADS, CSG_LOW_MINBLOCKS)
 cons_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W, const fe *__restrict__ ptab,
                 fe *__restrict__ low, unsigned item0) {
     extern __shared__ uint64_t part_dyn[];
@@ -184,6 +188,7 @@ cons_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, cons
     for (unsigned k = 0; k < 3 * airs::MAX_SPLIT_GROUPS * DEG; k++) part_dyn[k * CONS_THREADS + threadIdx.x] = 0;
     airs::CombT<true, DEG> C{A->alpha, A->beta, A->group, nullptr, 0, acc192(), &part_dyn[threadIdx.x], (size_t)CONS_THREADS,
                              &A->alpha_x[0][0], &A->beta_x[0][0], (size_t)CONS_MAX_CONSTRAINTS};
+    C.rt = &A->rt;
     if (KIND == 0) airs::eval_rescue_item<AIR>((int)blockIdx.z, f, pv, C);
     else airs::eval_rest<AIR>(f, pv, C);
 #pragma unroll
