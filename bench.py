@@ -39,6 +39,10 @@ CONS_KERNELS = {   # name: (description, algorithmic bytes per ce row, fraction 
     "cons_rescue": ("cons_low_kernel<TRANSACTION,0> (5 Rescue residuals per row, even ce cosets, split mode)", 5 * 14 * 8 + 5 * 6 * 8, 0.5, True),
     "cons_ecc_banks": ("phase: cons_ecc_low_kernel<TRANSACTION> (2 banks x 2 curve formulas, even ce cosets) + extension transforms + "
                        "cons_ecc_merge_kernel", 2 * 19 * 8 + 12 * 8 + 2 * 8, 1.0, False),
+    # inside cons_ecc_banks: the largest single launch of a proof.  Per even-coset row: the 18 point columns of each bank and the
+    # 12 key columns of the second one read once, 10 merged formula polynomials written
+    "cons_ecc_low": ("cons_ecc_low_kernel<TRANSACTION> (doubling and mixed-addition formulas of both scalar-multiplication banks, "
+                     "even ce cosets, split mode)", (2 * 18 + 12) * 8 + 10 * 8, 0.5, True),
     "cons_ecc_final": ("cons_item_kernel<TRANSACTION,2> (final point addition)", 36 * 8 + 4 * 8 + 8, 1.0, True),
     "cons_rest": ("phase: cons_low_kernel<TRANSACTION,3> (linear constraints, even cosets) + extension transforms + cons_final_kernel",
                   8 * TRACE_WIDTH + 8 * 8 + 8, 1.0, False),

@@ -127,14 +127,14 @@ struct CombT {
     // the accumulator of B_g of component j: words at part[((j * MAX_SPLIT_GROUPS + g) * 3 + k) * part_stride]
     CSG_HD void part_mac(int j, int g, fe b, fe v) {
         uint64_t *q = part + (size_t)(j * MAX_SPLIT_GROUPS + g) * 3 * part_stride;
-        f63::acc192 t;
+        f63::acc192w t;
         t.lo = q[0]; t.mid = q[part_stride]; t.hi = q[2 * part_stride];
         t.mac(b, v);
         q[0] = t.lo; q[part_stride] = t.mid; q[2 * part_stride] = t.hi;
     }
     CSG_HD fe part_value(int g, int j = 0) const {   // split mode: B_g of component j, reduced
         const uint64_t *q = part + (size_t)(j * MAX_SPLIT_GROUPS + g) * 3 * part_stride;
-        f63::acc192 t;
+        f63::acc192w t;
         t.lo = q[0]; t.mid = q[part_stride]; t.hi = q[2 * part_stride];
         return t.reduce();
     }

@@ -70,7 +70,7 @@ struct SplitExchange {
 // lde: coset-major extended trace; W: root table of size n; ptab / apoly: periodic tables and assertion value
 // polynomials; part: scratch of constraint_scratch_elements() for the per-item partial sums; out[kc * n + i] receives C(x)
 void eval_constraints(int air_id, const ConsArgs *args_dev, const ConsArgs &args_host, const fe *lde, const fe *W, const fe *ptab,
-                      const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr,   // ev: 5 events bracketing the 4 phases
+                      const fe *apoly, fe *part, fe *out, Stream &st, cudaEvent_t *ev = nullptr,   // ev: 6 events: [0..4] bracket the 4 phases, [5] follows the curve-formula kernel inside phase 2
                       const RootTable *rt = nullptr, NttScratch *sc = nullptr,   // given: low-degree constraints use half of the cosets (TX, Schnorr)
                       const SplitExchange *xch = nullptr);                      // given: args describe the cosets of one rank of a sharded proof
 size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets);

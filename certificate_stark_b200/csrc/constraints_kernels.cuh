@@ -149,6 +149,7 @@ void launch(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, const fe
     mark(0);
     if (NR > 0) CSG_LAUNCH(st, (cons_item_kernel<AIR, 0, DEG>), dim3(gx, h.ncosets, NR > 0 ? NR : 1), CONS_THREADS, 0, args_dev, lde, W, ptab, part, (unsigned)(NR + NE));
     mark(1);
+    mark(5);   // no separate formula kernel on this path
     fe *ecc_part = part + (size_t)NR * h.ncosets * n;
     // two scalar-multiplication banks, then the final addition (its own kernel: different code, fewer registers)
     if (NE > 0) CSG_LAUNCH(st, (cons_item_kernel<AIR, 1, DEG>), dim3(gx, h.ncosets, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, ecc_part, (unsigned)(NR + NE));
@@ -384,10 +385,14 @@ void launch_split(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, co
     mark(1);
     if (ecc_split) {
         CSG_LAUNCH(st, (cons_ecc_low_kernel<AIR, DEG>), dim3(gx, L, 4), CONS_THREADS, smem, args_dev, lde, ptab, M, eccl_even);
+        mark(5);   // ev[1] .. ev[5]: the curve-formula kernel alone, the largest single launch of a proof
         extend(eccl_even, eccl_coef, eccl_mix, eccl_odd, DEG * M.total);
         CSG_LAUNCH(st, (cons_ecc_merge_kernel<AIR, DEG>), dim3(gx, ce, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, M, (const fe *)eccl_even, (const fe *)eccl_odd, hi,
                    (unsigned)NE);
-    } else CSG_LAUNCH(st, (cons_item_kernel<AIR, 1, DEG>), dim3(gx, ce, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, hi, (unsigned)NE);
+    } else {
+        mark(5);
+        CSG_LAUNCH(st, (cons_item_kernel<AIR, 1, DEG>), dim3(gx, ce, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, hi, (unsigned)NE);
+    }
     mark(2);
     CSG_LAUNCH(st, (cons_item_kernel<AIR, 2, DEG>), dim3(gx, ce, 1), CONS_THREADS, 0, args_dev, lde, W, ptab, hi, (unsigned)NE);
     mark(3);

@@ -42,15 +42,7 @@ struct fp2acc {
     f63::acc128 c0, c1;
     // += (x0 + x1 u) * y, y given as (y0, y1, 2 y1, y0 + 2 y1)
     CSG_HD void mac(fe x0, fe x1, fe y0, fe y1, fe y1d, fe ys) { c0.mac(x0, y0); c0.mac(x1, y1d); c1.mac(x0, y1); c1.mac(x1, ys); }
-    CSG_HD void add(const fp2acc &o) {
-#if defined(__CUDA_ARCH__)
-        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(c0.lo), "+l"(c0.hi) : "l"(o.c0.lo), "l"(o.c0.hi));
-        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(c1.lo), "+l"(c1.hi) : "l"(o.c1.lo), "l"(o.c1.hi));
-#else
-        c0.lo += o.c0.lo; c0.hi += o.c0.hi + (c0.lo < o.c0.lo ? 1 : 0);
-        c1.lo += o.c1.lo; c1.hi += o.c1.hi + (c1.lo < o.c1.lo ? 1 : 0);
-#endif
-    }
+    CSG_HD void add(const fp2acc &o) { c0.add(o.c0); c1.add(o.c1); }
 };
 #if defined(__CUDACC__)
 static __host__ __device__ __noinline__ fp6 mul(fp6 x, fp6 y) {   // by value: operands travel in registers, not through local memory

@@ -130,32 +130,83 @@ CSG_HD fe pow(fe b, uint64_t e) {
 }
 CSG_HD fe inv(fe a) { return pow(a, P - 2); }
 
-// ---- lazily reduced 128-bit accumulator: sum of up to 14 products a_i * b_i (each < p^2) fits in 128 bits
+// ---- lazily reduced accumulators for sums of products.
+// Device form: the four 32x32 partial products of a term go to three 64-bit COLUMNS that are never aligned with each other
+// until the end -- e (weight 1) += a0 b0, o (weight 2^32) += a0 b1 + a1 b0, h (weight 2^64) += a1 b1 -- so a term is four
+// IMAD.WIDE with the 64-bit addend built in, the carry out of column e rides into column h as the carry-in of its
+// multiply-add, and the carries out of column o are counted (ptxas folds two counts into one IADD3.X).  5-6 instructions
+// per term instead of the ~15 of a 128-bit multiply-add with full carry propagation, most of them on the FMA pipe.
+// Host form: plain 64-bit words.
+
+// sum of up to 14 products a_i * b_i (each < p^2) fits in 128 bits
 struct acc128 {
+#if defined(__CUDA_ARCH__)
+    uint32_t e0, e1, o0, o1, h0, h1;   // value = e + o * 2^32 + h * 2^64 (the total is below 2^128, so h cannot overflow)
+    CSG_HD acc128() : e0(0), e1(0), o0(0), o1(0), h0(0), h1(0) {}
+    CSG_HD void mac(fe a, fe b) {
+        asm("{\n\t"
+            ".reg .u32 a0, a1, b0, b1;\n\t"
+            "mov.b64 {a0, a1}, %6;\n\t"
+            "mov.b64 {b0, b1}, %7;\n\t"
+            "mad.lo.cc.u32 %0, a0, b0, %0;\n\t"
+            "madc.hi.cc.u32 %1, a0, b0, %1;\n\t"
+            "madc.lo.cc.u32 %4, a1, b1, %4;\n\t"    // carry of column e has weight 2^64: the low word of column h
+            "madc.hi.u32 %5, a1, b1, %5;\n\t"
+            "mad.lo.cc.u32 %2, a0, b1, %2;\n\t"
+            "madc.hi.cc.u32 %3, a0, b1, %3;\n\t"
+            "addc.u32 %5, %5, 0;\n\t"               // carry of column o has weight 2^96: the high word of column h
+            "mad.lo.cc.u32 %2, a1, b0, %2;\n\t"
+            "madc.hi.cc.u32 %3, a1, b0, %3;\n\t"
+            "addc.u32 %5, %5, 0;\n\t"
+            "}"
+            : "+r"(e0), "+r"(e1), "+r"(o0), "+r"(o1), "+r"(h0), "+r"(h1) : "l"(a), "l"(b));
+    }
+    CSG_HD void add(const acc128 &x) {
+        asm("add.cc.u32 %0, %0, %6;\n\t"
+            "addc.cc.u32 %1, %1, %7;\n\t"
+            "addc.cc.u32 %4, %4, %10;\n\t"
+            "addc.u32 %5, %5, %11;\n\t"
+            "add.cc.u32 %2, %2, %8;\n\t"
+            "addc.cc.u32 %3, %3, %9;\n\t"
+            "addc.u32 %5, %5, 0;"
+            : "+r"(e0), "+r"(e1), "+r"(o0), "+r"(o1), "+r"(h0), "+r"(h1) : "r"(x.e0), "r"(x.e1), "r"(x.o0), "r"(x.o1), "r"(x.h0), "r"(x.h1));
+    }
+    CSG_HD void words(uint64_t &lo, uint64_t &hi) const {
+        asm("{\n\t"
+            ".reg .u32 l1, l2, l3;\n\t"
+            "add.cc.u32 l1, %3, %4;\n\t"
+            "addc.cc.u32 l2, %6, %5;\n\t"
+            "addc.u32 l3, %7, 0;\n\t"
+            "mov.b64 %0, {%2, l1};\n\t"
+            "mov.b64 %1, {l2, l3};\n\t"
+            "}"
+            : "=l"(lo), "=l"(hi) : "r"(e0), "r"(e1), "r"(o0), "r"(o1), "r"(h0), "r"(h1));
+    }
+#else
     uint64_t lo, hi;
     CSG_HD acc128() : lo(0), hi(0) {}
     CSG_HD void mac(fe a, fe b) {
-#if defined(__CUDA_ARCH__)
-        asm("mad.lo.cc.u64 %0, %2, %3, %0;\n\tmadc.hi.u64 %1, %2, %3, %1;" : "+l"(lo), "+l"(hi) : "l"(a), "l"(b));   // carry chain instead of compares
-#else
         u128 t = mul_wide(a, b);
         lo += t.lo;
         hi += t.hi + (lo < t.lo ? 1 : 0);
-#endif
     }
+    CSG_HD void add(const acc128 &x) { lo += x.lo; hi += x.hi + (lo < x.lo ? 1 : 0); }
+    CSG_HD void words(uint64_t &l, uint64_t &h) const { l = lo; h = hi; }
+#endif
     // value mod p (Montgomery-reduced): bring hi below p first so that t < p * 2^64
     CSG_HD fe reduce() const {
-        uint64_t h = hi;
+        uint64_t l, h;
+        words(l, h);
         if (h >= 2 * P) h -= 2 * P;
         if (h >= P) h -= P;
-        return redc(lo, h);
+        return redc(l, h);
     }
 };
 
-// ---- lazily reduced 192-bit accumulator for long sums of products (the random linear combination of constraints)
-struct acc192 {
+// 192-bit accumulator as three plain words: the form in which partial sums are parked in memory (airs.cuh, split mode)
+struct acc192w {
     uint64_t lo, mid, hi;
-    CSG_HD acc192() : lo(0), mid(0), hi(0) {}
+    CSG_HD acc192w() : lo(0), mid(0), hi(0) {}
     CSG_HD void mac(fe a, fe b) {
 #if defined(__CUDA_ARCH__)
         asm("mad.lo.cc.u64 %0, %3, %4, %0;\n\tmadc.hi.cc.u64 %1, %3, %4, %1;\n\taddc.u64 %2, %2, 0;" : "+l"(lo), "+l"(mid), "+l"(hi) : "l"(a), "l"(b));
@@ -179,6 +230,51 @@ struct acc192 {
         return add(add(m, redc(lo, 0)), mul(hi, R2));
     }
 };
+
+// ---- lazily reduced 192-bit accumulator for long sums of products (the random linear combination of constraints)
+#if defined(__CUDA_ARCH__)
+struct acc192 {
+    uint32_t e0, e1, o0, o1, h0, h1, c1, c2;   // value = e + o * 2^32 + h * 2^64 + c1 * 2^96 + c2 * 2^128
+    CSG_HD acc192() : e0(0), e1(0), o0(0), o1(0), h0(0), h1(0), c1(0), c2(0) {}
+    CSG_HD void mac(fe a, fe b) {
+        asm("{\n\t"
+            ".reg .u32 a0, a1, b0, b1;\n\t"
+            "mov.b64 {a0, a1}, %8;\n\t"
+            "mov.b64 {b0, b1}, %9;\n\t"
+            "mad.lo.cc.u32 %0, a0, b0, %0;\n\t"
+            "madc.hi.cc.u32 %1, a0, b0, %1;\n\t"
+            "madc.lo.cc.u32 %4, a1, b1, %4;\n\t"
+            "madc.hi.cc.u32 %5, a1, b1, %5;\n\t"
+            "addc.u32 %7, %7, 0;\n\t"
+            "mad.lo.cc.u32 %2, a0, b1, %2;\n\t"
+            "madc.hi.cc.u32 %3, a0, b1, %3;\n\t"
+            "addc.u32 %6, %6, 0;\n\t"
+            "mad.lo.cc.u32 %2, a1, b0, %2;\n\t"
+            "madc.hi.cc.u32 %3, a1, b0, %3;\n\t"
+            "addc.u32 %6, %6, 0;\n\t"
+            "}"
+            : "+r"(e0), "+r"(e1), "+r"(o0), "+r"(o1), "+r"(h0), "+r"(h1), "+r"(c1), "+r"(c2) : "l"(a), "l"(b));
+    }
+    CSG_HD fe reduce() const {
+        acc192w w;
+        uint32_t top;
+        asm("{\n\t"
+            ".reg .u32 l1, m0, m1;\n\t"
+            "add.cc.u32 l1, %4, %5;\n\t"
+            "addc.cc.u32 m0, %7, %6;\n\t"
+            "addc.cc.u32 m1, %8, %9;\n\t"
+            "addc.u32 %2, %10, 0;\n\t"
+            "mov.b64 %0, {%3, l1};\n\t"
+            "mov.b64 %1, {m0, m1};\n\t"
+            "}"
+            : "=l"(w.lo), "=l"(w.mid), "=r"(top) : "r"(e0), "r"(e1), "r"(o0), "r"(o1), "r"(h0), "r"(h1), "r"(c1), "r"(c2));
+        w.hi = top;
+        return w.reduce();
+    }
+};
+#else
+typedef acc192w acc192;
+#endif
 
 CSG_HD fe root_of_unity(unsigned logn) {  // primitive 2^logn-th root (winterfell StarkField::get_root_of_unity)
     fe r = to_mont(TWO_ADIC_ROOT);

@@ -125,7 +125,7 @@ struct csg_ctx {
     DBuf<fe> d_pw;
     csg_timings tm{};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // csg_timer_start / csg_timer_stop
-    cudaEvent_t cons_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t cons_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool split_low_degree = getenv("CSG_NO_SPLIT") == nullptr;   // CSG_NO_SPLIT=1: evaluate every constraint on every coset (A/B testing)
     cudaStream_t copy_stream = nullptr;          // H2D copies of trace column chunks, overlapped with their extension
     std::vector<cudaEvent_t> chunk_ev;
@@ -417,6 +417,7 @@ struct csg_ctx {
         tm.constraints = plane ? tm.constraints + ms : ms;
         float *parts_ms[4] = {&tm.cons_rescue, &tm.cons_ecc_banks, &tm.cons_ecc_final, &tm.cons_rest};
         for (int k = 0; k < 4; k++) { float pm = 0; CSG_CUDA(cudaEventElapsedTime(&pm, cons_ev[k], cons_ev[k + 1])); *parts_ms[k] = plane ? *parts_ms[k] + pm : pm; }
+        { float pm = 0; CSG_CUDA(cudaEventElapsedTime(&pm, cons_ev[1], cons_ev[5])); tm.cons_ecc_low = plane ? tm.cons_ecc_low + pm : pm; }
         if (plane + 1 == d || all_components) stage = S_EVALUATED;
     }
     // E-valued coefficients: the constraint values are base-field elements, so component j of the merged column is the same

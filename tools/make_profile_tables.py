@@ -36,9 +36,9 @@ def parse(path):
 
 
 def label(k):
-    for pat, name in [("cons_low_kernel<0, 0>", "cons_low<TX,0> Rescue residuals (even cosets)"), ("cons_ecc_low", "cons_ecc_low<TX> curve formulas (even cosets)"),
+    for pat, name in [("cons_low_kernel<0, 0", "cons_low<TX,0> Rescue residuals (even cosets)"), ("cons_ecc_low", "cons_ecc_low<TX> curve formulas (even cosets)"),
                       ("cons_ecc_merge", "cons_ecc_merge<TX> banks, all cosets"), ("cons_item_kernel<0, 2", "cons_item<TX,2> final point addition"),
-                      ("cons_low_kernel<0, 3>", "cons_low<TX,3> linear rest (even cosets)"), ("cons_final", "cons_final divisors + boundary"),
+                      ("cons_low_kernel<0, 3", "cons_low<TX,3> linear rest (even cosets)"), ("cons_final", "cons_final divisors + boundary"),
                       ("ntt1024_kernel<1", "ntt1024<staged> pass A"), ("ntt1024_kernel<0", "ntt1024<direct> pass B"), ("ntt_pass", "ntt_pass (generic)"),
                       ("hash_rows", "hash_rows<Blake3>"), ("merkle_level", "merkle_level<Blake3>")]:
         if pat in k:
@@ -67,7 +67,8 @@ def find(rows, pat):
 
 traffic = {"_source": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none, python bench.py --profile --steps 1 (1024 tx); "
                       f"profiles/{tag}_ncu_cons_summary.txt", "_pipes": {}}
-for key, pat in [("cons_rescue", "cons_low_kernel<0, 0>"), ("cons_ecc_final", "cons_item_kernel<0, 2"), ("cons_ecc_banks", "cons_ecc_low"), ("cons_rest", "cons_low_kernel<0, 3>")]:
+for key, pat in [("cons_rescue", "cons_low_kernel<0, 0"), ("cons_ecc_final", "cons_item_kernel<0, 2"), ("cons_ecc_banks", "cons_ecc_low"), ("cons_ecc_low", "cons_ecc_low"),
+                 ("cons_rest", "cons_low_kernel<0, 3")]:
     r = find(cons, pat)
     if r:
         traffic[key] = int(r.get("dramR", 0) + r.get("dramW", 0))
