@@ -107,12 +107,51 @@ CSG_HD fe redc_reference(uint64_t lo, uint64_t hi) {
     return u >= P ? u - P : u;
 }
 
-CSG_HD fe mul(fe a, fe b) { u128 t = mul_wide(a, b); return redc(t.lo, t.hi); }
+// a * b * 2^-64 mod p as a value in [0, a * b / 2^64 + p] (below 2p when a * b < p * 2^64): product and reduction in one
+// carry chain on the device.  The four partial products land directly in the words they belong to (two of them as
+// multiply-adds onto the middle words), and each reduction step m = -t_k, t += m * p is ONE multiply-add whose carry-in is
+// the carry of t_k + m (set exactly when t_k != 0): 22 SASS instructions for a full modular multiplication instead of 28.
+CSG_HD uint64_t mul_raw(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__) && !defined(CSG_REDC_REFERENCE) && !defined(CSG_REDC_CHECK)
+    uint64_t u;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, b0, b1, t0, t1, t2, t3, m, d;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "mov.b64 {b0, b1}, %2;\n\t"
+        "mul.lo.u32 t0, a0, b0;\n\t"
+        "mul.hi.u32 t1, a0, b0;\n\t"
+        "mul.lo.u32 t2, a1, b1;\n\t"
+        "mul.hi.u32 t3, a1, b1;\n\t"
+        "mad.lo.cc.u32 t1, a0, b1, t1;\n\t"
+        "madc.hi.cc.u32 t2, a0, b1, t2;\n\t"
+        "addc.u32 t3, t3, 0;\n\t"
+        "mad.lo.cc.u32 t1, a1, b0, t1;\n\t"
+        "madc.hi.cc.u32 t2, a1, b0, t2;\n\t"
+        "addc.u32 t3, t3, 0;\n\t"
+        "sub.u32 m, 0, t0;\n\t"
+        "add.cc.u32 d, t0, m;\n\t"                     // carry = (t0 != 0)
+        "madc.lo.cc.u32 t1, m, 0x41800000, t1;\n\t"
+        "madc.hi.cc.u32 t2, m, 0x41800000, t2;\n\t"
+        "addc.u32 t3, t3, 0;\n\t"
+        "sub.u32 m, 0, t1;\n\t"
+        "add.cc.u32 d, t1, m;\n\t"                     // carry = (t1 != 0)
+        "madc.lo.cc.u32 t2, m, 0x41800000, t2;\n\t"
+        "madc.hi.u32 t3, m, 0x41800000, t3;\n\t"
+        "mov.b64 %0, {t2, t3};\n\t"
+        "}"
+        : "=l"(u) : "l"(a), "l"(b));
+    return u;
+#else
+    u128 t = mul_wide(a, b);
+    return redc_raw(t.lo, t.hi);
+#endif
+}
+CSG_HD fe mul(fe a, fe b) { const uint64_t u = mul_raw(a, b); return u >= P ? u - P : u; }
 CSG_HD fe sqr(fe a) { return mul(a, a); }
 // lazy arithmetic on values in [0, 2p) (2p < 2^64; 4p is not, so sums are brought back below 2p at once):
 //   mul_2p: a < 2p, b < p  ->  a*b*2^-64 mod p, below 1.52 p, no conditional subtraction
 //   add_2p / sub_2p: operands and result in [0, 2p)
-CSG_HD uint64_t mul_2p(uint64_t a, fe b) { u128 t = mul_wide(a, b); return redc_raw(t.lo, t.hi); }
+CSG_HD uint64_t mul_2p(uint64_t a, fe b) { return mul_raw(a, b); }
 CSG_HD uint64_t add_2p(uint64_t a, uint64_t b) { uint64_t s = a + b; return s >= 2 * P ? s - 2 * P : s; }   // needs a + b < 2^64: one operand from mul_2p
 CSG_HD uint64_t add_2p_any(uint64_t a, uint64_t b) { const uint64_t t = 2 * P - b; return a >= t ? a - t : a + b; }   // any a, b < 2p (4p > 2^64)
 CSG_HD uint64_t sub_2p(uint64_t a, uint64_t b) { return a >= b ? a - b : a + 2 * P - b; }
