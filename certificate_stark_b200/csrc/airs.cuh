@@ -336,7 +336,12 @@ CSG_HD void scalar_mult_bank_outputs(const Frame &f, CB &C, int o, const fe (&q)
 #endif
     for (int i = 0; i < 6; i++) { p.x.c[i] = f.cur(o + i); p.y.c[i] = f.cur(o + 6 + i); p.z.c[i] = f.cur(o + 12 + i); }
     const ecc::point r = formula == 0 ? ecc::double_point(p) : ecc::add_mixed(p, ecc::load6(q), ecc::load6(q + 6));
-    for (int i = 0; i < 6; i++) { C.add(o + i, r.x.c[i]); C.add(o + 6 + i, r.y.c[i]); C.add(o + 12 + i, r.z.c[i]); }
+    // slot order = column order: the runs of equal degree group stay together (x, then y and z)
+    FlagAcc a(f63::ONE);
+    for (int i = 0; i < 6; i++) a.add(C, o + i, r.x.c[i]);
+    for (int i = 0; i < 6; i++) a.add(C, o + 6 + i, r.y.c[i]);
+    for (int i = 0; i < 6; i++) a.add(C, o + 12 + i, r.z.c[i]);
+    a.flush(C);
 }
 template <class CB>
 CSG_HD fe scalar_mult_bank_merge(const Frame &f, const CB &C, int comp, int o, fe doubling, fe addition, fe Cd, fe Cm) {   // comp: component of E-valued coefficients

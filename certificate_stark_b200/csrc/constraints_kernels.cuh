@@ -175,7 +175,7 @@ constexpr size_t split_smem_bytes(int deg) { return (size_t)3 * airs::MAX_SPLIT_
 // KIND 0: Rescue residual number blockIdx.z; KIND 3: the linear rest.
 // low[(((item * DEG + comp) * NP + p) * L + j) * n + i], p = 0 the alpha part, p = 1 + g the beta part of degree group g, j = kc / 2.
 template <int AIR, int KIND, int DEG>
-__global__ void __launch_bounds__(CONS_THREADS, KIND == 3 && DEG == 1 ? CSG_REST_MINBLOCKS : CSG_LOW_MINBLOCKS)   // the linear rest is latency-bound: 6 CTAs measured best
+__global__ void __launch_bounds__(CONS_THREADS, CSG_LOW_MINBLOCKS)   // 5 or 6 CTAs (spills) measured no faster for either kind
 cons_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W, const fe *__restrict__ ptab,
                 fe *__restrict__ low, unsigned item0) {
     extern __shared__ uint64_t part_dyn[];
