@@ -12,5 +12,5 @@ cap() {  # name, kernel regex, extra ncu args
 }
 cap cons "cons_" "-c 6"
 cap ntt "ntt" "-s 8 -c 6"
-cap hash "hash_rows|merkle_level" "-c 3"
+[ -n "$SKIP_HASH" ] || cap hash "hash_rows|merkle_level" "-c 3"
 ls -la $D gpurun_out | tail -20
