@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(32 * F_LANES, 512 / (32 * F_LANES)) ntt1024_ke
     // stays in L1) is applied on the way in and preB[lane] joins the twiddle on the way out: the data are then the only
     // stream read from HBM (the full per-coset table and the twiddle gather of the generic kernel are not needed).
     const bool fold = a.tw_logn && preA && preB;
+    const bool chain_out = a.tw_logn && !a.postA && !a.postB && !a.use_scalar;   // pass A: the output twiddle is a per-thread geometric chain
+    fe *PF = T2 + 1024;                                                      // its seeds, [3][NTH]
     auto scaled = [&](fe v, unsigned e, unsigned l) -> fe {   // the input scaling of element e of lane l of this tile
         if (fold) return mul(v, preA[e]);
         if (a.preFull) return mul(v, a.preFull[blockIdx.z * a.pre_full_bz + e * a.in_se + (lane0 + l) * a.in_sl]);
@@ -215,6 +217,20 @@ __global__ void __launch_bounds__(32 * F_LANES, 512 / (32 * F_LANES)) ntt1024_ke
             const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + l * F_SP + e);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(ok ? 8u : 0u) : "memory");
         }
+        if (chain_out) {
+            // the seeds of this thread's output twiddle chain (two roots and the lane's pre-scale) come along: read at the start
+            // of the output phase they cost every CTA one more exposed round trip
+            const unsigned l = tid & (F_LANES - 1), e0 = tid >> LLOG, L = lane0 + l;
+            if (L < a.nlanes) {
+                const unsigned long long N = 1ULL << a.logW;
+                unsigned long long i_step = (32ULL * L) << (a.logW - a.tw_logn), i_g0 = ((unsigned long long)e0 * L) << (a.logW - a.tw_logn);
+                if (a.inverse) { i_step = (N - i_step) & (N - 1); i_g0 = (N - i_g0) & (N - 1); }
+                const fe *srcs[3] = {a.W + i_step, a.W + i_g0, fold ? preB + L : a.W};   // W[0] = 1 when there is no pre-scale
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(PF + k * NTH + tid)), "l"(srcs[k]) : "memory");
+            }
+        }
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
@@ -222,8 +238,19 @@ __global__ void __launch_bounds__(32 * F_LANES, 512 / (32 * F_LANES)) ntt1024_ke
     fe *mine = sm + warp * F_SP;
     if (lane0 + warp < a.nlanes) {
         uint64_t v[32];
+        // register r: a = brev5(r).  The two common cases first, each a compact run of code: the unrolled general form with its
+        // three optional scalings per element spreads the executed instructions over far more instruction-cache lines
+        if (!STAGE_IN && !a.preFull && !preA && !preB) {
+            const fe *src = in + (lane0 + warp) * a.in_sl;
 #pragma unroll
-        for (int k = 0; k < 32; k++) v[k] = STAGE_IN ? scaled(mine[32 * brev5(k) + lane], 32 * brev5(k) + lane, warp) : load_scaled(32 * brev5(k) + lane, warp);   // register r: a = brev5(r)
+            for (int k = 0; k < 32; k++) v[k] = src[(32 * brev5(k) + lane) * a.in_se];
+        } else if (STAGE_IN && fold) {
+#pragma unroll
+            for (int k = 0; k < 32; k++) v[k] = mul(mine[32 * brev5(k) + lane], preA[32 * brev5(k) + lane]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; k++) v[k] = STAGE_IN ? scaled(mine[32 * brev5(k) + lane], 32 * brev5(k) + lane, warp) : load_scaled(32 * brev5(k) + lane, warp);
+        }
         __syncwarp();
 #pragma unroll 1
         for (int phase = 0; phase < 2; phase++) {
@@ -247,16 +274,14 @@ __global__ void __launch_bounds__(32 * F_LANES, 512 / (32 * F_LANES)) ntt1024_ke
     }
     __syncthreads();
 
-    const fe *postA = a.postA ? a.postA + blockIdx.z * a.post_bz : nullptr;
-    const fe *postB = a.postB ? a.postB + blockIdx.z * a.post_bz : nullptr;
-    if (a.tw_logn && !postA && !postB && !a.use_scalar) {
+    if (chain_out) {
         // pass A: element e of lane L is multiplied by w_n^(+-e L) (times preB[L] when folded).  A thread keeps one lane and
         // walks e in steps of 32: the factors form a geometric sequence, two interleaved chains, no table gather
         const unsigned l = tid & (F_LANES - 1), e0 = tid >> LLOG, L = lane0 + l;
         if (L < a.nlanes) {
-            const fe step = root_pow(a.W, a.logW, a.tw_logn, 32ULL * L, a.inverse), step2 = sqr(step);
-            fe g0 = root_pow(a.W, a.logW, a.tw_logn, (unsigned long long)e0 * L, a.inverse);
-            if (fold) g0 = mul(g0, preB[L]);
+            const fe step = STAGE_IN ? PF[tid] : root_pow(a.W, a.logW, a.tw_logn, 32ULL * L, a.inverse), step2 = sqr(step);
+            fe g0 = STAGE_IN ? PF[NTH + tid] : root_pow(a.W, a.logW, a.tw_logn, (unsigned long long)e0 * L, a.inverse);
+            if (fold) g0 = mul(g0, STAGE_IN ? PF[2 * NTH + tid] : preB[L]);
             fe g1 = mul(g0, step);
             fe *o = out + L * a.out_sl;
             const fe *src = sm + l * F_SP;
@@ -270,6 +295,8 @@ __global__ void __launch_bounds__(32 * F_LANES, 512 / (32 * F_LANES)) ntt1024_ke
         }
         return;
     }
+    const fe *postA = a.postA ? a.postA + blockIdx.z * a.post_bz : nullptr;
+    const fe *postB = a.postB ? a.postB + blockIdx.z * a.post_bz : nullptr;
 #pragma unroll 4
     for (unsigned idx = tid; idx < 1024 * F_LANES; idx += NTH) {
         const unsigned l = idx & (F_LANES - 1), e = idx >> LLOG;
@@ -293,7 +320,7 @@ bool fast1024_applies(const PassArgs &a) {
 }
 template <bool STAGE_IN, int F_LANES>
 void launch_fast1024_as(const PassArgs &a, const Fft32Tw &tw, unsigned ncols, unsigned ncosets, Stream &st) {
-    const size_t smem = ((size_t)F_LANES * FastShape<F_LANES>::SP + 1024) * sizeof(fe);
+    const size_t smem = ((size_t)F_LANES * FastShape<F_LANES>::SP + 1024 + 3 * FastShape<F_LANES>::THREADS) * sizeof(fe);
     dim3 grid((a.nlanes + F_LANES - 1) / F_LANES, ncols, ncosets);
     CSG_CUDA(cudaFuncSetAttribute(ntt1024_kernel<STAGE_IN, F_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CSG_LAUNCH(st, (ntt1024_kernel<STAGE_IN, F_LANES>), grid, FastShape<F_LANES>::THREADS, smem, a, tw);
