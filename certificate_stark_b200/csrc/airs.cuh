@@ -20,13 +20,18 @@
 #include "ecc.cuh"
 #include "rescue.cuh"
 #include "rescue_tables.h"
+#include <stdexcept>
 
 // Unroll factor of the short per-element loops of the linear constraints (device).  Fully unrolled, the linear-rest kernel is
 // 150 KB of straight-line code that every warp streams through once, and ncu attributes 30 % of its stall cycles to
 // instruction fetch (no_instruction); rolled loops measured 0.2 ms faster.  (Making the accumulator reduction a real call
 // halves the code again but measured 0.9 ms slower.)
+#if defined(__CUDA_ARCH__)
 #define CSG_PRAGMA_(x) _Pragma(#x)
 #define CSG_PRAGMA(x) CSG_PRAGMA_(x)
+#else
+#define CSG_PRAGMA(x)
+#endif
 #ifndef CSG_REST_UNROLL
 #define CSG_REST_UNROLL 1
 #endif
@@ -460,11 +465,10 @@ CSG_HD constexpr int rescue_item_ng(int air, int s, int user) {
     return air != TRANSACTION ? 1 : s == 0 ? 2 : s == 1 ? 3 : s == 2 ? 2 : 1;
 }
 
-#if defined(__CUDA_ARCH__)
 template <int NG, class CB>
-__device__ __forceinline__ void rescue_flush(CB &C, const RescueTables &R, int use, fe flag, const f63::acc192 &a, const f63::acc192 (&b)[NG]) {
+CSG_HD void rescue_flush(CB &C, const RescueTables &R, int use, fe flag, const f63::acc192 &a, const f63::acc192 (&b)[NG]) {
     C.sum.mac(flag, a.reduce());
-#pragma unroll
+CSG_PRAGMA(unroll)
     for (int q = 0; q < NG; q++)
         if (q < R.ng[use]) {
             const int g = R.grp[use][q];
@@ -475,7 +479,7 @@ __device__ __forceinline__ void rescue_flush(CB &C, const RescueTables &R, int u
 // rescue_state with the forward MDS product folded into per-proof coefficient tables (rescue_tables.h): the alpha part and
 // the beta part of each degree group of each user are accumulated unreduced and multiplied by the user's flag once.
 template <int NGA, int NGB, class PV, class CB>
-__device__ __forceinline__ void rescue_state_t(const Frame &f, const PV &pv, CB &C, int col0, int ark0, fe flag_a, int use_a, fe flag_b, int use_b) {
+CSG_HD void rescue_state_t(const Frame &f, const PV &pv, CB &C, int col0, int ark0, fe flag_a, int use_a, fe flag_b, int use_b) {
     const RescueTables &R = *C.rt;
     constexpr int NB = NGB > 0 ? NGB : 1;
     f63::acc192 aa, ba[NGA], ab, bb[NB];
@@ -483,38 +487,74 @@ CSG_PRAGMA(unroll CSG_RESCUE_FWD_UNROLL)
     for (int j = 0; j < 14; j++) {
         const fe t = rescue::cube(f.cur(col0 + j));
         aa.mac(R.a_fwd[use_a][j], t);
-#pragma unroll
+CSG_PRAGMA(unroll)
         for (int q = 0; q < NGA; q++) ba[q].mac(R.b_fwd[use_a][q][j], t);
         if (NGB > 0) {
             ab.mac(R.a_fwd[use_b][j], t);
-#pragma unroll
+CSG_PRAGMA(unroll)
             for (int q = 0; q < NGB; q++) bb[q].mac(R.b_fwd[use_b][q][j], t);
         }
     }
     fe tn[14];
-#pragma unroll
+CSG_PRAGMA(unroll)
     for (int j = 0; j < 14; j++) tn[j] = f63::sub(f.next(col0 + j), pv(ark0 + 14 + j));
     // two rows of the inverse MDS product per iteration: two independent multiply-add chains in flight
-#pragma unroll 1
+CSG_PRAGMA(unroll 1)
     for (int i = 0; i < 14; i += 2) {
         const uint64_t *inv_mds = CSG_TABLE(CSG_INV_MDS) + i * 14;
         f63::acc128 bwd0, bwd1;
-#pragma unroll
+CSG_PRAGMA(unroll)
         for (int j = 0; j < 14; j++) { bwd0.mac(inv_mds[j], tn[j]); bwd1.mac(inv_mds[14 + j], tn[j]); }
         const fe v0 = f63::sub(rescue::cube(bwd0.reduce()), pv(ark0 + i)), v1 = f63::sub(rescue::cube(bwd1.reduce()), pv(ark0 + i + 1));
         aa.mac(R.a_bwd[use_a][i], v0); aa.mac(R.a_bwd[use_a][i + 1], v1);
-#pragma unroll
+CSG_PRAGMA(unroll)
         for (int q = 0; q < NGA; q++) { ba[q].mac(R.b_bwd[use_a][q][i], v0); ba[q].mac(R.b_bwd[use_a][q][i + 1], v1); }
         if (NGB > 0) {
             ab.mac(R.a_bwd[use_b][i], v0); ab.mac(R.a_bwd[use_b][i + 1], v1);
-#pragma unroll
+CSG_PRAGMA(unroll)
             for (int q = 0; q < NGB; q++) { bb[q].mac(R.b_bwd[use_b][q][i], v0); bb[q].mac(R.b_bwd[use_b][q][i + 1], v1); }
         }
     }
     rescue_flush<NGA>(C, R, use_a, flag_a, aa, ba);
     if (NGB > 0) rescue_flush<NB>(C, R, use_b, flag_b, ab, bb);
 }
-#endif
+
+// The tables of every Rescue user of an AIR from the coefficients of one proof (host; rescue_tables.h).  Throws when the
+// slots of a user span more degree groups than its accumulators were compiled for.
+inline void fill_rescue_tables(int air, const fe *alpha, const fe *beta, const uint8_t *group, unsigned nconstraints, RescueTables &R) {
+    R = RescueTables{};
+    const int items = air == TRANSACTION ? 5 : air == MERKLE_UPDATE || air == MERKLE_INIT ? 4 : air == SCHNORR || air == RESCUE ? 1 : 0;
+    const uint64_t *mds = CSG_MDS_M;
+    for (int s = 0; s < items; s++) {
+        const RescueItem it = rescue_item(air, s);
+        for (int user = 0; user < (it.second ? 2 : 1); user++) {
+            const int slot = user ? it.slot_b : it.slot_a, use = 2 * s + user;
+            if (use >= RT_MAX_USES || slot + 14 > (int)nconstraints) throw std::runtime_error("Rescue user outside the constraint table");
+            unsigned ng = 0;
+            int q_of[14];
+            for (int i = 0; i < 14; i++) {
+                unsigned q = 0;
+                while (q < ng && R.grp[use][q] != group[slot + i]) q++;
+                if (q == ng) {
+                    if (ng == (unsigned)rescue_item_ng(air, s, user)) throw std::runtime_error("more degree groups among the slots of a Rescue user than compiled for");
+                    R.grp[use][ng++] = group[slot + i];
+                }
+                q_of[i] = (int)q;
+            }
+            R.ng[use] = (unsigned char)ng;
+            for (int i = 0; i < 14; i++) { R.a_bwd[use][i] = alpha[slot + i]; R.b_bwd[use][q_of[i]][i] = beta[slot + i]; }
+            for (int j = 0; j < 14; j++) {
+                fe a = 0, b[RT_MAX_GROUPS] = {0, 0, 0};
+                for (int i = 0; i < 14; i++) {
+                    a = f63::add(a, f63::mul(alpha[slot + i], mds[i * 14 + j]));
+                    b[q_of[i]] = f63::add(b[q_of[i]], f63::mul(beta[slot + i], mds[i * 14 + j]));
+                }
+                R.a_fwd[use][j] = f63::neg(a);
+                for (unsigned q = 0; q < ng; q++) R.b_fwd[use][q][j] = f63::neg(b[q]);
+            }
+        }
+    }
+}
 
 template <int AIR, class PV, class CB>
 CSG_HD void eval_rescue_item(int s, const Frame &f, const PV &pv, CB &C) {
@@ -525,7 +565,11 @@ CSG_HD void eval_rescue_item(int s, const Frame &f, const PV &pv, CB &C) {
     else if (AIR == SCHNORR) flag_a = pv(APW + 7);
     else if (AIR == RESCUE) flag_a = pv(0);
 #if defined(__CUDA_ARCH__)
-    if constexpr (CB::D == 1) {
+    constexpr bool tables = true;    // base field on the device: always through the tables
+#else
+    const bool tables = C.rt != nullptr;   // host (verifier, tests): the direct form unless tables are supplied
+#endif
+    if constexpr (CB::D == 1) if (tables) {
         if (AIR == TRANSACTION) {
             // item 0: both users own slots 0..13 -- one user under the sum of the flags
             if (s == 0) rescue_state_t<rescue_item_ng(TRANSACTION, 0, 0), 0>(f, pv, C, it.col0, it.ark0, f63::add(flag_a, flag_b), 0, 0, 0);
@@ -536,7 +580,6 @@ CSG_HD void eval_rescue_item(int s, const Frame &f, const PV &pv, CB &C) {
         } else rescue_state_t<1, 0>(f, pv, C, it.col0, it.ark0, flag_a, 2 * s, 0, 0);
         return;
     }
-#endif
     rescue_state(f, pv, C, it.col0, it.ark0, flag_a, it.slot_a, it.second, flag_b, it.slot_b);
 }
 // ---- curve items: bank 0 = S (generator), bank 1 = h.P (public key); then the final addition

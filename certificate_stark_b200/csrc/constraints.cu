@@ -28,49 +28,7 @@ unsigned long long redc_violations() {
 unsigned long long redc_violations() { return 0; }
 #endif
 
-void fill_rescue_tables(int air_id, ConsArgs &h) {
-    airs::RescueTables &R = h.rt;
-    memset(&R, 0, sizeof R);
-    int items = 0;
-    switch (air_id) {
-    case airs::TRANSACTION: items = airs::Items<airs::TRANSACTION>::rescue; break;
-    case airs::MERKLE_UPDATE: items = airs::Items<airs::MERKLE_UPDATE>::rescue; break;
-    case airs::MERKLE_INIT: items = airs::Items<airs::MERKLE_INIT>::rescue; break;
-    case airs::SCHNORR: items = airs::Items<airs::SCHNORR>::rescue; break;
-    case airs::RESCUE: items = airs::Items<airs::RESCUE>::rescue; break;
-    default: break;
-    }
-    const uint64_t *mds = CSG_MDS_M;
-    for (int s = 0; s < items; s++) {
-        const airs::RescueItem it = airs::rescue_item(air_id, s);
-        for (int user = 0; user < (it.second ? 2 : 1); user++) {
-            const int slot = user ? it.slot_b : it.slot_a, use = 2 * s + user;
-            if (use >= airs::RT_MAX_USES || slot + 14 > (int)h.nconstraints) throw std::runtime_error("Rescue user outside the constraint table");
-            unsigned ng = 0;
-            int q_of[14];
-            for (int i = 0; i < 14; i++) {
-                unsigned q = 0;
-                while (q < ng && R.grp[use][q] != h.group[slot + i]) q++;
-                if (q == ng) {
-                    if (ng == (unsigned)airs::rescue_item_ng(air_id, s, user)) throw std::runtime_error("more degree groups among the slots of a Rescue user than compiled for");
-                    R.grp[use][ng++] = h.group[slot + i];
-                }
-                q_of[i] = (int)q;
-            }
-            R.ng[use] = (unsigned char)ng;
-            for (int i = 0; i < 14; i++) { R.a_bwd[use][i] = h.alpha[slot + i]; R.b_bwd[use][q_of[i]][i] = h.beta[slot + i]; }
-            for (int j = 0; j < 14; j++) {
-                fe a = 0, b[airs::RT_MAX_GROUPS] = {0, 0, 0};
-                for (int i = 0; i < 14; i++) {
-                    a = add(a, mul(h.alpha[slot + i], mds[i * 14 + j]));
-                    b[q_of[i]] = add(b[q_of[i]], mul(h.beta[slot + i], mds[i * 14 + j]));
-                }
-                R.a_fwd[use][j] = neg(a);
-                for (unsigned q = 0; q < ng; q++) R.b_fwd[use][q][j] = neg(b[q]);
-            }
-        }
-    }
-}
+void fill_rescue_tables(int air_id, ConsArgs &h) { airs::fill_rescue_tables(air_id, h.alpha, h.beta, h.group, h.nconstraints, h.rt); }
 
 size_t constraint_scratch_elements(int air_id, size_t n, size_t ncosets) {
     size_t items = 0;

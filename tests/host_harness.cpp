@@ -67,6 +67,21 @@ static void check_eval(const csg::AirDesc &d, air_t *o) {
         fe t = S.sum.reduce();
         for (size_t g = 0; g < tg.adj.size(); g++) t = f63::add(t, f63::mul(xp[g], S.part_value((int)g)));
         CHECK(t == expect, "air %d rep %d: split evaluation differs from the oracle", AIR, rep);
+        // the device form of the Rescue constraints: forward MDS product folded into per-proof coefficient tables
+        // (rescue_tables.h; on the host only when tables are supplied), combined and split
+        airs::RescueTables RT;
+        airs::fill_rescue_tables(AIR, alpha.data(), beta.data(), tg.group_of.data(), (unsigned)nc, RT);
+        airs::Comb C2{alpha.data(), beta.data(), tg.group_of.data(), xp.data(), 1, f63::acc192(), nullptr, 0};
+        C2.rt = &RT;
+        airs::eval_transition<AIR>(f, P, C2);
+        CHECK(C2.sum.reduce() == expect, "air %d rep %d: evaluation through the Rescue tables differs from the oracle", AIR, rep);
+        std::vector<uint64_t> parts2(3 * airs::MAX_SPLIT_GROUPS, 0);
+        airs::SplitComb S2{alpha.data(), beta.data(), tg.group_of.data(), nullptr, 0, f63::acc192(), parts2.data(), 1};
+        S2.rt = &RT;
+        airs::eval_transition<AIR>(f, P, S2);
+        fe t2 = S2.sum.reduce();
+        for (size_t g = 0; g < tg.adj.size(); g++) t2 = f63::add(t2, f63::mul(xp[g], S2.part_value((int)g)));
+        CHECK(t2 == expect, "air %d rep %d: split evaluation through the Rescue tables differs from the oracle", AIR, rep);
     }
 }
 
