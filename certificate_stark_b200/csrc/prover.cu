@@ -1120,6 +1120,11 @@ long long csg_debug_redc_selftest(csg_ctx *ctx) {
     guarded(ctx, [&] { bad = redc_selftest(ctx->st); });
     return bad;
 }
+long long csg_debug_field_selftest(csg_ctx *ctx) {
+    long long bad = -1;
+    guarded(ctx, [&] { bad = field_selftest(ctx->st); });
+    return bad;
+}
 long long csg_debug_count_unreduced(csg_ctx *ctx, int which) {
     long long bad = -1;
     guarded(ctx, [&] {

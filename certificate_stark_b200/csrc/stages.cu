@@ -1,6 +1,7 @@
 // See stages.cuh.
 #include <vector>
 
+#include "field_selfcheck.cuh"
 #include "stages.cuh"
 
 namespace csg {
@@ -217,7 +218,23 @@ __global__ void redc_selftest_kernel(unsigned long long *bad, unsigned long long
     if (nb) atomicAdd(bad, nb);
 }
 
+__global__ void field_selfcheck_kernel(unsigned long long *bad, unsigned long long seed) {
+    const unsigned long long nb = field_selfcheck(seed + (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 0x9e3779b97f4a7c15ULL, 64);
+    if (nb) atomicAdd(bad, nb);
+}
+
 }  // namespace
+
+long long field_selftest(Stream &st) {
+    unsigned long long *d, h = 0;
+    CSG_CUDA(cudaMalloc((void **)&d, 8));
+    CSG_CUDA(cudaMemsetAsync(d, 0, 8, st.s));
+    CSG_LAUNCH(st, field_selfcheck_kernel, 256, 128, 0, d, 0x5eedULL);
+    CSG_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, st.s));
+    CSG_CUDA(cudaStreamSynchronize(st.s));
+    cudaFree(d);
+    return (long long)h;
+}
 
 long long redc_selftest(Stream &st) {
     unsigned long long *d, h = 0;

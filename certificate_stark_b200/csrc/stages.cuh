@@ -63,5 +63,6 @@ void coset_major_to_natural(const fe *lde, unsigned width, unsigned ncosets, siz
 // arithmetic self-test on the device: number of (random and edge-case) inputs on which the fast Montgomery reduction
 // disagrees with the textbook one; must be 0
 long long redc_selftest(Stream &st);
+long long field_selftest(Stream &st);   // field_selfcheck.cuh on 32768 threads: mismatches (0 = pass)
 
 }  // namespace csg

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../certificate_stark_b200/csrc/airs.cuh"
+#include "../certificate_stark_b200/csrc/field_selfcheck.cuh"
 #include "../certificate_stark_b200/csrc/host/air_desc.hpp"
 #include "../certificate_stark_b200/csrc/host/transcript.hpp"
 
@@ -152,6 +153,12 @@ static void check_batch_openings() {
 }
 
 int main() {
+    // the field self-check the device runs (csg_debug_field_selftest), on the host forms of the same arithmetic: pins the
+    // checker, so that a mismatch on the device is a device bug
+    for (uint64_t seed = 0; seed < 512; seed++) {
+        unsigned long long bad = f63::field_selfcheck(0x5eedULL + seed * 0x9e3779b97f4a7c15ULL, 64);
+        CHECK(bad == 0, "field self-check: %llu mismatches for seed %llu", bad, (unsigned long long)seed);
+    }
     check_air(0, 2048);
     check_air(1, 1024);
     check_air(2, 16);

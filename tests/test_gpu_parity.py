@@ -193,6 +193,15 @@ def test_errors_are_reported_not_swallowed(ctx, csg):
         ctx.prove(csg.AIR_TRANSACTION, t, p, csg.ProofOptions(blowup_factor=4))
 
 
+def test_device_field_arithmetic_selftest(ctx, csg):
+    # the fused modular multiplication and the column-form accumulators (field.cuh) against mul_wide + the textbook reduction +
+    # modular additions, on random operands and carry-path patterns; the same checker runs on the host in tests/host_harness.cpp
+    import ctypes as C
+    L = csg.lib()
+    L.csg_debug_field_selftest.restype, L.csg_debug_field_selftest.argtypes = C.c_longlong, [C.c_void_p]
+    assert L.csg_debug_field_selftest(ctx._h) == 0
+
+
 def test_device_montgomery_reduction_selftest(ctx, csg):
     # the 32-bit word-serial reduction used by every kernel against the textbook 64-bit one, on random and edge operands
     import ctypes as C
