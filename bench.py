@@ -66,6 +66,22 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def stage_roofline(stage_ms, n, hbm_peak):
+    """HBM view of the transform and commitment stages (BASELINE.json: "LDE/hash HBM GB/s"): the algorithmic bytes of
+    SURVEY.md section 8(d) -- K1 iNTT 16 n and K2 coset LDE 8 n + 8 b n per column; K3 row hashing 8 w + 32 per LDE row and
+    K4 Merkle tree 32 L + 32 (L - 1) -- divided by the stage's CUDA-event time.  Both stages are integer-pipe-bound
+    (profiles/README.md); the fractions say how far from the HBM roofline that leaves them."""
+    rows = n * BLOWUP
+    algorithmic = {"lde": TRACE_WIDTH * n * (16 + 8 + 8 * BLOWUP), "commit_trace": rows * (8 * TRACE_WIDTH + 32) + 32 * (2 * rows - 1)}
+    out = {}
+    for k, nbytes in algorithmic.items():
+        ms = stage_ms.get(k) or 0.0
+        gbs = nbytes / (ms / 1e3) / 1e9 if ms > 0 else None
+        out[k] = {"algorithmic_bytes": int(nbytes), "ms": ms, "achieved": gbs, "unit": "GB/s", "peak": hbm_peak,
+                  "frac": gbs / hbm_peak if gbs and hbm_peak else None}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons sampled DURING the timed region"""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -339,9 +355,13 @@ def main():
                          "peak_source": peak_src, "traffic": TRAFFIC.get(top), "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": top_ms,
                          "constraint_stage": {"ms": cons_ms, "kernels": kernels,
                                               "reference_modmul_per_s": rows * MODMUL_PER_ROW / (cons_ms / 1e3) if cons_ms > 0 else None},
-                         "note": "64-bit modular multiply has no native instruction (about 30 integer instructions): every arithmetic kernel of this path is "
+                         "note": "64-bit modular multiply has no native instruction (22 integer instructions, 5-6 per term of a lazily reduced sum): every arithmetic kernel of this path is "
                                  "integer-pipe-bound, not HBM-bound; profiles/README.md has the ALU/FMA pipe utilisation from ncu"},
         }
+        try:
+            line["stage_roofline"] = stage_roofline(line["stage_ms"], n, hbm_peak)
+        except Exception as e:   # a reporting extra: never lets the bench line go missing
+            line["stage_roofline"] = {"error": repr(e)}
         if sh_ms:
             line["sharded_proof"] = {
                 "note": f"ONE proof of the same {num_tx}-transaction batch split over the {world} GPUs by LDE coset (each GPU owns {BLOWUP // world} of the "

@@ -114,3 +114,14 @@ def test_product_verifier_accepts_valid_and_rejects_invalid_proofs(csg, oracle):
             assert csg.verify(air, pub, bytes(bad)) != 0, f"air {air}: flipped bit at {where} accepted"
         assert csg.verify(air, pub, proof[:-1]) == 16 and csg.verify(air, pub, proof + b"\0") == 16
         assert csg.verify((air + 1) % 6, pub, proof) != 0
+
+
+def test_bench_stage_roofline_arithmetic():
+    # bench.py's HBM view of the LDE and commitment stages: SURVEY.md 8(d) bytes / stage time, on the round-1 stage times
+    import bench
+    n = 1 << 20
+    r = bench.stage_roofline({"lde": 18.94, "commit_trace": 4.38}, n, 6544.0)
+    assert r["lde"]["algorithmic_bytes"] == 94 * n * 88 and r["commit_trace"]["algorithmic_bytes"] == (8 * n) * 784 + 32 * (16 * n - 1)
+    assert abs(r["lde"]["achieved"] - 94 * n * 88 / 18.94e-3 / 1e9) < 1e-6 and 0.06 < r["lde"]["frac"] < 0.08
+    assert 0.2 < r["commit_trace"]["frac"] < 0.3
+    assert bench.stage_roofline({}, n, 6544.0)["lde"]["achieved"] is None   # a missing stage does not raise
