@@ -22,6 +22,7 @@ P = 0x4180000000000001  # f63 modulus (/root/reference/src/range/tests.rs:59)
 AIR_TRANSACTION, AIR_MERKLE_UPDATE, AIR_MERKLE_INIT, AIR_SCHNORR, AIR_RANGE, AIR_RESCUE = range(6)
 HASH_BLAKE3_256, HASH_SHA3_256 = 2, 3
 FIELD_EXTENSION_NONE, FIELD_EXTENSION_QUADRATIC, FIELD_EXTENSION_CUBIC = 1, 2, 3
+REPR_CANONICAL, REPR_MONTGOMERY = 0, 1   # csg.h: representation of the trace words crossing the boundary
 TRACE_WIDTH = {AIR_TRANSACTION: 94, AIR_MERKLE_UPDATE: 65, AIR_MERKLE_INIT: 58, AIR_SCHNORR: 56, AIR_RANGE: 2, AIR_RESCUE: 14}
 _ERRORS = {1: "invalid argument", 2: "CUDA error", 3: "call out of order", 4: "unsupported", 5: "random coin failure"}
 
@@ -77,11 +78,13 @@ def lib() -> C.CDLL:
     vp, opt = C.c_void_p, C.POINTER(ProofOptions)
     sig = {
         "csg_create": (vp, [C.c_int]), "csg_destroy": (None, [vp]), "csg_last_error": (C.c_char_p, [vp]), "csg_free": (None, [vp]),
-        "csg_prove": (C.c_int, [vp, C.c_int, _u64p, C.c_size_t, _u64p, C.c_size_t, opt, C.POINTER(_u8p), _szp]),
+        "csg_prove": (C.c_int, [vp, C.c_int, _u64p, C.c_int, C.c_size_t, _u64p, C.c_size_t, opt, C.POINTER(_u8p), _szp]),
         "csg_set_air": (C.c_int, [vp, C.c_int, C.c_size_t, opt, _u64p, C.c_size_t]),
-        "csg_load_trace": (C.c_int, [vp, _u64p]), "csg_reload_resident_trace": (C.c_int, [vp]),
+        "csg_load_trace": (C.c_int, [vp, _u64p, C.c_int]), "csg_reload_resident_trace": (C.c_int, [vp]),
         "csg_prove_loaded": (C.c_int, [vp, C.POINTER(_u8p), _szp]),
-        "csg_prove_trace": (C.c_int, [vp, _u64p, C.POINTER(_u8p), _szp]),
+        "csg_prove_trace": (C.c_int, [vp, _u64p, C.c_int, C.POINTER(_u8p), _szp]),
+        "csg_host_alloc": (vp, [C.c_size_t]), "csg_host_free": (None, [vp]), "csg_host_register": (C.c_int, [vp, C.c_size_t]),
+        "csg_host_unregister": (C.c_int, [vp]),
         "csg_extend_and_commit_trace": (C.c_int, [vp, _u8p]), "csg_eval_constraints": (C.c_int, [vp, _u64p, _u64p]),
         "csg_commit_composition": (C.c_int, [vp, _u8p]), "csg_ood": (C.c_int, [vp, C.c_uint64, _u64p, _u64p, _u64p]),
         "csg_deep": (C.c_int, [vp, _u64p, _u64p, _u64p]), "csg_fri_commit_layer": (C.c_int, [vp, _u8p]),
@@ -91,6 +94,7 @@ def lib() -> C.CDLL:
         "csg_open_composition": (C.c_int, [vp, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
         "csg_open_fri_layer": (C.c_int, [vp, C.c_size_t, _u64p, C.c_size_t, _u64p, _u8p, C.c_size_t, _szp]),
         "csg_verify": (C.c_int, [C.c_int, _u64p, C.c_size_t, _u8p, C.c_size_t]),
+        "csg_verify_with_options": (C.c_int, [C.c_int, _u64p, C.c_size_t, _u8p, C.c_size_t, opt]),
         "csg_get_timings": (C.c_int, [vp, C.POINTER(Timings)]),
         "csg_dist_unique_id": (C.c_int, [_u8p]), "csg_dist_init": (C.c_int, [vp, C.c_int, C.c_int, _u8p]),
         "csg_dist_plan": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ShardPlan)]),
@@ -127,13 +131,17 @@ def _p8(a):
 
 
 VERIFY_ERRORS = {16: "malformed proof", 17: "inconsistent out-of-domain constraint evaluations", 18: "proof of work check failed",
-                 19: "trace query does not match the commitment", 20: "constraint query does not match the commitment", 21: "FRI verification failed"}
+                 19: "trace query does not match the commitment", 20: "constraint query does not match the commitment", 21: "FRI verification failed",
+                 22: "proof options weaker than the verifier's"}
 
 
-def verify(air_id: int, pub: np.ndarray, proof: bytes) -> int:
-    """winterfell::verify::<Air>(proof, pub_inputs): 0 when the proof is accepted, else a key of VERIFY_ERRORS.  Host-only."""
+def verify(air_id: int, pub: np.ndarray, proof: bytes, min_options: "ProofOptions | None" = None) -> int:
+    """winterfell::verify::<Air>(proof, pub_inputs): 0 when the proof is accepted, else a key of VERIFY_ERRORS.  Host-only.
+    With min_options the proof's own ProofOptions must be at least as strong (csg_verify_with_options)."""
     pub = np.ascontiguousarray(pub, dtype=np.uint64)
     buf = np.frombuffer(proof, dtype=np.uint8)
+    if min_options is not None:
+        return lib().csg_verify_with_options(air_id, _p64(pub), pub.size, _p8(buf), buf.size, C.byref(min_options))
     return lib().csg_verify(air_id, _p64(pub), pub.size, _p8(buf), buf.size)
 
 
@@ -197,14 +205,14 @@ class Context:
         return r.value, w.value
 
     # ---- level 1: Prover::prove(trace)
-    def prove(self, air_id: int, trace: np.ndarray, pub: np.ndarray, options: ProofOptions) -> bytes:
-        """trace: (width, n) canonical uint64 column-major table (TraceTable's layout) in HOST memory -> StarkProof bytes."""
+    def prove(self, air_id: int, trace: np.ndarray, pub: np.ndarray, options: ProofOptions, repr: int = REPR_CANONICAL) -> bytes:
+        """trace: (width, n) uint64 column-major table (TraceTable's layout) in HOST memory -> StarkProof bytes."""
         trace = np.ascontiguousarray(trace, dtype=np.uint64)
         pub = np.ascontiguousarray(pub, dtype=np.uint64)
         if trace.ndim != 2 or trace.shape[0] != TRACE_WIDTH[air_id]:
             raise CsgError(f"trace must be ({TRACE_WIDTH[air_id]}, n)")
         out, n = _u8p(), C.c_size_t()
-        self._check(lib().csg_prove(self._h, air_id, _p64(trace), trace.shape[1], _p64(pub), pub.size, C.byref(options), C.byref(out), C.byref(n)))
+        self._check(lib().csg_prove(self._h, air_id, _p64(trace), repr, trace.shape[1], _p64(pub), pub.size, C.byref(options), C.byref(out), C.byref(n)))
         return self._take_proof(out, n)
 
     # ---- level 2 pieces used by benchmarks: trace resident in HBM, proved repeatedly
@@ -212,18 +220,19 @@ class Context:
         pub = np.ascontiguousarray(pub, dtype=np.uint64)
         self._check(lib().csg_set_air(self._h, air_id, trace_len, C.byref(options), _p64(pub), pub.size))
 
-    def load_trace(self, trace):
+    def load_trace(self, trace, repr: int = REPR_CANONICAL):
         trace = np.ascontiguousarray(trace, dtype=np.uint64)
-        self._check(lib().csg_load_trace(self._h, _p64(trace)))
+        self._check(lib().csg_load_trace(self._h, _p64(trace), repr))
 
-    def load_trace_ptr(self, host_ptr: int):
-        """same, from a raw host pointer (e.g. a pinned torch tensor's data_ptr())"""
-        self._check(lib().csg_load_trace(self._h, C.cast(host_ptr, _u64p)))
+    def load_trace_ptr(self, host_ptr: int, repr: int = REPR_CANONICAL):
+        """same, from a raw host pointer (e.g. a HostBuffer's ptr)"""
+        self._check(lib().csg_load_trace(self._h, C.cast(host_ptr, _u64p), repr))
 
-    def prove_trace_ptr(self, host_ptr: int) -> bytes:
-        """proof of the trace at a raw HOST pointer (pinned memory makes the copy overlap the extension) for the AIR already set"""
+    def prove_trace_ptr(self, host_ptr: int, repr: int = REPR_CANONICAL) -> bytes:
+        """proof of the trace at a raw HOST pointer for the AIR already set: pinned memory (HostBuffer) is copied at link speed
+        under the extension, pageable memory is staged through the library's own pinned buffers"""
         out, n = _u8p(), C.c_size_t()
-        self._check(lib().csg_prove_trace(self._h, C.cast(host_ptr, _u64p), C.byref(out), C.byref(n)))
+        self._check(lib().csg_prove_trace(self._h, C.cast(host_ptr, _u64p), repr, C.byref(out), C.byref(n)))
         return self._take_proof(out, n)
 
     def reload_resident_trace(self):
@@ -287,6 +296,26 @@ class Context:
         ms = (C.c_float * 4)()
         self._check(lib().csg_k_sweep(self._h, width, n, blowup, hash_fn, iters, ms))
         return dict(zip(("lde_ms", "hash_rows_ms", "merkle_ms", "fri_fold_ms"), [float(v) for v in ms]))
+
+
+class HostBuffer:
+    """page-locked host memory from csg_host_alloc, viewed as a (width, n) uint64 array: where a caller builds a trace it is
+    going to prove more than once or wants copied at link speed"""
+
+    def __init__(self, width: int, n: int):
+        self.nbytes = width * n * 8
+        self.ptr = lib().csg_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise CsgError("csg_host_alloc failed (no CUDA device, or out of page-locked memory)")
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, _u64p), shape=(width, n))
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().csg_host_free(self.ptr)
+            self.ptr = None
+
+    __del__ = close
 
 
 def dist_plan(rank: int, world: int, blowup: int, ce_blowup: int, width: int) -> ShardPlan:
@@ -460,13 +489,13 @@ class TransactionExample:
 
     def verify(self, proof: bytes) -> bool:
         """TransactionExample::verify (src/lib.rs:144-150)"""
-        return verify(AIR_TRANSACTION, self.batch.public_inputs(), proof) == 0
+        return verify(AIR_TRANSACTION, self.batch.public_inputs(), proof, self.options) == 0
 
     def verify_with_wrong_inputs(self, proof: bytes) -> bool:
         """TransactionExample::verify_with_wrong_inputs (src/lib.rs:152-161): every limb of the final root replaced by its first"""
         pub = self.batch.public_inputs()
         pub[7:] = pub[7]
-        return verify(AIR_TRANSACTION, pub, proof) == 0
+        return verify(AIR_TRANSACTION, pub, proof, self.options) == 0
 
     def prove(self, witness_on_device: bool = True) -> bytes:
         if not witness_on_device:

@@ -197,20 +197,35 @@ bool merged_at_ext_frame(int air_id, const AirDesc &air, const TransitionGroups 
     return true;
 }
 
-int verify_impl(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len) {
+int verify_impl(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len, const csg_options *min_opt) {
     Reader R{proof, proof_len};
     const uint32_t w = (uint32_t)R.uint(1); const unsigned logn = (unsigned)R.uint(1);
-    R.take(R.uint(2));
+    // trace meta: the reference's provers attach none; a non-empty blob would be bytes bound to nothing (proof malleability)
+    if (R.uint(2) != 0) return CSG_VERIFY_MALFORMED;
     const size_t modlen = R.uint(1); const uint8_t *mod = R.take(modlen);
     csg_options o;
-    o.num_queries = (uint32_t)R.uint(1); o.blowup_factor = 1u << R.uint(1); o.grinding_factor = (uint32_t)R.uint(1);
+    o.num_queries = (uint32_t)R.uint(1);
+    const size_t log_blowup = R.uint(1);
+    o.grinding_factor = (uint32_t)R.uint(1);
     o.hash_fn = (uint32_t)R.uint(1); o.field_extension = (uint32_t)R.uint(1);
-    o.fri_folding_factor = 1u << R.uint(1); o.fri_max_remainder_size = 1u << R.uint(1);
-    if (R.bad || modlen != 8 || logn < 3 || logn > 40) return CSG_VERIFY_MALFORMED;
-    { uint64_t m; memcpy(&m, mod, 8); if (m != P) return CSG_VERIFY_MALFORMED; }
-    if (o.field_extension < CSG_FIELD_EXT_NONE || o.field_extension > CSG_FIELD_EXT_CUBIC || o.fri_folding_factor != 4 ||
-        (o.hash_fn != CSG_HASH_BLAKE3_256 && o.hash_fn != CSG_HASH_SHA3_256) || o.num_queries == 0 || o.blowup_factor < 2 || o.fri_max_remainder_size < 4)
+    const size_t log_folding = R.uint(1), log_remainder = R.uint(1);
+    const size_t context_len = R.off;     // the exact context bytes seed the coin below
+    // the same ranges the prover enforces (prover.cu set_air): blowup 2..32, folding 4, remainder 4..1024, grinding below 32;
+    // checked on the log2 bytes BEFORE shifting (a byte >= 32 would be undefined behaviour / wrap to a small value)
+    if (R.bad || modlen != 8 || logn < 3 || logn > 40 || log_blowup < 1 || log_blowup > 5 || log_folding != 2 || log_remainder < 2 || log_remainder > 10 ||
+        o.grinding_factor >= 32)
         return CSG_VERIFY_MALFORMED;
+    o.blowup_factor = 1u << log_blowup; o.fri_folding_factor = 1u << log_folding; o.fri_max_remainder_size = 1u << log_remainder;
+    { uint64_t m; memcpy(&m, mod, 8); if (m != P) return CSG_VERIFY_MALFORMED; }
+    if (o.field_extension < CSG_FIELD_EXT_NONE || o.field_extension > CSG_FIELD_EXT_CUBIC ||
+        (o.hash_fn != CSG_HASH_BLAKE3_256 && o.hash_fn != CSG_HASH_SHA3_256) || o.num_queries == 0)
+        return CSG_VERIFY_MALFORMED;
+    // acceptance policy of the caller: a proof whose own context is weaker than what the verifier expects is rejected, whatever
+    // it proves (winterfell v0.3's verify() trusts the context inside the proof; an acceptance check must not)
+    if (min_opt && (o.num_queries < min_opt->num_queries || o.blowup_factor < min_opt->blowup_factor || o.grinding_factor < min_opt->grinding_factor ||
+                    o.hash_fn != min_opt->hash_fn || o.field_extension < min_opt->field_extension || o.fri_folding_factor != min_opt->fri_folding_factor ||
+                    o.fri_max_remainder_size > min_opt->fri_max_remainder_size))
+        return CSG_VERIFY_WEAK_OPTIONS;
     const int d = (int)o.field_extension;
     const ExtConsts xk = d > 1 ? ext_consts() : ExtConsts{};
     const size_t n = (size_t)1 << logn, b = o.blowup_factor, lde_n = n * b, nq = o.num_queries;
@@ -220,7 +235,9 @@ int verify_impl(int air_id, const uint64_t *pub, size_t npub, const uint8_t *pro
     if (air.width != w) return CSG_VERIFY_MALFORMED;
     const size_t ce = air.ce_blowup(), nc = air.num_constraints(), na = air.assertions.size();
     if (ce > b) return CSG_VERIFY_MALFORMED;
-    size_t nfolds = 0; for (size_t dm = lde_n; dm > o.fri_max_remainder_size; dm /= 4) nfolds++;
+    size_t nfolds = 0, final_domain = lde_n;
+    for (; final_domain > o.fri_max_remainder_size; final_domain /= 4) nfolds++;
+    if (final_domain < 8) return CSG_VERIFY_MALFORMED;   // the remainder is committed as rows of 4: the prover refuses fewer than 2 rows
     const size_t nlayers = nfolds + 1;
 
     const size_t clen = R.uint(2); const uint8_t *commits = R.take(clen);
@@ -245,9 +262,7 @@ int verify_impl(int air_id, const uint64_t *pub, size_t npub, const uint8_t *pro
     // transcript
     Bytes seed;
     for (size_t i = 0; i < npub; i++) seed.u64(pub[i]);
-    seed.u8((uint8_t)w); seed.u8((uint8_t)logn); seed.u16(0); seed.u8(8); seed.u64(P);
-    seed.u8((uint8_t)o.num_queries); seed.u8((uint8_t)ilog2_host(b)); seed.u8((uint8_t)o.grinding_factor); seed.u8((uint8_t)o.hash_fn);
-    seed.u8((uint8_t)o.field_extension); seed.u8(2); seed.u8((uint8_t)ilog2_host(o.fri_max_remainder_size));
+    seed.put(proof, context_len);
     try {
         Coin coin(hf, seed.v.data(), seed.v.size());
         coin.reseed(commits);
@@ -403,5 +418,9 @@ int verify_impl(int air_id, const uint64_t *pub, size_t npub, const uint8_t *pro
 
 extern "C" int csg_verify(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len) {
     if (!pub || !proof) return CSG_VERIFY_MALFORMED;
-    return csg::verify_impl(air_id, pub, npub, proof, proof_len);
+    return csg::verify_impl(air_id, pub, npub, proof, proof_len, nullptr);
+}
+extern "C" int csg_verify_with_options(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len, const csg_options *min_options) {
+    if (!pub || !proof || !min_options) return CSG_VERIFY_MALFORMED;
+    return csg::verify_impl(air_id, pub, npub, proof, proof_len, min_options);
 }

@@ -5,6 +5,7 @@
 // -> DEEP composition -> FRI -> queries, with every bulk stage on the GPU and only the Fiat-Shamir transcript, proof
 // serialisation and a few hundred field operations per proof on the host.  Device data stays in Montgomery form and in
 // coset-major order (ntt.cuh) from the moment the trace is loaded until rows are opened.
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -129,6 +130,15 @@ struct csg_ctx {
     bool split_low_degree = getenv("CSG_NO_SPLIT") == nullptr;   // CSG_NO_SPLIT=1: evaluate every constraint on every coset (A/B testing)
     cudaStream_t copy_stream = nullptr;          // H2D copies of trace column chunks, overlapped with their extension
     std::vector<cudaEvent_t> chunk_ev;
+    int trace_repr = CSG_REPR_CANONICAL;         // representation of the words in d_io (csg_load_trace / csg_prove_trace)
+    // a trace in PAGEABLE host memory (a Rust Vec<u64>) is staged through a small ring of pinned buffers by the host threads:
+    // cudaMemcpyAsync from pageable memory is a synchronous, single-threaded bounce copy inside the driver
+    enum { STAGE_BUFS = 3 };
+    uint64_t *stage_buf[STAGE_BUFS] = {nullptr, nullptr, nullptr};
+    size_t stage_words = 0;
+    cudaEvent_t stage_ev[STAGE_BUFS] = {nullptr, nullptr, nullptr};
+    float h2d_ms_last = 0;
+    cudaEvent_t h2d_a = nullptr, h2d_b = nullptr;   // first byte .. last byte of the overlapped H2D copy, on the copy stream
     CosetTables lde_tables;                      // per-coset scale tables of the LDE domain, built once per csg_set_air
 
     // ------------------------------------------------------------------------------------------ setup
@@ -139,7 +149,9 @@ struct csg_ctx {
         if (o->hash_fn != CSG_HASH_BLAKE3_256 && o->hash_fn != CSG_HASH_SHA3_256) throw ArgError("hash function must be Blake3_256 or Sha3_256");
         if (o->num_queries == 0 || o->num_queries > 255 || o->grinding_factor >= 32) throw ArgError("num_queries in 1..255, grinding factor below 32");
         if (o->blowup_factor < 2 || o->blowup_factor > 32 || (o->blowup_factor & (o->blowup_factor - 1))) throw ArgError("blowup factor must be a power of two in 2..32");
-        if (o->fri_max_remainder_size < 4 || (o->fri_max_remainder_size & (o->fri_max_remainder_size - 1))) throw ArgError("FRI remainder size must be a power of two");
+        // winterfell caps the remainder at 1024 elements; its byte length is serialised as a u16 (8192 elements would wrap to 0)
+        if (o->fri_max_remainder_size < 4 || o->fri_max_remainder_size > 1024 || (o->fri_max_remainder_size & (o->fri_max_remainder_size - 1)))
+            throw ArgError("FRI remainder size must be a power of two in 4..1024");
         try { air = make_air(air_id, trace_len, pub, npub); } catch (const std::invalid_argument &e) { throw ArgError(e.what()); }
         opt = *o;
         d = (int)o->field_extension;
@@ -215,8 +227,16 @@ struct csg_ctx {
         }
     }
 
-    void load_trace(const uint64_t *trace) {
+    static void check_repr(int repr) { if (repr != CSG_REPR_CANONICAL && repr != CSG_REPR_MONTGOMERY) throw ArgError("repr must be CSG_REPR_CANONICAL or CSG_REPR_MONTGOMERY"); }
+    static bool is_pageable(const void *p) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+        return a.type == cudaMemoryTypeUnregistered;
+    }
+    void load_trace(const uint64_t *trace, int repr) {
         need(S_AIR, "csg_set_air must be called first");
+        check_repr(repr);
+        trace_repr = repr;
         const size_t count = (size_t)air.width * n;
         Timer &t = stage_timer;
         t.start(st);
@@ -244,7 +264,8 @@ struct csg_ctx {
     // Stage 1 runs column chunk by column chunk: representation change, interpolation and the `blowup` coset transforms of
     // a chunk need nothing from the other columns, so when the trace still lives in host memory (csg_prove) the H2D copy
     // of chunk c+1 overlaps the extension of chunk c.  host == nullptr: the canonical trace is already in d_io.
-    void extend_and_commit_trace(uint8_t root[32], const uint64_t *host = nullptr) {
+    void extend_and_commit_trace(uint8_t root[32], const uint64_t *host = nullptr, int host_repr = CSG_REPR_CANONICAL) {
+        if (host) { check_repr(host_repr); trace_repr = host_repr; }
         if (!host) need(S_TRACE, "csg_load_trace must be called first");
         else need(S_AIR, "csg_set_air must be called first");
         const size_t w = air.width;
@@ -257,22 +278,45 @@ struct csg_ctx {
         Timer &t = stage_timer;
         t.start(st);
         d_io.reserve(w * n); d_polys.reserve(wpad * n); scratch.reserve(wpad * n); d_lde.reserve(w * n * bl);
+        const bool staged = host && is_pageable(host);
         if (host) {
             if (!copy_stream) CSG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
             while (chunk_ev.size() < (cpr + CHUNK - 1) / CHUNK + 1) { cudaEvent_t e; CSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); chunk_ev.push_back(e); }
+            if (!h2d_a) { CSG_CUDA(cudaEventCreate(&h2d_a)); CSG_CUDA(cudaEventCreate(&h2d_b)); }
+            if (staged && stage_words < CHUNK * n) {
+                for (auto &b : stage_buf) { if (b) cudaFreeHost(b); b = nullptr; }
+                for (auto &b : stage_buf) CSG_CUDA(cudaHostAlloc((void **)&b, CHUNK * n * sizeof(uint64_t), cudaHostAllocDefault));
+                stage_words = CHUNK * n;
+                for (auto &e : stage_ev) if (!e) CSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
             // the copies must not overtake earlier work on the proving stream that still reads d_io
             CSG_CUDA(cudaEventRecord(chunk_ev[0], st.s));
             CSG_CUDA(cudaStreamWaitEvent(copy_stream, chunk_ev[0], 0));
-            for (size_t c0 = c_lo, k = 0; c0 < c_hi; c0 += CHUNK, k++) {
-                const size_t nc = std::min(CHUNK, c_hi - c0);
-                CSG_CUDA(cudaMemcpyAsync(d_io.p + c0 * n, host + c0 * n, nc * n * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
-                CSG_CUDA(cudaEventRecord(chunk_ev[k], copy_stream));
-            }
+            CSG_CUDA(cudaEventRecord(h2d_a, copy_stream));
         }
         for (size_t c0 = c_lo, k = 0; c0 < c_hi; c0 += CHUNK, k++) {
             const size_t nc = std::min(CHUNK, c_hi - c0);
-            if (host) CSG_CUDA(cudaStreamWaitEvent(st.s, chunk_ev[k], 0));
-            to_montgomery(d_io.p + c0 * n, d_polys.p + c0 * n, nc * n, st);
+            if (host) {
+                const uint64_t *src = host + c0 * n;
+                if (staged) {   // host threads fill a pinned buffer while the GPU extends the previous chunks
+                    uint64_t *buf = stage_buf[k % STAGE_BUFS];
+                    if (k >= STAGE_BUFS) CSG_CUDA(cudaEventSynchronize(stage_ev[k % STAGE_BUFS]));
+                    const size_t words = nc * n, SL = (size_t)1 << 17;   // 1 MB slices
+                    const long long nsl = (long long)((words + SL - 1) / SL);
+#pragma omp parallel for schedule(static)
+                    for (long long sl = 0; sl < nsl; sl++) {
+                        const size_t o = (size_t)sl * SL;
+                        memcpy(buf + o, src + o, std::min(SL, words - o) * sizeof(uint64_t));
+                    }
+                    src = buf;
+                }
+                CSG_CUDA(cudaMemcpyAsync(d_io.p + c0 * n, src, nc * n * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
+                if (staged) CSG_CUDA(cudaEventRecord(stage_ev[k % STAGE_BUFS], copy_stream));
+                CSG_CUDA(cudaEventRecord(chunk_ev[k], copy_stream));
+                if (c0 + CHUNK >= c_hi) CSG_CUDA(cudaEventRecord(h2d_b, copy_stream));
+                CSG_CUDA(cudaStreamWaitEvent(st.s, chunk_ev[k], 0));
+            }
+            to_montgomery(d_io.p + c0 * n, d_polys.p + c0 * n, nc * n, st, trace_repr == CSG_REPR_MONTGOMERY);
             intt_columns(roots, ntt, d_polys.p + c0 * n, n, scratch.p + c0 * n, n, nc, logn, st);
             if (G == 1) coset_ntt_columns(roots, ntt, scratch.p + c0 * n, n, d_lde.p + c0 * n, n, w * n, nc, logn, lde_tables, st);
         }
@@ -291,8 +335,11 @@ struct csg_ctx {
             if (c_hi < w) coset_ntt_columns(roots, ntt, scratch.p + c_hi * n, n, d_lde.p + c_hi * n, n, w * n, w - c_hi, logn, lde_tables, st);
         }
         std::swap(d_polys.p, scratch.p); std::swap(d_polys.n, scratch.n);   // d_polys = coefficients
-        if (host) { nfri = 0; tm.h2d = 0; }
         tm.lde = t.stop(st);
+        if (host) {   // the copy ran under the extension: its own duration (first byte .. last byte), not time added to the proof
+            nfri = 0; tm.h2d = 0;
+            if (c_hi > c_lo) { CSG_CUDA(cudaEventSynchronize(h2d_b)); CSG_CUDA(cudaEventElapsedTime(&tm.h2d, h2d_a, h2d_b)); }
+        }
         t.start(st);
         commit_rows(d_lde.p, (unsigned)w, w * n, d_tnodes);
         download_root(d_tnodes, root);
@@ -750,7 +797,7 @@ struct csg_ctx {
         for (const xe &e : v) for (int j = 0; j < d; j++) out.push_back(e.c[j]);
         return out;
     }
-    void prove_loaded(uint8_t **proof, size_t *proof_len, const uint64_t *host = nullptr) {
+    void prove_loaded(uint8_t **proof, size_t *proof_len, const uint64_t *host = nullptr, int host_repr = CSG_REPR_CANONICAL) {
         if (!host) need(S_TRACE, "csg_load_trace must be called first");
         auto t0 = std::chrono::steady_clock::now();
         const unsigned long long launches0 = st.launches;
@@ -764,7 +811,7 @@ struct csg_ctx {
         auto base = [](const std::vector<xe> &v) { std::vector<fe> o; for (const xe &e : v) o.push_back(e.c[0]); return o; };
 
         uint8_t trace_root[32], comp_root[32];
-        extend_and_commit_trace(trace_root, host);
+        extend_and_commit_trace(trace_root, host, host_repr);
         coin.reseed(trace_root);
         std::vector<xe> t_ab(2 * nc), b_ab(2 * na + 2, x_zero());
         for (size_t i = 0; i < 2 * nc; i++) t_ab[i] = coin.draw_x(d);
@@ -988,6 +1035,9 @@ void csg_destroy(csg_ctx *ctx) {
     if (ctx->comm_stream.s) { cudaStreamSynchronize(ctx->comm_stream.s); cudaStreamDestroy(ctx->comm_stream.s); }
     ctx->comm.reset();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto b : ctx->stage_buf) if (b) cudaFreeHost(b);
+    for (auto e : ctx->stage_ev) if (e) cudaEventDestroy(e);
+    if (ctx->h2d_a) { cudaEventDestroy(ctx->h2d_a); cudaEventDestroy(ctx->h2d_b); }
     delete ctx;
     cudaStreamDestroy(s);
 }
@@ -997,24 +1047,44 @@ void csg_free(void *p) { free(p); }
 int csg_set_air(csg_ctx *ctx, int air_id, size_t trace_len, const csg_options *opt, const uint64_t *pub, size_t npub) {
     return guarded(ctx, [&] { ctx->set_air(air_id, trace_len, opt, pub, npub); });
 }
-int csg_load_trace(csg_ctx *ctx, const uint64_t *trace) { return guarded(ctx, [&] { if (!trace) throw ArgError("null trace"); ctx->load_trace(trace); }); }
+int csg_load_trace(csg_ctx *ctx, const uint64_t *trace, int repr) { return guarded(ctx, [&] { if (!trace) throw ArgError("null trace"); ctx->load_trace(trace, repr); }); }
 int csg_reload_resident_trace(csg_ctx *ctx) { return guarded(ctx, [&] { ctx->reload_resident(); }); }
 int csg_prove_loaded(csg_ctx *ctx, uint8_t **proof, size_t *proof_len) {
     return guarded(ctx, [&] { if (!proof || !proof_len) throw ArgError("null output"); ctx->prove_loaded(proof, proof_len); });
 }
-int csg_prove(csg_ctx *ctx, int air_id, const uint64_t *trace, size_t trace_len, const uint64_t *pub, size_t npub, const csg_options *opt,
+int csg_prove(csg_ctx *ctx, int air_id, const uint64_t *trace, int repr, size_t trace_len, const uint64_t *pub, size_t npub, const csg_options *opt,
               uint8_t **proof, size_t *proof_len) {
     return guarded(ctx, [&] {
         if (!trace || !proof || !proof_len) throw ArgError("null argument");
+        csg_ctx::check_repr(repr);
         ctx->set_air(air_id, trace_len, opt, pub, npub);
-        ctx->prove_loaded(proof, proof_len, trace);
+        ctx->prove_loaded(proof, proof_len, trace, repr);
     });
 }
-int csg_prove_trace(csg_ctx *ctx, const uint64_t *trace, uint8_t **proof, size_t *proof_len) {
+int csg_prove_trace(csg_ctx *ctx, const uint64_t *trace, int repr, uint8_t **proof, size_t *proof_len) {
     return guarded(ctx, [&] {
         if (!trace || !proof || !proof_len) throw ArgError("null argument");
-        ctx->prove_loaded(proof, proof_len, trace);
+        csg_ctx::check_repr(repr);
+        ctx->need(S_AIR, "csg_set_air must be called first");
+        ctx->prove_loaded(proof, proof_len, trace, repr);
     });
+}
+// page-locked host memory for traces: the H2D copy of csg_prove / csg_prove_trace then runs at link speed under the extension
+void *csg_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (!bytes || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void csg_host_free(void *p) { if (p) cudaFreeHost(p); }
+int csg_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return CSG_ERR_ARG;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return CSG_ERR_CUDA; }
+    return CSG_OK;
+}
+int csg_host_unregister(void *p) {
+    if (!p) return CSG_ERR_ARG;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return CSG_ERR_CUDA; }
+    return CSG_OK;
 }
 int csg_extend_and_commit_trace(csg_ctx *ctx, uint8_t root[32]) { return guarded(ctx, [&] { ctx->extend_and_commit_trace(root); }); }
 int csg_eval_constraints(csg_ctx *ctx, const uint64_t *t_coeffs, const uint64_t *b_coeffs) {
@@ -1081,7 +1151,18 @@ int csg_fri_remainder(csg_ctx *ctx, uint64_t *out, size_t cap, size_t *len) {
         *len = rem.size();
     });
 }
+// query positions handed in by the caller's coin: at most 255 (the slot count of a batch opening is one byte), distinct, inside the tree
+static std::vector<size_t> checked_positions(const uint64_t *positions, size_t npos, size_t nleaves) {
+    if (!positions || npos == 0 || npos > 255) throw ArgError("between 1 and 255 query positions");
+    std::vector<size_t> pos(positions, positions + npos);
+    std::vector<size_t> sorted(pos);
+    std::sort(sorted.begin(), sorted.end());
+    if (sorted.back() >= nleaves) throw ArgError("query position outside the evaluation domain");
+    if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) throw ArgError("query positions must be distinct");
+    return pos;
+}
 static void copy_opening(const std::vector<uint64_t> &r, const std::vector<uint8_t> &p, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
+    if (!rows || !paths || !paths_len) throw ArgError("null output");
     if (p.size() > cap) throw ArgError("path buffer too small");
     memcpy(rows, r.data(), r.size() * 8);
     memcpy(paths, p.data(), p.size());
@@ -1090,7 +1171,7 @@ static void copy_opening(const std::vector<uint64_t> &r, const std::vector<uint8
 int csg_open_trace(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
     return guarded(ctx, [&] {
         ctx->need(S_COMMITTED, "the trace must be committed first");
-        std::vector<size_t> pos(positions, positions + npos);
+        std::vector<size_t> pos = checked_positions(positions, npos, ctx->lde_n);
         const size_t w = ctx->air.width;
         copy_opening(ctx->open_rows(ctx->d_lde.p, (unsigned)w, (unsigned)ctx->b, w * ctx->n, ctx->n, pos, true), ctx->open_paths(ctx->d_tnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
     });
@@ -1098,7 +1179,7 @@ int csg_open_trace(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_
 int csg_open_composition(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
     return guarded(ctx, [&] {
         ctx->need(S_COMPOSED, "the composition polynomial must be committed first");
-        std::vector<size_t> pos(positions, positions + npos);
+        std::vector<size_t> pos = checked_positions(positions, npos, ctx->lde_n);
         const size_t cw = ctx->ce * ctx->d;
         copy_opening(ctx->open_rows(ctx->d_clde.p, (unsigned)cw, (unsigned)ctx->b, cw * ctx->n, ctx->n, pos, true), ctx->open_paths(ctx->d_cnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
     });
@@ -1107,8 +1188,8 @@ int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, si
     return guarded(ctx, [&] {
         ctx->need(S_DEEP, "the DEEP composition must be computed first");
         if (layer >= ctx->nfri || !ctx->fri[layer]->committed) throw ArgError("no such committed FRI layer");
-        std::vector<size_t> pos(positions, positions + npos);
         const FriLayer &L = *ctx->fri[layer];
+        std::vector<size_t> pos = checked_positions(positions, npos, L.m / 4);
         copy_opening(ctx->open_fri_rows(L, pos), ctx->open_paths(L.nodes, L.m / 4, pos), rows, paths, cap, paths_len);
     });
 }
@@ -1158,6 +1239,7 @@ int csg_build_trace_transaction_device(csg_ctx *ctx, const csg_tx_batch *b) {
         in.reserve(packed.size()); ctx->d_wit_finals.reserve(ntx * 48); ctx->d_io.reserve((size_t)ctx->air.width * ctx->n);
         CSG_CUDA(cudaMemcpyAsync(in.p, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice, ctx->st.s));
         build_transaction_trace(in.p, ntx, 15, ctx->d_io.p, ctx->d_wit_finals.p, ctx->st);
+        ctx->trace_repr = CSG_REPR_CANONICAL;
         ctx->tm.h2d = t.stop(ctx->st);   // here: witness generation time
         ctx->nfri = 0;
         ctx->stage = S_TRACE;

@@ -9,9 +9,10 @@ using namespace f63;
 
 namespace {
 
-__global__ void to_mont_kernel(const uint64_t *__restrict__ in, fe *__restrict__ out, unsigned long long count) {
+// by = R^2: canonical words -> Montgomery form; by = R (the Montgomery form of 1): words that already are in Montgomery form, reduced below p
+__global__ void to_mont_kernel(const uint64_t *__restrict__ in, fe *__restrict__ out, unsigned long long count, fe by) {
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x, step = (unsigned long long)gridDim.x * blockDim.x;
-    for (; i < count; i += step) out[i] = mul(in[i], R2);
+    for (; i < count; i += step) out[i] = mul(in[i], by);
 }
 __global__ void from_mont_kernel(const fe *__restrict__ in, uint64_t *__restrict__ out, unsigned long long count) {
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x, step = (unsigned long long)gridDim.x * blockDim.x;
@@ -252,8 +253,8 @@ void coset_major_to_natural(const fe *lde, unsigned width, unsigned ncosets, siz
     CSG_LAUNCH(st, coset_to_natural_kernel, grid, 256, 0, lde, width, ncosets, (unsigned long long)n, out);
 }
 
-void to_montgomery(const uint64_t *in, fe *out, size_t count, Stream &st) {
-    CSG_LAUNCH(st, to_mont_kernel, grid_for(count, 256), 256, 0, in, out, (unsigned long long)count);
+void to_montgomery(const uint64_t *in, fe *out, size_t count, Stream &st, bool already_montgomery) {
+    CSG_LAUNCH(st, to_mont_kernel, grid_for(count, 256), 256, 0, in, out, (unsigned long long)count, already_montgomery ? ONE : R2);
 }
 void from_montgomery(const fe *in, uint64_t *out, size_t count, Stream &st) {
     CSG_LAUNCH(st, from_mont_kernel, grid_for(count, 256), 256, 0, in, out, (unsigned long long)count);

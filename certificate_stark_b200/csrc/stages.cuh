@@ -8,7 +8,8 @@
 namespace csg {
 
 // canonical u64 -> Montgomery (BaseElement::new) and back
-void to_montgomery(const uint64_t *in, fe *out, size_t count, Stream &st);
+// canonical words (or, with already_montgomery, Montgomery words as winterfell's TraceTable stores them) -> reduced Montgomery form
+void to_montgomery(const uint64_t *in, fe *out, size_t count, Stream &st, bool already_montgomery = false);
 
 // e[k][m] (k < ce): coefficient m of the size-n interpolant of C on ce coset k, already divided by s_k^m.
 // cols[r][q] = coefficient q*ce + r of the degree < ce*n composition polynomial (CompositionPoly::new's transposition).

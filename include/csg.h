@@ -27,7 +27,7 @@ extern "C" {
 enum { CSG_OK = 0, CSG_ERR_ARG = 1, CSG_ERR_CUDA = 2, CSG_ERR_STATE = 3, CSG_ERR_UNSUPPORTED = 4, CSG_ERR_COIN = 5 };
 /* csg_verify results other than CSG_OK (the VerifierError kinds of winterfell::verify) */
 enum { CSG_VERIFY_MALFORMED = 16, CSG_VERIFY_OOD_MISMATCH = 17, CSG_VERIFY_POW = 18, CSG_VERIFY_TRACE_QUERY = 19,
-       CSG_VERIFY_CONSTRAINT_QUERY = 20, CSG_VERIFY_FRI = 21 };
+       CSG_VERIFY_CONSTRAINT_QUERY = 20, CSG_VERIFY_FRI = 21, CSG_VERIFY_WEAK_OPTIONS = 22 };
 
 /* AIR ids: the six `impl Air` of the reference */
 enum {
@@ -50,6 +50,11 @@ typedef struct {
     uint32_t num_queries, blowup_factor, grinding_factor, hash_fn, field_extension, fri_folding_factor, fri_max_remainder_size;
 } csg_options;
 
+/* representation of the trace words handed to csg_prove / csg_load_trace / csg_prove_trace.  winterfell's f63
+ * BaseElement is a u64 in Montgomery form (R = 2^64; src/utils/ecc.rs:23-45 gives the generator through from_raw_unchecked), so
+ * TraceTable column memory can cross the boundary untouched as CSG_REPR_MONTGOMERY; CSG_REPR_CANONICAL = BaseElement::to_repr(). */
+enum { CSG_REPR_CANONICAL = 0, CSG_REPR_MONTGOMERY = 1 };
+
 typedef struct csg_ctx csg_ctx;
 
 /* ---- context ------------------------------------------------------------------------------------------------- */
@@ -57,9 +62,16 @@ csg_ctx *csg_create(int device);            /* NULL if the device cannot be open
 void csg_destroy(csg_ctx *ctx);
 const char *csg_last_error(const csg_ctx *ctx);
 void csg_free(void *p);                     /* frees buffers returned by csg_prove */
+/* page-locked host memory for traces (cudaHostAlloc / cudaHostRegister): from it the H2D copy runs at link speed under the trace
+ * extension.  A trace in ordinary pageable memory is accepted as well: the library stages it through its own pinned buffers with
+ * the host's threads (slower by the host memcpy, still overlapped).  csg_host_alloc returns NULL on failure. */
+void *csg_host_alloc(size_t bytes);
+void csg_host_free(void *p);
+int csg_host_register(void *p, size_t bytes);
+int csg_host_unregister(void *p);
 
 /* ---- level 1: replaces `prover.prove(trace)` (src/lib.rs:140) -------------------------------------------------
- * trace: column-major [width][trace_len], canonical, exactly TraceTable's storage.
+ * trace: column-major [width][trace_len], exactly TraceTable's storage; repr says whether the words are canonical or Montgomery.
  * pub:   the AIR's PublicInputs as canonical words in write_into() order:
  *        TRANSACTION / MERKLE_UPDATE  initial_root[7] final_root[7]      (src/air.rs:57-62)
  *        MERKLE_INIT                  s_inputs[14] r_inputs[14] delta    (src/merkle/init/air.rs:36-42)
@@ -67,22 +79,27 @@ void csg_free(void *p);                     /* frees buffers returned by csg_pro
  *        RANGE                        number                              (src/range/air.rs:33-37)
  *        RESCUE                       seed[7] result[7]                   (benches/rescue.rs:136-141)
  * proof: malloc'ed StarkProof::to_bytes(); release with csg_free. */
-int csg_prove(csg_ctx *ctx, int air_id, const uint64_t *trace, size_t trace_len, const uint64_t *pub, size_t npub,
+int csg_prove(csg_ctx *ctx, int air_id, const uint64_t *trace, int repr, size_t trace_len, const uint64_t *pub, size_t npub,
               const csg_options *opt, uint8_t **proof, size_t *proof_len);
 
 /* ---- verification: replaces `winterfell::verify::<Air>(proof, pub_inputs)` (src/lib.rs:144-150).  Host-only, as in the
  * reference; needs no context and no GPU.  Returns CSG_OK or one of CSG_VERIFY_*. */
 int csg_verify(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len);
+/* csg_verify trusts the ProofOptions recorded inside the proof, as winterfell::verify does.  An acceptance check should not: this
+ * form also rejects (CSG_VERIFY_WEAK_OPTIONS) a proof made with fewer queries, a smaller blowup or grinding factor, a smaller
+ * field extension, another hash function or a larger FRI remainder than `min_options` -- the options the verifying side holds
+ * (TransactionExample keeps them in `options`, src/lib.rs:92-98). */
+int csg_verify_with_options(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len, const csg_options *min_options);
 
 /* ---- level 2: the stages of Prover::prove, transcript on the caller's side --------------------------------------
  * call order: set_air, load_trace, [extend_and_commit_trace, eval_constraints, commit_composition, ood, deep,
  * (fri_commit_layer, fri_fold)*, fri_remainder, open]; prove_loaded() runs the bracketed part with the built-in
  * transcript.  Challenges are canonical field elements drawn by the caller's RandomCoin. */
 int csg_set_air(csg_ctx *ctx, int air_id, size_t trace_len, const csg_options *opt, const uint64_t *pub, size_t npub);
-int csg_load_trace(csg_ctx *ctx, const uint64_t *trace);                     /* H2D copy of width*trace_len words */
+int csg_load_trace(csg_ctx *ctx, const uint64_t *trace, int repr);           /* H2D copy of width*trace_len words */
 int csg_prove_loaded(csg_ctx *ctx, uint8_t **proof, size_t *proof_len);      /* proof of the resident trace */
 /* proof of a trace in HOST memory for the AIR set by csg_set_air: the H2D copy is pipelined with the trace extension */
-int csg_prove_trace(csg_ctx *ctx, const uint64_t *trace, uint8_t **proof, size_t *proof_len);
+int csg_prove_trace(csg_ctx *ctx, const uint64_t *trace, int repr, uint8_t **proof, size_t *proof_len);
 int csg_reload_resident_trace(csg_ctx *ctx);                                 /* re-arm the trace left in HBM by the last csg_load_trace (benchmarks) */
 int csg_extend_and_commit_trace(csg_ctx *ctx, uint8_t root[32]);             /* Trace::extend + build_commitment */
 /* t_coeffs: (alpha,beta) per transition constraint; b_coeffs: (alpha,beta) per assertion in winterfell's sorted order */
@@ -99,7 +116,9 @@ int csg_fri_fold_ext(csg_ctx *ctx, const uint64_t *alpha);
 int csg_fri_commit_layer(csg_ctx *ctx, uint8_t root[32]);                    /* transpose/4, hash, Merkle */
 int csg_fri_fold(csg_ctx *ctx, uint64_t alpha);                              /* degree-respecting projection */
 int csg_fri_remainder(csg_ctx *ctx, uint64_t *out, size_t cap, size_t *len);
-/* openings at the query positions: rows are written row-major, paths in BatchMerkleProof::serialize_nodes() form */
+/* openings at the query positions (1..255 distinct positions inside the domain, else CSG_ERR_ARG): `rows` receives npos rows of the
+ * opened matrix, row-major -- the caller provides npos * width words (trace: AIR width; composition: ce_blowup * d; FRI layer: 4 * d);
+ * `paths` (capacity `cap` bytes) receives BatchMerkleProof::serialize_nodes() */
 int csg_open_trace(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len);
 int csg_open_composition(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len);
 int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len);

@@ -116,6 +116,37 @@ def test_product_verifier_accepts_valid_and_rejects_invalid_proofs(csg, oracle):
         assert csg.verify((air + 1) % 6, pub, proof) != 0
 
 
+def test_verifier_rejects_weak_or_malformed_contexts(csg, oracle):
+    # the context bytes of a proof are attacker-controlled.  (a) log2 fields out of range must not be shifted
+    # (a blowup byte of 35 used to behave like 3); (b) a non-empty trace-meta blob is bound to nothing; (c) options that end the
+    # FRI domain below 8 elements used to index before the start of a heap buffer; (d) an acceptance check needs a floor.
+    trace, pub = csg.build_rescue_trace(np.arange(42, 49, dtype=np.uint64), 16)
+    proof = oracle.prove(csg.AIR_RESCUE, trace, pub, oracle.options(blowup=4))
+    assert csg.verify(csg.AIR_RESCUE, pub, proof) == 0
+    # context layout: width, log n, meta length (2), modulus length, modulus (8), queries, log blowup, grinding, hash, extension, log folding, log remainder
+    assert proof[0] == 14 and proof[2:4] == b"\0\0" and proof[4] == 8 and proof[14] == 2
+    for off, val in [(14, 34), (14, 0), (14, 6), (18, 3), (18, 34), (19, 1), (19, 11), (19, 40), (15, 32), (1, 41)]:
+        bad = bytearray(proof)
+        bad[off] = val
+        assert csg.verify(csg.AIR_RESCUE, pub, bytes(bad)) == 16, f"context byte {off} = {val} not rejected as malformed"
+    meta = proof[:2] + b"\x01\x00\xaa" + proof[4:]
+    assert csg.verify(csg.AIR_RESCUE, pub, meta) == 16
+    # blowup 2 and remainder 4 on a 4^k domain end at 2 elements: the prover refuses these options, so must the verifier
+    rt, rp = csg.build_range_trace(77)
+    rproof = bytearray(oracle.prove(csg.AIR_RANGE, rt, rp, oracle.options(blowup=8)))
+    rproof[14], rproof[19] = 1, 2          # 64 * 2 = 128 -> 32 -> 8 -> 2
+    assert csg.verify(csg.AIR_RANGE, rp, bytes(rproof)) == 16
+    # the floor: 42 queries expected, a proof with 8 (or grinding below, another hash, a smaller blowup) is refused before any work
+    weak = oracle.prove(csg.AIR_RESCUE, trace, pub, oracle.options(blowup=4, num_queries=8))
+    assert csg.verify(csg.AIR_RESCUE, pub, weak) == 0
+    assert csg.verify(csg.AIR_RESCUE, pub, weak, csg.ProofOptions(blowup_factor=4)) == 22
+    assert csg.verify(csg.AIR_RESCUE, pub, proof, csg.ProofOptions(blowup_factor=4)) == 0
+    assert csg.verify(csg.AIR_RESCUE, pub, proof, csg.ProofOptions(blowup_factor=8)) == 22
+    assert csg.verify(csg.AIR_RESCUE, pub, proof, csg.ProofOptions(blowup_factor=4, grinding_factor=8)) == 22
+    assert csg.verify(csg.AIR_RESCUE, pub, proof, csg.ProofOptions(blowup_factor=4, hash_fn=csg.HASH_SHA3_256)) == 22
+    assert csg.verify(csg.AIR_RESCUE, pub, proof, csg.ProofOptions(blowup_factor=2, num_queries=10, fri_max_remainder_size=1024)) == 0
+
+
 def test_bench_stage_roofline_arithmetic():
     # bench.py's HBM view of the LDE and commitment stages: SURVEY.md 8(d) bytes / stage time, on the round-1 stage times
     import bench

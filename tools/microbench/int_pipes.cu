@@ -1,0 +1,126 @@
+// Integer-pipe microbenchmark for sm_100a (B200): issue rates of the instruction classes the f63 kernels are made of, alone and
+// mixed, and of whole NTT butterflies in several formulations.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o int_pipes int_pipes.cu && ./int_pipes
+//   ncu --metrics smsp__inst_executed.sum,smsp__inst_executed_pipe_alu.sum,smsp__inst_executed_pipe_fma.sum,\
+//       smsp__inst_executed_pipe_fmaheavy.sum,smsp__inst_executed_pipe_fmalite.sum,gpu__time_duration.sum ./int_pipes
+// Each kernel: 148 CTAs x 1024 threads (8 warps per SM sub-partition), ITER trips of a body of 8 independent chains per thread.
+// The program prints time only; per-opcode counts of each body come from `cuobjdump -sass` (tools/microbench/README).
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../certificate_stark_b200/csrc/field.cuh"
+using namespace f63;
+
+#define ITER 1024
+#define CHK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
+
+__device__ __forceinline__ uint64_t add64_fma(uint64_t x, uint64_t y, uint32_t one) {
+    // 64-bit add on the FMA pipe: low word through a wide multiply-add by a runtime 1, high word through a 32-bit multiply-add
+    uint64_t s = (uint64_t)(uint32_t)y * one + x;
+    uint32_t hi = (uint32_t)(y >> 32) * one + (uint32_t)(s >> 32);
+    return ((uint64_t)hi << 32) | (uint32_t)s;
+}
+// butterfly formulations: (x, y, w) -> (x + w y, x - w y); x, y lazily reduced
+template <int V> __device__ __forceinline__ void bfly(uint64_t &x, uint64_t &y, uint64_t w, uint32_t one) {
+    if (V == 0) {          // current: product below 1.52p, sums brought back below 2p by compare + select
+        const uint64_t t = mul_2p(y, w), a = x;
+        x = add_2p(a, t); y = sub_2p(a, t);
+    } else if (V == 1) {   // product fully reduced, invariant x < 2^63: the fix is "subtract p when bit 63 is set", done with multiply-adds
+        const uint64_t t0 = mul_raw(y, w), t = t0 >= P ? t0 - P : t0, nt = P - t, a = x;
+        uint64_t s = a + t, d = a + nt;
+        uint32_t qs = (uint32_t)(s >> 63), qd = (uint32_t)(d >> 63);
+        s = (uint64_t)qs * 0xFFFFFFFFu + s; s = (((uint64_t)((uint32_t)(s >> 32) + qs * 0xBE7FFFFFu)) << 32) | (uint32_t)s;
+        d = (uint64_t)qd * 0xFFFFFFFFu + d; d = (((uint64_t)((uint32_t)(d >> 32) + qd * 0xBE7FFFFFu)) << 32) | (uint32_t)d;
+        x = s; y = d;
+    } else if (V == 2) {   // as 0 with the two 64-bit additions on the FMA pipe
+        const uint64_t t = mul_2p(y, w), a = x;
+        uint64_t s = add64_fma(a, t, one);
+        x = s >= 2 * P ? s - 2 * P : s;
+        y = sub_2p(a, t);
+    } else if (V == 3) {   // mask form of the conditional corrections (shift + and instead of compare + select)
+        const uint64_t t = mul_2p(y, w), a = x;
+        uint64_t s = a + t - 2 * P;                                  // a + t < 3.52p: s "negative" exactly when a + t < 2p
+        uint64_t m = (uint64_t)((int64_t)s >> 63);                    // wrong when s >= 2^63 legitimately: s < 1.52p < 2^63, fine
+        x = s + (m & (2 * P));
+        uint64_t d = a - t;
+        uint64_t borrow = (uint64_t)0 - (uint64_t)(a < t);
+        y = d + (borrow & (2 * P));
+    }
+}
+template <int V> __global__ void __launch_bounds__(1024, 1) kb(uint64_t *out, uint64_t seed, uint32_t one) {
+    uint64_t x[8], y[8], w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x[i] = (seed + threadIdx.x * 16 + i) % P; y[i] = (seed * 3 + i + threadIdx.x) % P; w[i] = (seed * 5 + 7 * i + 1) % P; }
+    for (int it = 0; it < ITER; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) bfly<V>(x[i], y[i], w[i], one);
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= x[i] ^ y[i];
+    if (s == 0x12345678u) out[threadIdx.x] = s;
+}
+
+template <int KIND> __global__ void __launch_bounds__(1024, 1) k(uint64_t *out, uint32_t seed, uint32_t one) {
+    uint32_t a[8], b[8];
+    uint64_t q[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = seed + threadIdx.x * 8 + i; b[i] = seed * 3 + i; q[i] = ((uint64_t)a[i] << 32) | b[i]; }
+    const uint32_t c = seed | 1, d = seed * 7 + 1;
+    const uint64_t cd = ((uint64_t)c << 32) | d;
+    for (int it = 0; it < ITER; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (KIND == 0) q[i] = (uint64_t)(uint32_t)q[i] * c + q[i];                      // IMAD.WIDE.U32 with a 64-bit addend
+            else if (KIND == 1) a[i] = a[i] * c + b[i];                                       // IMAD
+            else if (KIND == 2) { a[i] = __umulhi(a[i], c) + b[i]; }                          // IMAD.HI
+            else if (KIND == 3) { a[i] += c; b[i] += d; }                                     // IADD3 x2
+            else if (KIND == 4) { a[i] = (a[i] ^ c) & (a[i] | d); b[i] = (b[i] & c) ^ (b[i] | d); }   // LOP3 x2
+            else if (KIND == 5) { a[i] = a[i] >= b[i] ? d : a[i]; b[i] += one; }              // ISETP + SEL (+1 add)
+            else if (KIND == 6) q[i] += cd;                                                   // 64-bit add: IADD3 + IADD3.X / IMAD.X
+            else if (KIND == 7) q[i] = add64_fma(q[i], cd, one);                              // 64-bit add on the FMA pipe
+            else if (KIND == 8) { q[i] = (uint64_t)(uint32_t)q[i] * c + q[i]; a[i] += c; }    // IMAD.WIDE + IADD3
+            else if (KIND == 9) { q[i] = (uint64_t)(uint32_t)q[i] * c + q[i]; a[i] += c; b[i] += d; }   // IMAD.WIDE + 2 IADD3
+            else if (KIND == 10) { a[i] = a[i] * c + b[i]; b[i] += d; }                       // IMAD + IADD3
+            else if (KIND == 11) { a[i] = __funnelshift_l(a[i], b[i], 7); b[i] = __funnelshift_l(b[i], a[i], 9); }   // SHF x2
+            else if (KIND == 12) q[i] = mul_raw(q[i], cd >> 2);                               // modular multiplication (lazy), dependent chain
+            else if (KIND == 13) q[i] = mul(q[i], cd >> 2);                                   // modular multiplication, reduced
+        }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= a[i] ^ b[i] ^ q[i];
+    if (s == 0x12345678u) out[threadIdx.x] = s;
+}
+
+template <class F> int timed(const char *name, F launch) {
+    cudaEvent_t a, b;
+    CHK(cudaEventCreate(&a)); CHK(cudaEventCreate(&b));
+    launch(0);
+    CHK(cudaDeviceSynchronize());
+    CHK(cudaEventRecord(a));
+    for (int r = 0; r < 4; r++) launch(r + 1);
+    CHK(cudaEventRecord(b));
+    CHK(cudaEventSynchronize(b));
+    float ms;
+    CHK(cudaEventElapsedTime(&ms, a, b));
+    printf("%-14s %9.4f ms per launch   (%d trips x 8 chains x 8 warps per SMSP)\n", name, ms / 4, ITER);
+    return 0;
+}
+
+int main() {
+    cudaDeviceProp p;
+    CHK(cudaGetDeviceProperties(&p, 0));
+    int khz = 0;
+    CHK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
+    printf("%s, %d SMs, clock attribute %.0f MHz\n", p.name, p.multiProcessorCount, khz / 1e3);
+    uint64_t *d;
+    CHK(cudaMalloc(&d, 8192));
+    const int s = p.multiProcessorCount;
+#define RUNK(K) timed("class " #K, [&](int r) { k<K><<<s, 1024>>>(d, 12345 + r, 1); });
+    RUNK(0) RUNK(1) RUNK(2) RUNK(3) RUNK(4) RUNK(5) RUNK(6) RUNK(7) RUNK(8) RUNK(9) RUNK(10) RUNK(11) RUNK(12) RUNK(13)
+#define RUNB(V) timed("butterfly " #V, [&](int r) { kb<V><<<s, 1024>>>(d, 12345 + r, 1); });
+    RUNB(0) RUNB(1) RUNB(2) RUNB(3)
+    CHK(cudaDeviceSynchronize());
+    return 0;
+}
