@@ -10,10 +10,14 @@ data-path collective, scaling is weak -- that is `value`.  The same run then als
 (coset-sharded proof, NCCL exchanges; `sharded_proof` in the JSON line): the latency view of the same hardware.
 
   value     tx/s with the trace already resident in HBM when the timed region starts (device-event time, max over ranks)
-  e2e       the same through csg_prove() with the trace in pinned HOST memory: H2D copy and proof D2H inside the region
-  roofline  the dominant kernel (constraint evaluation), algorithmic bytes / its CUDA-event time, against the measured HBM peak
-  cpu_baseline  the CPU oracle (a port: the Rust reference cannot be built here) on a bounded sample, N=1 rank 0 only
---impl reference times that CPU port alone, with all host threads.
+  e2e       the same through csg_prove_trace() with the trace in page-locked HOST memory (csg_host_alloc): H2D copy and proof D2H
+            inside the region; e2e_pageable: the same from ordinary pageable memory (what a Rust Vec<u64> is)
+  roofline  the dominant kernel family by time (the 1024-point NTT passes: the whole LDE stage is launches of that one kernel):
+            integer-issue fraction (warp instructions / s against 148 SMs x 4 schedulers x SM clock) with the HBM fraction beside it
+  stage_roofline  every stage against both rooflines
+  cpu_baseline  the CPU oracle (a port: the Rust reference cannot be built here) proving the SAME batch once, N=1 rank 0 only;
+            its proof bytes are compared with the GPU's (`parity`)
+--impl reference times that CPU port alone, with all host threads, on full-size batches.
 """
 import argparse
 import json
@@ -49,13 +53,28 @@ CONS_KERNELS = {   # name: (description, algorithmic bytes per ce row, fraction 
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu capture of this same command (profiles/README.md);
-# null for kernels that were not captured
-TRAFFIC, PIPES = {}, {}
+def csrc_sha16():
+    """fingerprint of the kernel sources: profiles/traffic.json (ncu counters of one proof) is only quoted when it was captured
+    from exactly these sources"""
+    import hashlib
+    h = hashlib.sha256()
+    d = ROOT / "certificate_stark_b200" / "csrc"
+    for f in sorted(list(d.glob("*.cu")) + list(d.glob("*.cuh")) + list(d.glob("*.h"))):
+        h.update(f.name.encode()); h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+# ncu counters of ONE proof of this workload (tools/make_traffic.py from the launch list of `bench.py --profile --steps 1`):
+# per stage and for the dominant kernel, warp instructions executed and DRAM bytes.  Instruction counts are a property of the
+# code and the workload, not of the run -- but only of the code they were taken from: stale captures are dropped, not restated.
+TRAFFIC = {}
 _t = ROOT / "profiles" / "traffic.json"
 if _t.exists():
-    TRAFFIC = json.loads(_t.read_text())
-    PIPES = TRAFFIC.get("_pipes", {})     # ALU / FMA pipe utilisation and issue-slot use of the same launches (ncu): the binding resource
+    try:
+        TRAFFIC = json.loads(_t.read_text())
+    except Exception:
+        TRAFFIC = {}
+TRAFFIC_FRESH = bool(TRAFFIC) and TRAFFIC.get("_captured_at", {}).get("csrc_sha16") == csrc_sha16()
 
 
 def measured_peaks():
@@ -66,19 +85,43 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
-def stage_roofline(stage_ms, n, hbm_peak):
-    """HBM view of the transform and commitment stages (BASELINE.json: "LDE/hash HBM GB/s"): the algorithmic bytes of
-    SURVEY.md section 8(d) -- K1 iNTT 16 n and K2 coset LDE 8 n + 8 b n per column; K3 row hashing 8 w + 32 per LDE row and
-    K4 Merkle tree 32 L + 32 (L - 1) -- divided by the stage's CUDA-event time.  Both stages are integer-pipe-bound
-    (profiles/README.md); the fractions say how far from the HBM roofline that leaves them."""
-    rows = n * BLOWUP
-    algorithmic = {"lde": TRACE_WIDTH * n * (16 + 8 + 8 * BLOWUP), "commit_trace": rows * (8 * TRACE_WIDTH + 32) + 32 * (2 * rows - 1)}
+def stage_bytes(n):
+    """algorithmic HBM bytes of each stage of one proof (SURVEY.md 8(d) per-unit figures x units)"""
+    rows, w, ce = n * BLOWUP, TRACE_WIDTH, BLOWUP
+    fri = 0
+    m = rows
+    while m > 256:
+        fri += 8 * m + 8 * m // 4 + 32 * m // 4 + 32 * (2 * (m // 4) - 1)   # layer in, folded layer out, row digests, tree
+        m //= 4
+    return {
+        "lde": w * n * (16 + 8 + 8 * BLOWUP),                                    # K1 16 n + K2 8 n + 8 b n per column
+        "commit_trace": rows * (8 * w + 32) + 32 * (2 * rows - 1),              # K3 8 w + 32 per row, K4 32 L + 32 (L - 1)
+        "constraints": rows * CONSTRAINT_BYTES_PER_ROW,                          # K5: every LDE row read once, one merged value written
+        "composition": 8 * rows * 2 + ce * n * (8 + 8 * BLOWUP) + rows * (8 * ce + 32) + 32 * (2 * rows - 1),   # K6 + LDE of ce columns + K3/K4
+        "ood_deep": 8 * n * (w + ce) * 2 + 3 * n * (8 + 8 * BLOWUP) + rows * 32,  # K7 reads every coefficient; K8 combines them, extends 3 columns, 24 B in + 8 out per row
+        "fri": fri,
+    }
+
+
+def stage_roofline(stage_ms, n, hbm_peak, int_peak_gwips=None, stage_insts=None):
+    """Every stage against both rooflines.  HBM: the algorithmic bytes above / the stage's CUDA-event time against the measured
+    copy bandwidth.  INT: warp instructions executed in the stage (ncu, profiles/traffic.json, only when captured from these
+    sources) / the same time, against 148 SMs x 4 schedulers x the SM clock sampled during the run.  The arithmetic stages are
+    integer-issue-bound (64-bit modular multiplication has no native instruction); the fractions say how far each is from either roof."""
     out = {}
-    for k, nbytes in algorithmic.items():
+    for k, nbytes in stage_bytes(n).items():
         ms = stage_ms.get(k) or 0.0
         gbs = nbytes / (ms / 1e3) / 1e9 if ms > 0 else None
-        out[k] = {"algorithmic_bytes": int(nbytes), "ms": ms, "achieved": gbs, "unit": "GB/s", "peak": hbm_peak,
-                  "frac": gbs / hbm_peak if gbs and hbm_peak else None}
+        rec = {"algorithmic_bytes": int(nbytes), "ms": ms, "achieved": gbs, "unit": "GB/s", "peak": hbm_peak,
+               "frac": gbs / hbm_peak if gbs and hbm_peak else None}
+        wi = (stage_insts or {}).get(k, {}).get("warp_insts") if stage_insts else None
+        if wi and ms > 0 and int_peak_gwips:
+            gw = wi / (ms / 1e3) / 1e9
+            rec["int"] = {"warp_insts": int(wi), "achieved": gw, "peak": int_peak_gwips, "unit": "Gwarp-inst/s", "frac": gw / int_peak_gwips}
+            dram = (stage_insts or {}).get(k, {}).get("dram_bytes")
+            if dram:
+                rec["traffic"] = int(dram)
+        out[k] = rec
     return out
 
 
@@ -119,7 +162,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_port_run(num_tx, steps, warmup, seed=1):
+def cpu_port_run(num_tx, steps, warmup, seed=1, want_proof=False):
     """the CPU oracle's prover (OpenMP, all host threads) on num_tx transactions; returns mean seconds per proof"""
     import certificate_stark_b200 as csg
     from oracle import pyoracle as O
@@ -130,24 +173,33 @@ def cpu_port_run(num_tx, steps, warmup, seed=1):
         O.prove(O.AIR_TRANSACTION, trace, pub, opt)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.prove(O.AIR_TRANSACTION, trace, pub, opt)
-    return (time.perf_counter() - t0) / max(steps, 1)
+        proof = O.prove(O.AIR_TRANSACTION, trace, pub, opt)
+    sec = (time.perf_counter() - t0) / max(steps, 1)
+    return (sec, proof) if want_proof else sec
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference path's CPU implementation.  The reference is Rust over an un-vendored winterfell fork
-    and no Rust toolchain exists in this image, so what runs is the C/OpenMP port of that path (oracle/), on a bounded sample."""
+    and no Rust toolchain exists in this image, so what runs is the C/OpenMP port of that path (oracle/) with all host threads,
+    on FULL-SIZE batches of the configured workload.  One proof takes 20-100 s, so the number of steps actually run is capped by a
+    time budget (`steps_run`; no warm-up beyond one small proof that loads the library and its tables)."""
     if rank != 0:
         return
-    sample_tx = min(args.num_tx, 64)
-    sec = cpu_port_run(sample_tx, args.steps, min(args.warmup, 1))
-    value = sample_tx / sec
+    cpu_port_run(min(args.num_tx, 16), 1, 0)            # load the library, build the tables
+    budget_s, times = float(os.environ.get("CSG_REFERENCE_BUDGET_S", "150")), []
+    t_all = time.perf_counter()
+    while len(times) < max(args.steps, 1) and (not times or time.perf_counter() - t_all + times[-1] <= budget_s):
+        times.append(cpu_port_run(args.num_tx, 1, 0, seed=1000))
+    sec = sum(times) / len(times)
+    value = args.num_tx / sec
     cores = os.cpu_count() or 1
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (f63 modular)",
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "steps_run": len(times),
+            "warmup": 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (f63 modular)",
             "data": "synthetic", "config": workload_config(args.num_tx, 1),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample_tx}-transaction batch (trace {sample_tx * ROWS_PER_TX} x 94, blowup 8) per step; C/OpenMP port of the path, the Rust reference cannot be built here"},
+                             "sample": f"{len(times)} full proof(s) of a {args.num_tx}-transaction batch (trace {args.num_tx * ROWS_PER_TX} x 94, blowup 8), "
+                                       f"{sec:.1f} s each, out of the {args.steps} steps asked for (time budget {budget_s:.0f} s); C/OpenMP port of the path, "
+                                       "the Rust reference cannot be built here"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -200,12 +252,12 @@ def main():
     num_tx = args.num_tx
     n = num_tx * ROWS_PER_TX
     opt = csg.ProofOptions()
-    # synthetic batch (seeded per rank), witness built on the host straight into pinned memory
-    pinned = torch.empty((TRACE_WIDTH, n), dtype=torch.int64, pin_memory=True)
-    trace = pinned.numpy().view(np.uint64)
+    # synthetic batch (seeded per rank), witness built on the host straight into page-locked memory (csg_host_alloc)
+    ctx = csg.Context(local_rank)
+    pinned = csg.HostBuffer(TRACE_WIDTH, n)
+    trace = pinned.array
     batch = csg.TransactionBatch(seed=1000 + rank, num_tx=num_tx)
     _, pub = batch.transaction_trace(out=trace)
-    ctx = csg.Context(local_rank)
     ctx.set_air(csg.AIR_TRANSACTION, n, pub, opt)
 
     def prove_resident():
@@ -213,16 +265,16 @@ def main():
         return ctx.prove_loaded()
 
     def prove_e2e():
-        return ctx.prove_trace_ptr(pinned.data_ptr())      # csg_prove_trace: host buffer in, proof bytes out
+        return ctx.prove_trace_ptr(pinned.ptr)      # csg_prove_trace: host buffer in, proof bytes out
 
-    ctx.load_trace_ptr(pinned.data_ptr())
+    ctx.load_trace_ptr(pinned.ptr)
     proof = None
     warmup = 1 if args.profile else max(args.warmup, 3)
     for _ in range(warmup):
         proof = prove_resident()
 
     # ---- timed region 1: trace resident in HBM
-    stage_sum, launches = {}, 0
+    stage_sum, launches, stage_launches = {}, 0, {}
     with ClockSampler(local_rank) as clocks:
         barrier()
         ctx.timer_start()
@@ -232,25 +284,35 @@ def main():
             t = ctx.timings()
             launches += int(t["kernel_launches"])
             for k, v in t.items():
-                if k not in ("total", "kernel_launches"):
+                if k not in ("total", "kernel_launches", "stage_launches"):
                     stage_sum[k] = stage_sum.get(k, 0.0) + v
+            stage_launches = t["stage_launches"]
             assert p == proof, "non-deterministic proof"
         dev_ms = ctx.timer_stop()     # CUDA events on the proving stream around the K steps
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
     clock_summary = clocks.summary()
 
-    # ---- timed region 2: end to end through the C ABI with host buffers
-    e2e_ms, e2e_h2d_ms = 0.0, 0.0
+    # ---- timed region 2: end to end through the C ABI with host buffers (a) page-locked, (b) pageable
+    e2e_ms, e2e_h2d_ms, e2e_pg_ms = 0.0, 0.0, 0.0
     if not args.profile:
-        prove_e2e()
+        assert prove_e2e() == proof, "the end-to-end path gives a different proof"
         barrier()
         ctx.timer_start()
         for _ in range(args.steps):
             p = prove_e2e()
-            e2e_h2d_ms += ctx.timings()["h2d"]
+            e2e_h2d_ms += ctx.timings()["h2d"]     # first byte .. last byte of the copy, on the copy stream (it runs under the extension)
         e2e_ms = ctx.timer_stop()
         barrier()
+        pageable = np.array(trace)                 # ordinary host memory: what a Rust Vec<u64> is
+        assert ctx.prove_trace_ptr(pageable.ctypes.data) == proof
+        barrier()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            ctx.prove_trace_ptr(pageable.ctypes.data)
+        e2e_pg_ms = ctx.timer_stop()
+        barrier()
+        del pageable
 
     # ---- timed region 3: TransactionExample::prove() as a whole = build_trace + prove, with the witness built on the device
     wit_ms = 0.0
@@ -288,7 +350,7 @@ def main():
     if run_sharded:
         import hashlib
         sctx.set_air(csg.AIR_TRANSACTION, n, pub0, opt)
-        sctx.load_trace_ptr(pinned.data_ptr())
+        sctx.load_trace_ptr(pinned.ptr)
         for _ in range(3):
             sctx.reload_resident_trace()
             sp = sctx.prove_loaded()
@@ -304,23 +366,23 @@ def main():
             t = sctx.timings()
             sh_comm_ms += t["comm"]
             for k, v in t.items():
-                if k not in ("total", "kernel_launches"):
+                if k not in ("total", "kernel_launches", "stage_launches"):
                     sh_stage[k] = sh_stage.get(k, 0.0) + v
         sh_ms = sctx.timer_stop()
         barrier()
-        sctx.prove_trace_ptr(pinned.data_ptr())
+        sctx.prove_trace_ptr(pinned.ptr)
         barrier()
         sctx.timer_start()
         for _ in range(args.steps):
-            sctx.prove_trace_ptr(pinned.data_ptr())
+            sctx.prove_trace_ptr(pinned.ptr)
         sh_e2e_ms = sctx.timer_stop()
         barrier()
         sctx.close()
 
-    times = torch.tensor([dev_ms, wall_ms, e2e_ms, wit_ms, sh_ms, sh_e2e_ms, sh_comm_ms], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, wall_ms, e2e_ms, wit_ms, sh_ms, sh_e2e_ms, sh_comm_ms, e2e_pg_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_ms, wit_ms, sh_ms, sh_e2e_ms, sh_comm_ms = [float(x) for x in times.cpu()]
+    dev_ms, wall_ms, e2e_ms, wit_ms, sh_ms, sh_e2e_ms, sh_comm_ms, e2e_pg_ms = [float(x) for x in times.cpu()]
 
     if rank == 0:
         steps = max(args.steps, 1)
@@ -333,33 +395,57 @@ def main():
                        "algorithmic_bytes_per_launch": int(rows * CONS_KERNELS[k][2]) * CONS_KERNELS[k][1]} for k in CONS_KERNELS}
         for v in kernels.values():
             v["achieved_gbs"] = v["algorithmic_bytes_per_launch"] / (v["launch_ms"] / 1e3) / 1e9 if v["launch_ms"] > 0 else None
-        # the dominant single kernel of the proof (the two "phase" entries are several launches each: extension transforms included)
-        top = max((k for k in kernels if CONS_KERNELS[k][3]), key=lambda k: kernels[k]["launch_ms"])
-        top_ms, alg_bytes = kernels[top]["launch_ms"], kernels[top]["algorithmic_bytes_per_launch"]
-        achieved = kernels[top]["achieved_gbs"]
+        # The dominant kernel FAMILY by time is the 1024-point NTT pass (`ntt1024_kernel`, ~40 % of a proof); the LDE stage is
+        # nothing but launches of it (the representation change rides on the inverse transform), so its per-launch time is measured
+        # live: stage CUDA-event time / launches in the stage.  It is integer-issue-bound, so the headline fraction is the INT one
+        # (warp instructions from the ncu capture of these very sources / time, against 148 x 4 schedulers x the sampled SM clock);
+        # the HBM fraction of the algorithmic bytes stands beside it.
+        stage_ms = {k: v / steps for k, v in stage_sum.items()}
+        lde_ms, lde_launches = stage_ms.get("lde", 0.0), int(stage_launches.get("lde", 0)) or 1
+        launch_ms = lde_ms / lde_launches
+        alg_bytes = stage_bytes(n)["lde"] / lde_launches
+        hbm_achieved = alg_bytes / (launch_ms / 1e3) / 1e9 if launch_ms > 0 else None
+        clk_mhz = clock_summary.get("sm_mhz") or sm_max
+        int_peak = 148 * 4 * clk_mhz * 1e6 / 1e9          # Gwarp-inst/s: one warp instruction per scheduler per clock
+        fresh = TRAFFIC if TRAFFIC_FRESH else {}
+        lde_cap = fresh.get("stages", {}).get("lde", {})
+        roof = {"kernel": f"ntt1024_kernel (1024-point sub-transform passes of every size-2^20 NTT; the LDE stage = {lde_launches} launches of it per proof)",
+                "launch_ms": launch_ms, "launches_per_step": lde_launches, "algorithmic_bytes_per_launch": int(alg_bytes),
+                "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (hbm_achieved / hbm_peak) if hbm_achieved else None, "peak_source": peak_src},
+                "traffic": None}
+        if lde_cap.get("warp_insts") and launch_ms > 0:
+            wi = lde_cap["warp_insts"] / lde_launches
+            gw = wi / (launch_ms / 1e3) / 1e9
+            roof.update({"bound": "int", "achieved": gw, "peak": int_peak, "unit": "Gwarp-inst/s", "frac": gw / int_peak,
+                         "warp_insts_per_launch": int(wi), "thread_insts_per_element": lde_cap["warp_insts"] * 32 / (TRACE_WIDTH * n * (1 + BLOWUP)) / 2,
+                         "peak_source": f"148 SMs x 4 schedulers x {clk_mhz:.0f} MHz (SM clock sampled during the timed region)",
+                         "pipes": lde_cap.get("pipes"), "traffic": int(lde_cap["dram_bytes"] / lde_launches) if lde_cap.get("dram_bytes") else None,
+                         "captured_at": TRAFFIC.get("_captured_at")})
+        else:   # no ncu capture of these sources: only the HBM view can be stated
+            roof.update({"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (hbm_achieved / hbm_peak) if hbm_achieved else None,
+                         "note": "integer-issue-bound kernel; profiles/traffic.json was not captured from these sources, so no instruction counts are quoted"})
+        roof["constraint_stage"] = {"ms": cons_ms, "kernels": kernels,
+                                    "reference_modmul_per_s": rows * MODMUL_PER_ROW / (cons_ms / 1e3) if cons_ms > 0 else None}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (f63 modular)",
             "data": "synthetic", "config": workload_config(num_tx, world),
             "proofs_per_s": world / (ms_per_step / 1e3), "wall_ms_per_step": wall_ms / steps, "proof_bytes": len(proof),
-            "stage_ms": {k: v / steps for k, v in stage_sum.items()},
+            "stage_ms": stage_ms, "stage_launches": stage_launches,
             "e2e": {"value": (world * num_tx / (e2e_ms / steps / 1e3)) if e2e_ms else None, "unit": UNIT, "ms_per_step": e2e_ms / steps,
-                    "h2d_ms_per_step": e2e_h2d_ms / steps, "h2d_bytes_per_step": int(TRACE_WIDTH * n * 8), "d2h_bytes_per_step": int(len(proof))},
+                    "h2d_ms_per_step": e2e_h2d_ms / steps, "h2d_bytes_per_step": int(TRACE_WIDTH * n * 8), "d2h_bytes_per_step": int(len(proof)),
+                    "host_memory": "page-locked (csg_host_alloc); the copy runs on its own stream under the trace extension"},
+            "e2e_pageable": {"value": (world * num_tx / (e2e_pg_ms / steps / 1e3)) if e2e_pg_ms else None, "unit": UNIT, "ms_per_step": e2e_pg_ms / steps,
+                             "host_memory": "pageable (numpy array): staged through the library's pinned ring by the host threads"},
             "build_trace_and_prove": {"value": (world * num_tx / (wit_ms / steps / 1e3)) if wit_ms else None, "unit": UNIT, "ms_per_step": wit_ms / steps,
                                       "note": "TransactionExample::prove() as a whole: witness generated on the device (csg_build_trace_transaction_device), "
                                               "2.2 KB per transaction H2D, then the proof; the host builder needs ~0.4 s for the same batch"},
             "gpu_launches": launches,
             "clocks": clock_summary,
-            "roofline": {"kernel": kernels[top]["kernel"] + ", 1 launch per proof", "bound": "hbm", "pipes": PIPES.get(top),
-                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                         "peak_source": peak_src, "traffic": TRAFFIC.get(top), "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": top_ms,
-                         "constraint_stage": {"ms": cons_ms, "kernels": kernels,
-                                              "reference_modmul_per_s": rows * MODMUL_PER_ROW / (cons_ms / 1e3) if cons_ms > 0 else None},
-                         "note": "64-bit modular multiply has no native instruction (22 integer instructions, 5-6 per term of a lazily reduced sum): every arithmetic kernel of this path is "
-                                 "integer-pipe-bound, not HBM-bound; profiles/README.md has the ALU/FMA pipe utilisation from ncu"},
+            "roofline": roof,
         }
         try:
-            line["stage_roofline"] = stage_roofline(line["stage_ms"], n, hbm_peak)
+            line["stage_roofline"] = stage_roofline(stage_ms, n, hbm_peak, int_peak, fresh.get("stages"))
         except Exception as e:   # a reporting extra: never lets the bench line go missing
             line["stage_roofline"] = {"error": repr(e)}
         if sh_ms:
@@ -372,11 +458,16 @@ def main():
                 "e2e_ms_per_proof": sh_e2e_ms / steps, "e2e_tx_per_s": num_tx / (sh_e2e_ms / steps / 1e3),
                 "e2e_h2d_bytes_per_rank": int(-(-TRACE_WIDTH // world) * n * 8)}
         if world == 1 and not args.no_cpu_baseline and not args.profile:
-            sample_tx = min(num_tx, 64)
-            sec = cpu_port_run(sample_tx, 1, 0)
-            line["cpu_baseline"] = {"value": sample_tx / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": f"one proof of a {sample_tx}-transaction batch (trace {sample_tx * ROWS_PER_TX} x 94, blowup 8): {sec:.2f} s; "
+            # the CPU port proves the SAME batch once (20-100 s on the box's cores): the baseline at the metric's own config, and
+            # the byte-for-byte check of the timed GPU proof against the oracle, outside every timed region
+            import hashlib
+            sec, cpu_proof = cpu_port_run(num_tx, 1, 0, seed=1000 + rank, want_proof=True)
+            line["cpu_baseline"] = {"value": num_tx / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": f"one proof of the same {num_tx}-transaction batch (trace {num_tx * ROWS_PER_TX} x 94, blowup 8): {sec:.2f} s; "
                                               "C/OpenMP port of the path (oracle/), the Rust reference cannot be built here"}
+            line["parity"] = {"gpu_proof_sha256": hashlib.sha256(proof).hexdigest(), "oracle_proof_sha256": hashlib.sha256(cpu_proof).hexdigest(),
+                              "identical": proof == cpu_proof, "oracle": "oracle/ (C restatement; parity unpinned against the Rust reference)"}
+            assert proof == cpu_proof, "the timed GPU proof differs from the CPU oracle's proof of the same batch"
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -49,10 +49,14 @@ class ShardPlan(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d", "lde", "commit_trace", "constraints", "composition", "ood_deep", "fri", "queries", "total")] + \
-               [("kernel_launches", C.c_uint64)] + [(n, C.c_float) for n in ("cons_rescue", "cons_ecc_banks", "cons_ecc_final", "cons_rest", "comm", "cons_ecc_low")]
+               [("kernel_launches", C.c_uint64)] + [(n, C.c_float) for n in ("cons_rescue", "cons_ecc_banks", "cons_ecc_final", "cons_rest", "comm", "cons_ecc_low")] + \
+               [("stage_launches", C.c_uint32 * 7)]
+    STAGES = ("lde", "commit_trace", "constraints", "composition", "ood_deep", "fri", "queries")
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "stage_launches"}
+        d["stage_launches"] = dict(zip(self.STAGES, [int(v) for v in self.stage_launches]))
+        return d
 
 
 def build(force: bool = False) -> Path:

@@ -29,6 +29,7 @@ struct PassArgs {
     const fe *postA, *postB; unsigned long long post_bz;  // output (e, lane) *= postA[e] * postB[lane]
     unsigned tw_logn;                              // != 0: output (e, lane) *= w_{2^tw_logn}^(+-e*lane)
     int use_scalar; fe scalar;                     // output *= scalar
+    int clamp_in;                                  // input words are arbitrary u64 (a caller's trace): bring them below 2p first
 };
 
 __device__ __forceinline__ fe root_pow(const fe *W, unsigned logW, unsigned logm, unsigned long long e, int inverse) {
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
         if (lane0 + l < a.nlanes) {
             const unsigned long long m = e * a.in_se + (lane0 + l) * a.in_sl;
             v = in[m];
+            if (a.clamp_in && v >= 2 * P) v -= 2 * P;
             if (a.preFull) v = mul(v, a.preFull[blockIdx.z * a.pre_full_bz + m]);
             else {
                 if (preA) v = mul(v, preA[e]);
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(32 * F_LANES, 512 / (32 * F_LANES)) ntt1024_ke
     const bool chain_out = a.tw_logn && !a.postA && !a.postB && !a.use_scalar;   // pass A: the output twiddle is a per-thread geometric chain
     fe *PF = T2 + 1024;                                                      // its seeds, [3][NTH]
     auto scaled = [&](fe v, unsigned e, unsigned l) -> fe {   // the input scaling of element e of lane l of this tile
+        if (a.clamp_in && v >= 2 * P) v -= 2 * P;
         if (fold) return mul(v, preA[e]);
         if (a.preFull) return mul(v, a.preFull[blockIdx.z * a.pre_full_bz + e * a.in_se + (lane0 + l) * a.in_sl]);
         if (preA) v = mul(v, preA[e]);
@@ -407,23 +410,25 @@ void RootTable::build(unsigned logn_, Stream &st) {
 }
 
 void intt_columns(const RootTable &rt, NttScratch &sc, const fe *in, size_t in_stride, fe *out, size_t out_stride, size_t ncols,
-                  unsigned logn, Stream &st) {
+                  unsigned logn, Stream &st, fe out_factor, bool raw_input) {
     if (logn > rt.logn) throw std::runtime_error("root table too small");
     const size_t n = (size_t)1 << logn;
-    const fe ninv = inv(to_mont(n % P));
+    // the transform is linear: a constant factor on the input (the representation change of a caller's trace) rides on the 1/n scaling
+    const fe ninv = out_factor ? mul(inv(to_mont(n % P)), out_factor) : inv(to_mont(n % P));
     Split sp = split_of(logn);
     PassArgs a{};
     a.W = rt.W.p; a.logW = rt.logn; a.inverse = 1;
     if (sp.l2 == 0) {  // single pass: lanes are columns
         a.in = in; a.out = out; a.logS = logn; a.logT = lanes_log(logn, 31); a.nlanes = (unsigned)ncols;
         a.in_se = 1; a.in_sl = in_stride; a.out_se = 1; a.out_sl = out_stride;
-        a.use_scalar = 1; a.scalar = ninv;
+        a.use_scalar = 1; a.scalar = ninv; a.clamp_in = raw_input;
         launch_pass(a, 1, 1, st);
         return;
     }
     const size_t n1 = (size_t)1 << sp.l1, n2 = (size_t)1 << sp.l2;
     sc.tmp.reserve(ncols * n);
     // pass A: sub-transforms over i1 (stride n2) for T adjacent i2, twiddle w_n^-(k1*i2), tmp[k1*n2 + i2]
+    a.clamp_in = raw_input;
     a.in = in; a.out = sc.tmp.p; a.logS = sp.l1; a.logT = lanes_log(sp.l1, sp.l2); a.nlanes = (unsigned)n2;
     a.in_se = n2; a.in_sl = 1; a.out_se = n2; a.out_sl = 1; a.in_by = in_stride; a.out_by = n; a.tw_logn = logn;
     launch_pass(a, (unsigned)ncols, 1, st);

@@ -29,9 +29,11 @@ struct NttScratch {
     DBuf<fe> shifts;  // coset shifts (device copy)
 };
 
-// coefficients: out[c*out_stride + m], from evaluations in[c*in_stride + i] over <w_n>; includes the 1/n scaling
+// coefficients: out[c*out_stride + m], from evaluations in[c*in_stride + i] over <w_n>; includes the 1/n scaling.
+// out_factor != 0: every output is also multiplied by it (R^2 turns a transform of canonical words into Montgomery-form
+// coefficients at no cost); raw_input: the words come from a caller and may be anything below 2^64 (brought below 2p on load)
 void intt_columns(const RootTable &rt, NttScratch &sc, const fe *in, size_t in_stride, fe *out, size_t out_stride, size_t ncols,
-                  unsigned logn, Stream &st);
+                  unsigned logn, Stream &st, fe out_factor = 0, bool raw_input = false);
 // evaluations of each column polynomial over the cosets shift[z]*<w_n>:
 //   out[z*out_coset_stride + c*out_col_stride + i] = sum_m coeffs[c*in_stride + m] * shift[z]^m * w_n^(m*i)
 void coset_ntt_columns(const RootTable &rt, NttScratch &sc, const fe *coeffs, size_t in_stride, fe *out, size_t out_col_stride,

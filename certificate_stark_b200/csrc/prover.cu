@@ -48,11 +48,14 @@ class Timer {   // device time of a stage, CUDA events on the proving stream; th
     ~Timer() { if (a_) { cudaEventDestroy(a_); cudaEventDestroy(b_); } }
     void start(Stream &st) {
         if (!a_) { CSG_CUDA(cudaEventCreate(&a_)); CSG_CUDA(cudaEventCreate(&b_)); }
+        l0_ = st.launches;
         CSG_CUDA(cudaEventRecord(a_, st.s));
     }
-    float stop(Stream &st) { CSG_CUDA(cudaEventRecord(b_, st.s)); CSG_CUDA(cudaEventSynchronize(b_)); float ms = 0; CSG_CUDA(cudaEventElapsedTime(&ms, a_, b_)); return ms; }
+    unsigned launches = 0;   // kernels launched between the last start() and stop()
+    float stop(Stream &st) { launches = (unsigned)(st.launches - l0_); CSG_CUDA(cudaEventRecord(b_, st.s)); CSG_CUDA(cudaEventSynchronize(b_)); float ms = 0; CSG_CUDA(cudaEventElapsedTime(&ms, a_, b_)); return ms; }
   private:
     cudaEvent_t a_ = nullptr, b_ = nullptr;
+    unsigned long long l0_ = 0;
 };
 
 }  // namespace
@@ -316,8 +319,9 @@ struct csg_ctx {
                 if (c0 + CHUNK >= c_hi) CSG_CUDA(cudaEventRecord(h2d_b, copy_stream));
                 CSG_CUDA(cudaStreamWaitEvent(st.s, chunk_ev[k], 0));
             }
-            to_montgomery(d_io.p + c0 * n, d_polys.p + c0 * n, nc * n, st, trace_repr == CSG_REPR_MONTGOMERY);
-            intt_columns(roots, ntt, d_polys.p + c0 * n, n, scratch.p + c0 * n, n, nc, logn, st);
+            // the representation change of the caller's words costs nothing: interpolation is linear, so the factor R^2 of
+            // "canonical -> Montgomery" joins the 1/n scaling of the inverse transform (Montgomery words need no factor)
+            intt_columns(roots, ntt, d_io.p + c0 * n, n, scratch.p + c0 * n, n, nc, logn, st, trace_repr == CSG_REPR_MONTGOMERY ? 0 : R2, true);
             if (G == 1) coset_ntt_columns(roots, ntt, scratch.p + c0 * n, n, d_lde.p + c0 * n, n, w * n, nc, logn, lde_tables, st);
         }
         if (G > 1) {
@@ -335,7 +339,7 @@ struct csg_ctx {
             if (c_hi < w) coset_ntt_columns(roots, ntt, scratch.p + c_hi * n, n, d_lde.p + c_hi * n, n, w * n, w - c_hi, logn, lde_tables, st);
         }
         std::swap(d_polys.p, scratch.p); std::swap(d_polys.n, scratch.n);   // d_polys = coefficients
-        tm.lde = t.stop(st);
+        tm.lde = t.stop(st); tm.stage_launches[0] = t.launches;
         if (host) {   // the copy ran under the extension: its own duration (first byte .. last byte), not time added to the proof
             nfri = 0; tm.h2d = 0;
             if (c_hi > c_lo) { CSG_CUDA(cudaEventSynchronize(h2d_b)); CSG_CUDA(cudaEventElapsedTime(&tm.h2d, h2d_a, h2d_b)); }
@@ -343,7 +347,7 @@ struct csg_ctx {
         t.start(st);
         commit_rows(d_lde.p, (unsigned)w, w * n, d_tnodes);
         download_root(d_tnodes, root);
-        tm.commit_trace = t.stop(st);
+        tm.commit_trace = t.stop(st); tm.stage_launches[1] = t.launches;
         stage = S_COMMITTED;
     }
 
@@ -462,6 +466,7 @@ struct csg_ctx {
         else for (auto &e : cons_ev) CSG_CUDA(cudaEventRecord(e, st.s));
         const float ms = t.stop(st);   // also keeps `polys` alive until the copy has completed
         tm.constraints = plane ? tm.constraints + ms : ms;
+        tm.stage_launches[2] = plane ? tm.stage_launches[2] + t.launches : t.launches;
         float *parts_ms[4] = {&tm.cons_rescue, &tm.cons_ecc_banks, &tm.cons_ecc_final, &tm.cons_rest};
         for (int k = 0; k < 4; k++) { float pm = 0; CSG_CUDA(cudaEventElapsedTime(&pm, cons_ev[k], cons_ev[k + 1])); *parts_ms[k] = plane ? *parts_ms[k] + pm : pm; }
         { float pm = 0; CSG_CUDA(cudaEventElapsedTime(&pm, cons_ev[1], cons_ev[5])); tm.cons_ecc_low = plane ? tm.cons_ecc_low + pm : pm; }
@@ -540,7 +545,7 @@ struct csg_ctx {
         coset_ntt_columns(roots, ntt, d_cpolys.p, n, d_clde.p, n, cw * n, cw, logn, lde_shift.data(), bl, st);
         commit_rows(d_clde.p, (unsigned)cw, cw * n, d_cnodes);
         download_root(d_cnodes, root);
-        tm.composition = t.stop(st);
+        tm.composition = t.stop(st); tm.stage_launches[3] = t.launches;
         stage = S_COMPOSED;
     }
 
@@ -559,7 +564,7 @@ struct csg_ctx {
         const fe zm = f63::pow(z, ce);
         ood_comp.resize(ce);
         eval_polys_at(d_cpolys.p, n, ce, n, &zm, 1, ood_comp.data(), scratch2, st);
-        tm.ood_deep = t.stop(st);
+        tm.ood_deep = t.stop(st); tm.stage_launches[4] = t.launches;
         stage = S_OOD;
     }
     void deep(const fe *trace_ab, const fe *comp_d, fe lambda, fe mu) {
@@ -592,8 +597,8 @@ struct csg_ctx {
         if (fri.empty()) fri.emplace_back(new FriLayer());
         nfri = 1;
         fri[0]->evals = d_deep.p; fri[0]->m = lde_n; fri[0]->committed = false;
-        tm.ood_deep += t.stop(st);   // also keeps coef alive until the copies have completed
-        tm.fri = 0;
+        tm.ood_deep += t.stop(st); tm.stage_launches[4] += t.launches;   // also keeps coef alive until the copies have completed
+        tm.fri = 0; tm.stage_launches[5] = 0;
         stage = S_DEEP;
     }
 
@@ -628,7 +633,7 @@ struct csg_ctx {
                 basis = x_mul(d, basis, phi);
             }
         }
-        tm.ood_deep = t.stop(st);
+        tm.ood_deep = t.stop(st); tm.stage_launches[4] = t.launches;
         stage = S_OOD;
     }
     void deep_x(const xe *trace_ab, const xe *comp_d, const xe &lambda, const xe &mu) {
@@ -674,8 +679,8 @@ struct csg_ctx {
         if (fri.empty()) fri.emplace_back(new FriLayer());
         nfri = 1;
         fri[0]->evals = d_deep.p; fri[0]->m = lde_n; fri[0]->committed = false;
-        tm.ood_deep += t.stop(st);
-        tm.fri = 0;
+        tm.ood_deep += t.stop(st); tm.stage_launches[4] += t.launches;
+        tm.fri = 0; tm.stage_launches[5] = 0;
         stage = S_DEEP;
     }
 
@@ -692,7 +697,7 @@ struct csg_ctx {
         merkle_build(L.nodes.p, q, (int)opt.hash_fn, st);
         download_root(L.nodes, root);
         L.committed = true;
-        tm.fri += t.stop(st);
+        tm.fri += t.stop(st); tm.stage_launches[5] += t.launches;
     }
     void fri_fold(fe alpha) { fri_fold_x(x_from(alpha)); }
     void fri_fold_x(const xe &alpha) {
@@ -719,7 +724,7 @@ struct csg_ctx {
         else { FoldArgsX ax{a, alpha, d}; fri_fold4_ext(L.evals, m, m, roots.W.p, ax, N.owned.p, q, st); }
         N.evals = N.owned.p; N.m = q; N.committed = false;
         nfri++;
-        tm.fri += t.stop(st);
+        tm.fri += t.stop(st); tm.stage_launches[5] += t.launches;
     }
     size_t num_fri_folds() const { size_t r = 0, d = lde_n; while (d > opt.fri_max_remainder_size) { d /= 4; r++; } return r; }
 
@@ -908,7 +913,7 @@ struct csg_ctx {
         for (size_t k = 0; k < rem_len; k++) pf.u64(rows[rem_off + k]);
         pf.u8(1);
         pf.u64(nonce);
-        tm.queries = tq.stop(st);
+        tm.queries = tq.stop(st); tm.stage_launches[6] = tq.launches;
         tm.kernel_launches = st.launches - launches0;
         tm.comm = comm_ms();
         tm.total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1072,7 +1077,7 @@ int csg_prove_trace(csg_ctx *ctx, const uint64_t *trace, int repr, uint8_t **pro
 // page-locked host memory for traces: the H2D copy of csg_prove / csg_prove_trace then runs at link speed under the extension
 void *csg_host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (!bytes || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (!bytes || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
 void csg_host_free(void *p) { if (p) cudaFreeHost(p); }

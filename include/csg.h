@@ -154,6 +154,9 @@ typedef struct {
     float cons_rescue, cons_ecc_banks, cons_ecc_final, cons_rest;
     float comm; /* sharded proofs: time inside the exchanges (all-gathers, row sums), already included in the stage times */
     float cons_ecc_low; /* part of cons_ecc_banks: the curve-formula kernel on the even cosets alone (0 when the split is off) */
+    /* kernels launched inside each stage, in the order lde, commit_trace, constraints, composition, ood_deep, fri, queries:
+     * lets a profiler's launch list of one proof be cut into stages */
+    uint32_t stage_launches[7];
 } csg_timings;
 int csg_get_timings(const csg_ctx *ctx, csg_timings *out);
 /* CUDA events on the proving stream around an arbitrary sequence of calls (bench.py's timed region) */

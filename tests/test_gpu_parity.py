@@ -251,3 +251,22 @@ def test_degenerate_shapes_fail_cleanly(ctx, csg):
     # the context stays usable after errors
     t, p = csg.build_range_trace(123)
     assert csg.verify(csg.AIR_RANGE, p, ctx.prove(csg.AIR_RANGE, t, p, csg.ProofOptions())) == 0
+
+
+def test_independent_python_witnesses_prove_identically(ctx, oracle, csg):
+    # witnesses from oracle/pyair.py (second, independent restatement: own metadata, tree, signing and trace layout; tests/
+    # test_air_independent.py) through the GPU prover: the bytes must be the C oracle's, and both verifiers accept
+    from oracle import pyair
+    cols = lambda rows: np.ascontiguousarray(np.array(rows, dtype=np.uint64).T)      # noqa: E731
+    batch = pyair.TransactionBatch(seed=13, num_tx=2)
+    cases = [(csg.AIR_TRANSACTION, batch.transaction_trace(), batch.pub_inputs(), 8),
+             (csg.AIR_MERKLE_UPDATE, batch.merkle_update_trace(), batch.pub_inputs(), 8),
+             (csg.AIR_SCHNORR, *pyair.schnorr_batch(seed=14, num_sig=2), 8),
+             (csg.AIR_SCHNORR, *pyair.schnorr_batch(seed=15, num_sig=1), 8),
+             (csg.AIR_RANGE, *pyair.range_trace(987654321987), 8),
+             (csg.AIR_RESCUE, *pyair.rescue_trace(list(range(42, 49)), 32), 4)]
+    for air, rows, pub, blowup in cases:
+        trace, pub = cols(rows), np.array(pub, dtype=np.uint64)
+        got, want = prove_both(ctx, oracle, csg, air, trace, pub, blowup=blowup)
+        assert_same_proof(got, want)
+        assert csg.verify(air, pub, got) == 0 and oracle.verify(air, pub, got) == 0

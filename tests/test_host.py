@@ -26,15 +26,16 @@ def test_ctypes_mirrors_match_the_header_layout(csg, tmp_path):
     # the structs that cross the C ABI by value or by pointer: size and the offset of the last field, as gcc lays out include/csg.h
     src = tmp_path / "layout.c"
     src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "csg.h"\n'
-                   'int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(csg_options), sizeof(csg_shard_plan), sizeof(csg_timings), '
-                   'offsetof(csg_timings, kernel_launches), offsetof(csg_timings, cons_ecc_low)); return 0; }\n')
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(csg_options), sizeof(csg_shard_plan), sizeof(csg_timings), '
+                   'offsetof(csg_timings, kernel_launches), offsetof(csg_timings, cons_ecc_low), offsetof(csg_timings, stage_launches)); return 0; }\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)])
-    opt, plan, tim, off_launches, off_last = map(int, subprocess.check_output([str(exe)]).split())
+    opt, plan, tim, off_launches, off_last, off_stage = map(int, subprocess.check_output([str(exe)]).split())
     assert C.sizeof(csg.ProofOptions) == opt
     assert C.sizeof(csg.ShardPlan) == plan
     assert C.sizeof(csg.Timings) == tim
     assert csg.Timings.kernel_launches.offset == off_launches and csg.Timings.cons_ecc_low.offset == off_last
+    assert csg.Timings.stage_launches.offset == off_stage
 
 
 def test_no_cpu_fallback(csg):
