@@ -93,6 +93,43 @@ template <int KIND> __global__ void __launch_bounds__(1024, 1) k(uint64_t *out, 
     if (s == 0x12345678u) out[threadIdx.x] = s;
 }
 
+// lazily reduced multiply-accumulate chains (field.cuh acc128): NACC independent accumulators per thread, each fed ITER terms
+template <int NACC> __global__ void __launch_bounds__(1024, 1) kmac(uint64_t *out, uint64_t seed) {
+    acc128 acc[NACC];
+    uint64_t a[NACC], b = (seed * 7 + threadIdx.x) % P;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) a[i] = (seed + threadIdx.x * 16 + i) % P;
+    for (int it = 0; it < ITER / 8; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+#pragma unroll
+            for (int i = 0; i < NACC; i++) acc[i].mac(a[i], b);
+            b += 0x9e3779b97f4a7c15ULL;
+            b &= 0x3fffffffffffffffULL;
+        }
+#pragma unroll
+        for (int i = 0; i < NACC; i++) { a[i] = acc[i].reduce(); acc[i] = acc128(); }   // 8 terms, then one reduction (the MDS rows have 14)
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) s ^= a[i];
+    if (s == 0x12345678u) out[threadIdx.x] = s;
+}
+// the butterfly kernels again with fewer resident warps: THREADS per CTA, one CTA per SM
+template <int V, int THREADS> __global__ void __launch_bounds__(THREADS, 1) kbo(uint64_t *out, uint64_t seed, uint32_t one) {
+    uint64_t x[8], y[8], w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x[i] = (seed + threadIdx.x * 16 + i) % P; y[i] = (seed * 3 + i + threadIdx.x) % P; w[i] = (seed * 5 + 7 * i + 1) % P; }
+    for (int it = 0; it < ITER; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) bfly<V>(x[i], y[i], w[i], one);
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= x[i] ^ y[i];
+    if (s == 0x12345678u) out[threadIdx.x] = s;
+}
+
 template <class F> int timed(const char *name, F launch) {
     cudaEvent_t a, b;
     CHK(cudaEventCreate(&a)); CHK(cudaEventCreate(&b));
@@ -121,6 +158,13 @@ int main() {
     RUNK(0) RUNK(1) RUNK(2) RUNK(3) RUNK(4) RUNK(5) RUNK(6) RUNK(7) RUNK(8) RUNK(9) RUNK(10) RUNK(11) RUNK(12) RUNK(13)
 #define RUNB(V) timed("butterfly " #V, [&](int r) { kb<V><<<s, 1024>>>(d, 12345 + r, 1); });
     RUNB(0) RUNB(1) RUNB(2) RUNB(3)
+    timed("mac x2", [&](int r) { kmac<2><<<s, 1024>>>(d, 12345 + r); });
+    timed("mac x4", [&](int r) { kmac<4><<<s, 1024>>>(d, 12345 + r); });
+    timed("mac x8", [&](int r) { kmac<8><<<s, 1024>>>(d, 12345 + r); });
+    timed("bfly0 w4", [&](int r) { kbo<0, 512><<<s, 512>>>(d, 12345 + r, 1); });
+    timed("bfly0 w2", [&](int r) { kbo<0, 256><<<s, 256>>>(d, 12345 + r, 1); });
+    timed("bfly0 w1", [&](int r) { kbo<0, 128><<<s, 128>>>(d, 12345 + r, 1); });
+    timed("bfly3 w4", [&](int r) { kbo<3, 512><<<s, 512>>>(d, 12345 + r, 1); });
     CHK(cudaDeviceSynchronize());
     return 0;
 }
