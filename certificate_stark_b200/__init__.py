@@ -50,7 +50,7 @@ class ShardPlan(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d", "lde", "commit_trace", "constraints", "composition", "ood_deep", "fri", "queries", "total")] + \
                [("kernel_launches", C.c_uint64)] + [(n, C.c_float) for n in ("cons_rescue", "cons_ecc_banks", "cons_ecc_final", "cons_rest", "comm", "cons_ecc_low")] + \
-               [("stage_launches", C.c_uint32 * 7)]
+               [("stage_launches", C.c_uint32 * 7), ("batch_build", C.c_float)]
     STAGES = ("lde", "commit_trace", "constraints", "composition", "ood_deep", "fri", "queries")
 
     def as_dict(self):
@@ -108,6 +108,8 @@ def lib() -> C.CDLL:
         "csg_tx_batch_roots": (None, [vp, _u64p, _u64p]),
         "csg_build_trace_transaction": (C.c_int, [vp, _u64p, _u64p]),
         "csg_build_trace_transaction_device": (C.c_int, [vp, vp]), "csg_download_trace": (C.c_int, [vp, _u64p]),
+        "csg_tx_batch_build_device": (C.c_int, [vp, C.c_uint64, C.c_size_t, C.c_uint, _u64p]),
+        "csg_build_trace_transaction_resident": (C.c_int, [vp]), "csg_download_batch_records": (C.c_int, [vp, _u64p, C.c_size_t]),
         "csg_tx_batch_pack": (C.c_size_t, [vp, _u64p]), "csg_tx_batch_depth": (C.c_uint, [vp]), "csg_build_trace_merkle_update": (C.c_int, [vp, _u64p, _u64p]),
         "csg_build_trace_merkle_init": (C.c_int, [_u64p, _u64p, C.c_uint64, _u64p, _u64p]),
         "csg_sig_batch_new": (vp, [C.c_uint64, C.c_size_t]), "csg_sig_batch_free": (None, [vp]), "csg_sig_batch_size": (C.c_size_t, [vp]),
@@ -250,6 +252,21 @@ class Context:
     def build_transaction_trace(self, batch: "TransactionBatch"):
         """TransactionProver::build_trace on the device (witness_gen.cu): the trace never exists in host memory"""
         self._check(lib().csg_build_trace_transaction_device(self._h, batch._h))
+
+    def build_batch(self, seed: int, num_tx: int, tree_depth: int = 15) -> np.ndarray:
+        """TransactionMetadata::build_random on the device (batch_gen.cu): returns the public inputs; the packed records stay in HBM"""
+        pub = np.zeros(14, dtype=np.uint64)
+        self._check(lib().csg_tx_batch_build_device(self._h, seed, num_tx, tree_depth, _p64(pub)))
+        return pub
+
+    def build_transaction_trace_resident(self):
+        """build_trace on the device from the records left by build_batch"""
+        self._check(lib().csg_build_trace_transaction_resident(self._h))
+
+    def download_batch_records(self, num_tx: int) -> np.ndarray:
+        out = np.zeros((num_tx, 276), dtype=np.uint64)
+        self._check(lib().csg_download_batch_records(self._h, _p64(out), out.size))
+        return out
 
     def download_trace(self, width: int, trace_len: int) -> np.ndarray:
         out = np.empty((width, trace_len), dtype=np.uint64)
@@ -442,6 +459,12 @@ class TransactionBatch:
             raise CsgError("number of transactions must be a power of two")
         return trace, pub
 
+    def packed_records(self) -> np.ndarray:
+        """the per-transfer records the device witness builder consumes (csg_tx_batch_pack): (num_tx, 276) words"""
+        out = np.zeros((self.num_tx, 276), dtype=np.uint64)
+        lib().csg_tx_batch_pack(self._h, _p64(out))
+        return out
+
     def merkle_update_trace(self):
         """MerkleProver::build_trace (src/merkle/update/prover.rs:37-80) -> (trace (65, 512*num_tx), pub[14])"""
         trace, pub = np.zeros((65, 512 * self.num_tx), dtype=np.uint64), np.zeros(14, dtype=np.uint64)
@@ -483,25 +506,32 @@ class TransactionExample:
     """TransactionExample::{new, prove} (src/lib.rs:92-141): a batch of transactions and the proof of their state transition.
     `verify` runs on the host, as winterfell::verify does for the reference (src/lib.rs:144-150)."""
 
-    def __init__(self, options: ProofOptions, num_transactions: int, seed: int = 1, device: int = 0):
+    def __init__(self, options: ProofOptions, num_transactions: int, seed: int = 1, device: int = 0, batch_on_device: bool = False):
         if num_transactions < 1 or num_transactions & (num_transactions - 1):
             raise CsgError("number of transactions must be a power of 2")  # src/lib.rs:100-103
-        self.options = options
-        self.batch = TransactionBatch(seed, num_transactions)
+        self.options, self.seed, self.num_transactions = options, seed, num_transactions
+        # TransactionMetadata::build_random (src/lib.rs:111): on the host (OpenMP, seconds for large batches) or by kernels at prove() time
+        self.batch = None if batch_on_device else TransactionBatch(seed, num_transactions)
         self.ctx = Context(device)
         self.pub_inputs = None
 
     def verify(self, proof: bytes) -> bool:
         """TransactionExample::verify (src/lib.rs:144-150)"""
-        return verify(AIR_TRANSACTION, self.batch.public_inputs(), proof, self.options) == 0
+        pub = self.pub_inputs if self.batch is None else self.batch.public_inputs()
+        return verify(AIR_TRANSACTION, pub, proof, self.options) == 0
 
     def verify_with_wrong_inputs(self, proof: bytes) -> bool:
         """TransactionExample::verify_with_wrong_inputs (src/lib.rs:152-161): every limb of the final root replaced by its first"""
-        pub = self.batch.public_inputs()
+        pub = np.array(self.pub_inputs if self.batch is None else self.batch.public_inputs())
         pub[7:] = pub[7]
         return verify(AIR_TRANSACTION, pub, proof, self.options) == 0
 
     def prove(self, witness_on_device: bool = True) -> bytes:
+        if self.batch is None:                               # metadata, witness and proof all on the device
+            self.pub_inputs = pub = self.ctx.build_batch(self.seed, self.num_transactions)
+            self.ctx.set_air(AIR_TRANSACTION, 1024 * self.num_transactions, pub, self.options)
+            self.ctx.build_transaction_trace_resident()
+            return self.ctx.prove_loaded()
         if not witness_on_device:
             trace, pub = self.batch.transaction_trace()      # prover.build_trace(&tx_metadata)   src/lib.rs:130  (host)
             self.pub_inputs = pub

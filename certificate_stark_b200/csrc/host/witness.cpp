@@ -14,9 +14,13 @@
 #include <cstring>
 #include <vector>
 
+#include <map>
+#include <stdexcept>
+
 #include "../../../include/csg.h"
 #include "../ecc.cuh"
 #include "../rescue.cuh"
+#include "batch_plan.hpp"
 
 using f63::fe;
 
@@ -227,7 +231,125 @@ void fill_fragment(uint64_t *trace, size_t total_len, size_t width, size_t row0,
         for (size_t c = 0; c < width; c++) trace[c * total_len + row0 + i + 1] = f63::from_mont(st[c]);
     }
 }
+// ---- the seeded draws of TransactionMetadata::build_random (src/lib.rs:235-464), with no hashing: shared by the host builder
+// below and by the plan of the device-side builder
+struct BatchDraws {
+    std::vector<size_t> created; std::vector<Account> created_values;   // initial accounts in draw order (a slot may repeat: the last one stays)
+    std::vector<size_t> s_idx, r_idx;
+    std::vector<Account> s_old, r_old, s_new, r_new;                     // the two leaves before and after each transfer
+    std::vector<fe> deltas;
+    std::vector<unsigned> s_sk;
+    std::vector<uint64_t> sig_seeds;
+};
+BatchDraws draw_batch(uint64_t seed, size_t num_tx, unsigned tree_depth) {
+    SplitMix64 rng{seed};
+    BatchDraws D;
+    const size_t tree_size = (size_t)1 << tree_depth;
+    fe pk[4][12];
+    for (unsigned k = 1; k <= 3; k++) { U256 s = {{k, 0, 0, 0}}; to_affine(scalar_mul_generator(s), pk[k]); }
+    std::vector<unsigned> skeys(tree_size, 0);
+    std::vector<Account> values(tree_size); for (auto &v : values) v.fill(0);
+    auto new_account = [&](size_t idx) {
+        unsigned sk = 1 + rng.next() % 3; skeys[idx] = sk;
+        Account a;
+        for (int i = 0; i < 12; i++) a[i] = pk[sk][i];
+        a[12] = f63::to_mont(rng.next() % f63::P); a[13] = f63::to_mont(rng.next() % f63::P);
+        values[idx] = a; D.created.push_back(idx); D.created_values.push_back(a);
+    };
+    D.s_idx.resize(num_tx); D.r_idx.resize(num_tx);
+    for (size_t t = 0; t < num_tx; t++) { D.s_idx[t] = rng.next() % tree_size; new_account(D.s_idx[t]); }
+    for (size_t t = 0; t < num_tx; t++) {
+        size_t r = rng.next() % tree_size;
+        while (r == D.s_idx[t]) r = rng.next() % tree_size;
+        D.r_idx[t] = r;
+        if (!skeys[r]) new_account(r);
+    }
+    for (size_t t = 0; t < num_tx; t++) {
+        const size_t si = D.s_idx[t], ri = D.r_idx[t];
+        uint64_t sb = f63::from_mont(values[si][12]), rb = f63::from_mont(values[ri][12]);
+        uint64_t bound = std::min(sb, UINT64_MAX - rb);
+        fe delta = f63::to_mont((rng.next() % (bound ? bound : 1)) % f63::P);
+        D.s_sk.push_back(skeys[si]); D.s_old.push_back(values[si]); D.r_old.push_back(values[ri]); D.deltas.push_back(delta);
+        values[si][12] = f63::sub(values[si][12], delta); values[si][13] = f63::add(values[si][13], f63::ONE);
+        values[ri][12] = f63::add(values[ri][12], delta);
+        D.s_new.push_back(values[si]); D.r_new.push_back(values[ri]);
+    }
+    D.sig_seeds.resize(num_tx);
+    for (auto &s : D.sig_seeds) s = rng.next();
+    return D;
+}
 }  // namespace
+
+// the tree's history as merge records (batch_plan.hpp): the AccountTree above, with record ids in place of hashes
+csg::BatchPlan csg::plan_tx_batch(uint64_t seed, size_t num_tx, unsigned tree_depth) {
+    if (!num_tx || tree_depth < 1 || tree_depth > 15 || ((tree_depth + 1) & tree_depth)) throw std::invalid_argument("bad transaction batch parameters");
+    const BatchDraws D = draw_batch(seed, num_tx, tree_depth);
+    BatchPlan P;
+    P.depth = tree_depth; P.ntx = num_tx;
+    const size_t nev = 2 * num_tx;
+    // time 0: the last account drawn for each slot, then the set of touched nodes level by level
+    std::vector<std::map<size_t, int32_t>> last(tree_depth + 1);   // node index -> latest record id, per level
+    std::map<size_t, size_t> base_leaf;                              // slot -> index into created (last wins)
+    for (size_t k = 0; k < D.created.size(); k++) base_leaf[D.created[k]] = k;
+    P.nbase.assign(tree_depth + 1, 0);
+    P.nbase[0] = (uint32_t)base_leaf.size();
+    std::vector<std::vector<size_t>> base_nodes(tree_depth + 1);
+    for (auto &kv : base_leaf) base_nodes[0].push_back(kv.first);
+    for (unsigned l = 1; l <= tree_depth; l++) {
+        for (size_t i : base_nodes[l - 1]) if (base_nodes[l].empty() || base_nodes[l].back() != (i >> 1)) base_nodes[l].push_back(i >> 1);   // sorted input: duplicates are adjacent
+        P.nbase[l] = (uint32_t)base_nodes[l].size();
+    }
+    P.level_off.assign(tree_depth + 2, 0);
+    for (unsigned l = 0; l <= tree_depth; l++) P.level_off[l + 1] = P.level_off[l] + P.nbase[l] + (uint32_t)nev;
+    const size_t total = P.level_off[tree_depth + 1];
+    P.left.assign(total, 0); P.right.assign(total, 0);
+    P.accounts.resize((size_t)14 * (P.nbase[0] + nev));
+    {
+        size_t k = 0;
+        for (auto &kv : base_leaf) { memcpy(&P.accounts[14 * k], D.created_values[kv.second].data(), 14 * sizeof(fe)); last[0][kv.first] = (int32_t)(P.level_off[0] + k); k++; }
+    }
+    auto ref = [&](unsigned level, size_t node) -> int32_t { auto it = last[level].find(node); return it == last[level].end() ? -(int32_t)(level + 1) : it->second; };
+    for (unsigned l = 1; l <= tree_depth; l++)
+        for (size_t k = 0; k < base_nodes[l].size(); k++) {
+            const size_t node = base_nodes[l][k];
+            const int32_t id = (int32_t)(P.level_off[l] + k);
+            P.left[id] = ref(l - 1, 2 * node); P.right[id] = ref(l - 1, 2 * node + 1);
+            last[l][node] = id;
+        }
+    // the update events in time order
+    P.tx_words.resize((size_t)BatchPlan::TX_WORDS * num_tx); P.tx_refs.resize((size_t)BatchPlan::TX_REFS * num_tx);
+    auto path = [&](size_t leaf, int32_t *out) {   // [leaf version, sibling version at level 0, 1, ...] (winterfell MerkleTree::prove)
+        out[0] = ref(0, leaf);
+        for (unsigned l = 0; l < tree_depth; l++) out[1 + l] = ref(l, (leaf >> l) ^ 1);
+        for (unsigned l = tree_depth + 1; l < 16; l++) out[l] = -1;
+    };
+    auto update = [&](size_t ev, size_t leaf, const Account &value) {
+        memcpy(&P.accounts[14 * (P.nbase[0] + ev)], value.data(), 14 * sizeof(fe));
+        for (unsigned l = 0; l <= tree_depth; l++) {
+            const size_t node = leaf >> l;
+            const int32_t id = (int32_t)(P.level_off[l] + P.nbase[l] + ev);
+            if (l) {   // the child on the path was just written; the other one is whatever version is current
+                const size_t child = leaf >> (l - 1);
+                const int32_t own = (int32_t)(P.level_off[l - 1] + P.nbase[l - 1] + ev), other = ref(l - 1, child ^ 1);
+                P.left[id] = (child & 1) ? other : own; P.right[id] = (child & 1) ? own : other;
+            }
+            last[l][node] = id;
+        }
+    };
+    for (size_t t = 0; t < num_tx; t++) {
+        uint64_t *w = &P.tx_words[(size_t)BatchPlan::TX_WORDS * t];
+        int32_t *r = &P.tx_refs[(size_t)BatchPlan::TX_REFS * t];
+        memcpy(w, D.s_old[t].data(), 14 * sizeof(fe)); memcpy(w + 14, D.r_old[t].data(), 14 * sizeof(fe));
+        w[28] = D.deltas[t]; w[29] = D.s_idx[t]; w[30] = D.r_idx[t]; w[31] = D.s_sk[t]; w[32] = D.sig_seeds[t];
+        r[32] = ref(tree_depth, 0);
+        path(D.s_idx[t], r);
+        update(2 * t, D.s_idx[t], D.s_new[t]);
+        update(2 * t + 1, D.r_idx[t], D.r_new[t]);
+        path(D.r_idx[t], r + 16);
+    }
+    P.final_root = ref(tree_depth, 0);
+    return P;
+}
 
 extern "C" {
 
@@ -274,60 +396,33 @@ int csg_build_trace_merkle_init(const uint64_t s_inputs[14], const uint64_t r_in
 
 csg_tx_batch *csg_tx_batch_new(uint64_t seed, size_t num_tx, unsigned tree_depth) {
     if (!num_tx || tree_depth < 1 || tree_depth > 15 || ((tree_depth + 1) & tree_depth)) return nullptr;  // depth+1 must be a power of two (src/lib.rs:106-109)
-    SplitMix64 rng{seed};
+    const BatchDraws D = draw_batch(seed, num_tx, tree_depth);
     auto *B = new csg_tx_batch;
     B->tree_depth = tree_depth;
-    size_t tree_size = (size_t)1 << tree_depth;
-    fe pk[4][12];
-    for (unsigned k = 1; k <= 3; k++) { U256 s = {{k, 0, 0, 0}}; to_affine(scalar_mul_generator(s), pk[k]); }
-    std::vector<unsigned> skeys(tree_size, 0);
-    std::vector<Account> values(tree_size); for (auto &v : values) v.fill(0);
+    B->s_idx = D.s_idx; B->r_idx = D.r_idx;
     AccountTree tree(tree_depth);
-    std::vector<size_t> created;
-    auto new_account = [&](size_t idx) {   // the leaf hashes and their paths are computed in bulk below
-        unsigned sk = 1 + rng.next() % 3; skeys[idx] = sk;
-        Account a;
-        for (int i = 0; i < 12; i++) a[i] = pk[sk][i];
-        a[12] = f63::to_mont(rng.next() % f63::P); a[13] = f63::to_mont(rng.next() % f63::P);
-        values[idx] = a; created.push_back(idx);
-    };
-    B->s_idx.resize(num_tx); B->r_idx.resize(num_tx);
-    for (size_t t = 0; t < num_tx; t++) { B->s_idx[t] = rng.next() % tree_size; new_account(B->s_idx[t]); }
-    for (size_t t = 0; t < num_tx; t++) {
-        size_t r = rng.next() % tree_size;
-        while (r == B->s_idx[t]) r = rng.next() % tree_size;
-        B->r_idx[t] = r;
-        if (!skeys[r]) new_account(r);
-    }
     {   // a slot drawn twice keeps its last account, as with one update per draw
-        std::vector<Hash7> leaves(created.size());
+        std::vector<Hash7> leaves(D.created.size());
 #pragma omp parallel for schedule(static)
-        for (long k = 0; k < (long)created.size(); k++) leaves[k] = account_leaf(values[created[k]]);
-        for (size_t k = 0; k < created.size(); k++) tree.set_leaf(created[k], leaves[k]);
+        for (long k = 0; k < (long)D.created.size(); k++) leaves[k] = account_leaf(D.created_values[k]);
+        for (size_t k = 0; k < D.created.size(); k++) tree.set_leaf(D.created[k], leaves[k]);
         tree.rebuild();
     }
-    std::vector<unsigned> s_sk(num_tx);
     for (size_t t = 0; t < num_tx; t++) {
-        size_t si = B->s_idx[t], ri = B->r_idx[t];
-        uint64_t sb = f63::from_mont(values[si][12]), rb = f63::from_mont(values[ri][12]);
-        uint64_t bound = std::min(sb, UINT64_MAX - rb);
-        fe delta = f63::to_mont((rng.next() % (bound ? bound : 1)) % f63::P);
+        const size_t si = D.s_idx[t], ri = D.r_idx[t];
         B->initial_roots.push_back(tree.root());
-        s_sk[t] = skeys[si]; B->s_old.push_back(values[si]); B->r_old.push_back(values[ri]); B->deltas.push_back(delta);
+        B->s_old.push_back(D.s_old[t]); B->r_old.push_back(D.r_old[t]); B->deltas.push_back(D.deltas[t]);
         B->s_paths.push_back(tree.prove(si));
-        values[si][12] = f63::sub(values[si][12], delta); values[si][13] = f63::add(values[si][13], f63::ONE);
-        values[ri][12] = f63::add(values[ri][12], delta);
-        tree.update_leaf(si, account_leaf(values[si])); tree.update_leaf(ri, account_leaf(values[ri]));
+        tree.update_leaf(si, account_leaf(D.s_new[t])); tree.update_leaf(ri, account_leaf(D.r_new[t]));
         B->r_paths.push_back(tree.prove(ri));
     }
     B->final_root = tree.root();
     B->msgs.resize(num_tx); B->sigs.resize(num_tx);
-    std::vector<uint64_t> sig_seeds(num_tx); for (auto &s : sig_seeds) s = rng.next();
 #pragma omp parallel for schedule(dynamic)
     for (size_t t = 0; t < num_tx; t++) {
-        SplitMix64 r2{sig_seeds[t]};
+        SplitMix64 r2{D.sig_seeds[t]};
         B->msgs[t] = build_tx_message(B->s_old[t], B->r_old[t], B->deltas[t], B->s_old[t][13]);
-        B->sigs[t] = sign(B->msgs[t], s_sk[t], r2);
+        B->sigs[t] = sign(B->msgs[t], D.s_sk[t], r2);
     }
     return B;
 }

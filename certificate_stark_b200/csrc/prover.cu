@@ -20,6 +20,7 @@
 #include "ext_stages.cuh"
 #include "hash.cuh"
 #include "host/air_desc.hpp"
+#include "host/batch_plan.hpp"
 #include "host/transcript.hpp"
 #include "ntt.cuh"
 #include "stages.cuh"
@@ -106,6 +107,14 @@ struct csg_ctx {
     cudaEvent_t ev_intt = nullptr, ev_gathered = nullptr;
 
     DBuf<uint64_t> d_io, d_wit_in;
+    // device-side batch builder (batch_gen.cu): plan uploads, node versions, signatures; tables cached per context
+    DBuf<uint64_t> d_b_accounts, d_b_txw, d_b_sigs;
+    DBuf<int> d_b_left, d_b_right, d_b_refs;
+    DBuf<fe> d_b_hashes, d_b_defaults, d_b_gtable;
+    unsigned b_defaults_depth = 0;
+    bool b_gtable_built = false;
+    size_t wit_resident_ntx = 0;             // transfers whose packed records are resident in d_wit_in
+    unsigned wit_resident_depth = 0;
     DBuf<fe> d_wit_finals;
     std::vector<uint64_t> wit_packed;
     const csg_tx_batch *wit_packed_for = nullptr;
@@ -1238,6 +1247,7 @@ int csg_build_trace_transaction_device(csg_ctx *ctx, const csg_tx_batch *b) {
             csg_tx_batch_pack(b, packed.data());
             ctx->wit_packed_for = b;
         }
+        ctx->wit_resident_ntx = 0;   // d_wit_in is overwritten below
         Timer &t = ctx->stage_timer;
         t.start(ctx->st);
         DBuf<uint64_t> &in = ctx->d_wit_in;
@@ -1248,6 +1258,69 @@ int csg_build_trace_transaction_device(csg_ctx *ctx, const csg_tx_batch *b) {
         ctx->tm.h2d = t.stop(ctx->st);   // here: witness generation time
         ctx->nfri = 0;
         ctx->stage = S_TRACE;
+    });
+}
+// TransactionMetadata::build_random on the device: plan on the host (draws + tree shape, no hashing), hashes on the GPU
+int csg_tx_batch_build_device(csg_ctx *ctx, uint64_t seed, size_t num_tx, unsigned tree_depth, uint64_t pub[14]) {
+    return guarded(ctx, [&] {
+        if (!pub) throw ArgError("null output");
+        BatchPlan P;
+        try { P = plan_tx_batch(seed, num_tx, tree_depth); } catch (const std::invalid_argument &e) { throw ArgError(e.what()); }
+        Stream &st = ctx->st;
+        Timer &t = ctx->stage_timer;
+        t.start(st);
+        const size_t total = P.level_off[P.depth + 1];
+        ctx->d_b_accounts.reserve(P.accounts.size()); ctx->d_b_txw.reserve(P.tx_words.size()); ctx->d_b_sigs.reserve(14 * num_tx);
+        ctx->d_b_left.reserve(total); ctx->d_b_right.reserve(total); ctx->d_b_refs.reserve(P.tx_refs.size());
+        ctx->d_b_hashes.reserve(7 * total); ctx->d_b_defaults.reserve(7 * 16); ctx->d_b_gtable.reserve(64 * 16 * 12);
+        ctx->d_wit_in.reserve((size_t)WIT_WORDS * num_tx);
+        CSG_CUDA(cudaMemcpyAsync(ctx->d_b_accounts.p, P.accounts.data(), P.accounts.size() * 8, cudaMemcpyHostToDevice, st.s));
+        CSG_CUDA(cudaMemcpyAsync(ctx->d_b_txw.p, P.tx_words.data(), P.tx_words.size() * 8, cudaMemcpyHostToDevice, st.s));
+        CSG_CUDA(cudaMemcpyAsync(ctx->d_b_left.p, P.left.data(), total * 4, cudaMemcpyHostToDevice, st.s));
+        CSG_CUDA(cudaMemcpyAsync(ctx->d_b_right.p, P.right.data(), total * 4, cudaMemcpyHostToDevice, st.s));
+        CSG_CUDA(cudaMemcpyAsync(ctx->d_b_refs.p, P.tx_refs.data(), P.tx_refs.size() * 4, cudaMemcpyHostToDevice, st.s));
+        if (ctx->b_defaults_depth != P.depth) { batch_defaults(P.depth, ctx->d_b_defaults.p, st); ctx->b_defaults_depth = P.depth; }
+        if (!ctx->b_gtable_built) { batch_gtable(ctx->d_b_gtable.p, st); ctx->b_gtable_built = true; }
+        BatchDevice B{P.depth, (unsigned)num_tx, P.level_off.data(), ctx->d_b_accounts.p, ctx->d_b_left.p, ctx->d_b_right.p, ctx->d_b_txw.p, ctx->d_b_refs.p,
+                      ctx->d_b_hashes.p, ctx->d_b_defaults.p, ctx->d_b_gtable.p, ctx->d_b_sigs.p, ctx->d_wit_in.p};
+        batch_build(B, st);
+        // public inputs: the root before the first transfer and the root after the last one (TransactionProver::get_pub_inputs)
+        fe roots[14];
+        auto fetch = [&](int ref, fe *out) {
+            const fe *src = ref >= 0 ? ctx->d_b_hashes.p + (size_t)ref * 7 : ctx->d_b_defaults.p + (size_t)(-ref - 1) * 7;
+            CSG_CUDA(cudaMemcpyAsync(out, src, 7 * sizeof(fe), cudaMemcpyDeviceToHost, st.s));
+        };
+        fetch(P.tx_refs[32], roots); fetch(P.final_root, roots + 7);
+        ctx->tm.batch_build = t.stop(st);   // synchronises: the plan's host vectors and `roots` are complete
+        for (int i = 0; i < 14; i++) pub[i] = from_mont(roots[i]);
+        ctx->wit_resident_ntx = num_tx; ctx->wit_resident_depth = P.depth;
+        ctx->wit_packed_for = nullptr;       // d_wit_in no longer holds a host batch's records
+    });
+}
+int csg_build_trace_transaction_resident(csg_ctx *ctx) {
+    return guarded(ctx, [&] {
+        ctx->need(S_AIR, "csg_set_air must be called first");
+        const size_t ntx = ctx->wit_resident_ntx;
+        if (!ntx) throw StateError("csg_tx_batch_build_device must be called first");
+        if (ctx->air.id != CSG_AIR_TRANSACTION || ctx->n != ntx * 1024) throw ArgError("the AIR set on this context is not the transaction AIR of this batch size");
+        if (ctx->wit_resident_depth != 15) throw ArgError("the transaction AIR is built for tree depth 15");
+        Timer &t = ctx->stage_timer;
+        t.start(ctx->st);
+        ctx->d_wit_finals.reserve(ntx * 48); ctx->d_io.reserve((size_t)ctx->air.width * ctx->n);
+        build_transaction_trace(ctx->d_wit_in.p, ntx, 15, ctx->d_io.p, ctx->d_wit_finals.p, ctx->st);
+        ctx->trace_repr = CSG_REPR_CANONICAL;
+        ctx->tm.h2d = t.stop(ctx->st);   // here: witness generation time
+        ctx->nfri = 0;
+        ctx->stage = S_TRACE;
+    });
+}
+int csg_download_batch_records(csg_ctx *ctx, uint64_t *out, size_t cap_words) {
+    return guarded(ctx, [&] {
+        const size_t words = (size_t)WIT_WORDS * ctx->wit_resident_ntx;
+        if (!words) throw StateError("no device-built batch is resident");
+        if (!out || cap_words < words) throw ArgError("record buffer too small");
+        CSG_CUDA(cudaMemcpyAsync(out, ctx->d_wit_in.p, words * 8, cudaMemcpyDeviceToHost, ctx->st.s));
+        CSG_CUDA(cudaStreamSynchronize(ctx->st.s));
     });
 }
 int csg_download_trace(csg_ctx *ctx, uint64_t *trace) {

@@ -78,14 +78,14 @@ CSG_HD void apply_round(fe *state, size_t step) {
     mat_mul<false>(t, s);
     for (int i = 0; i < 14; i++) state[i] = f63::add(s[i], ark[14 + i]);
 }
-inline void apply_permutation(fe *state) { for (int i = 0; i < NUM_ROUNDS; i++) apply_round(state, i); }
-inline void merge(const fe *a, const fe *b, fe *out) {
+CSG_HD void apply_permutation(fe *state) { for (int i = 0; i < NUM_ROUNDS; i++) apply_round(state, i); }
+CSG_HD void merge(const fe *a, const fe *b, fe *out) {
     fe st[14];
     for (int i = 0; i < 7; i++) { st[i] = a[i]; st[7 + i] = b[i]; }
     apply_permutation(st);
     for (int i = 0; i < 7; i++) out[i] = st[i];
 }
-inline void digest(const fe *data, size_t n, fe *out) {
+CSG_HD void digest(const fe *data, size_t n, fe *out) {
     fe st[14] = {0};
     size_t i = 0;
     for (size_t k = 0; k < n; k++) {

@@ -22,4 +22,22 @@ enum : int {
 // canonical column-major trace of ntx transactions (94 x 1024*ntx) into trace_dev; finals_dev: 48 elements per transaction
 void build_transaction_trace(const uint64_t *inputs_dev, size_t ntx, unsigned tree_depth, uint64_t *trace_dev, fe *finals_dev, Stream &st);
 
+// ---- TransactionMetadata::build_random on the device (batch_gen.cu; the plan comes from host/batch_plan.hpp)
+struct BatchDevice {
+    unsigned depth, ntx;
+    const unsigned *level_off;   // HOST array: first record id of each level 0..depth, then the total
+    const uint64_t *accounts;    // device: 14 words per level-0 record
+    const int *left, *right;     // device: child versions of every record
+    const uint64_t *tx_words;    // device: 33 words per transfer
+    const int *tx_refs;          // device: 33 version references per transfer
+    fe *hashes;                  // device: 7 elements per record (output)
+    const fe *defaults;          // device: empty-subtree hash of every level
+    const fe *gtable;            // device: fixed-base table of the generator
+    uint64_t *sigs;              // device: 14 words per transfer (rx, s, h)
+    uint64_t *records;           // device: WIT_WORDS words per transfer (output: what build_transaction_trace reads)
+};
+void batch_defaults(unsigned depth, fe *defaults_dev, Stream &st);   // (depth + 1) * 7 elements
+void batch_gtable(fe *table_dev, Stream &st);                        // 64 * 16 * 12 elements
+void batch_build(const BatchDevice &B, Stream &st);
+
 }  // namespace csg

@@ -157,6 +157,7 @@ typedef struct {
     /* kernels launched inside each stage, in the order lde, commit_trace, constraints, composition, ood_deep, fri, queries:
      * lets a profiler's launch list of one proof be cut into stages */
     uint32_t stage_launches[7];
+    float batch_build; /* device time of the last csg_tx_batch_build_device */
 } csg_timings;
 int csg_get_timings(const csg_ctx *ctx, csg_timings *out);
 /* CUDA events on the proving stream around an arbitrary sequence of calls (bench.py's timed region) */
@@ -177,6 +178,16 @@ int csg_build_trace_transaction(const csg_tx_batch *b, uint64_t *trace /* 94 x 1
  * crosses PCIe.  csg_download_trace copies the resident canonical trace back (tests). */
 int csg_build_trace_transaction_device(csg_ctx *ctx, const csg_tx_batch *b);
 int csg_download_trace(csg_ctx *ctx, uint64_t *trace /* width x trace_len */);
+/* TransactionMetadata::build_random ON THE DEVICE (src/lib.rs:235-464): the same seeded draws as
+ * csg_tx_batch_new(seed, num_tx, tree_depth), but the depth-15 Rescue account tree, its update by every transfer, the authentication
+ * paths, the signature points r.G and the message hashes are computed by kernels (the tree's history level by level: thousands of
+ * independent permutations per launch instead of 32 dependent ones per transfer).  The packed witness records stay in HBM; only the
+ * public inputs (root before the first transfer, root after the last) come back.  Follow with csg_set_air(TRANSACTION,
+ * 1024 * num_tx, opt, pub, 14), csg_build_trace_transaction_resident, csg_prove_loaded.  csg_download_batch_records (tests) copies
+ * the records back: csg_tx_batch_pack(csg_tx_batch_new(seed, ...)) bit for bit. */
+int csg_tx_batch_build_device(csg_ctx *ctx, uint64_t seed, size_t num_tx, unsigned tree_depth, uint64_t pub[14]);
+int csg_build_trace_transaction_resident(csg_ctx *ctx);
+int csg_download_batch_records(csg_ctx *ctx, uint64_t *out /* 276 words per transfer */, size_t cap_words);
 size_t csg_tx_batch_pack(const csg_tx_batch *b, uint64_t *out /* NULL: returns the word count */);
 unsigned csg_tx_batch_depth(const csg_tx_batch *b);
 int csg_build_trace_merkle_update(const csg_tx_batch *b, uint64_t *trace /* 65 x 512*num_tx */, uint64_t pub[14]); /* src/merkle/update/prover.rs:37-80 */
