@@ -110,7 +110,8 @@ def lib() -> C.CDLL:
         "csg_build_trace_transaction_device": (C.c_int, [vp, vp]), "csg_download_trace": (C.c_int, [vp, _u64p]),
         "csg_tx_batch_build_device": (C.c_int, [vp, C.c_uint64, C.c_size_t, C.c_uint, _u64p]),
         "csg_build_trace_transaction_resident": (C.c_int, [vp]), "csg_download_batch_records": (C.c_int, [vp, _u64p, C.c_size_t]),
-        "csg_tx_batch_pack": (C.c_size_t, [vp, _u64p]), "csg_tx_batch_depth": (C.c_uint, [vp]), "csg_build_trace_merkle_update": (C.c_int, [vp, _u64p, _u64p]),
+        "csg_tx_batch_pack": (C.c_size_t, [vp, _u64p]), "csg_sig_batch_pack": (C.c_size_t, [vp, _u64p]),
+        "csg_build_trace_merkle_update_device": (C.c_int, [vp, vp]), "csg_build_trace_schnorr_device": (C.c_int, [vp, vp]), "csg_tx_batch_depth": (C.c_uint, [vp]), "csg_build_trace_merkle_update": (C.c_int, [vp, _u64p, _u64p]),
         "csg_build_trace_merkle_init": (C.c_int, [_u64p, _u64p, C.c_uint64, _u64p, _u64p]),
         "csg_sig_batch_new": (vp, [C.c_uint64, C.c_size_t]), "csg_sig_batch_free": (None, [vp]), "csg_sig_batch_size": (C.c_size_t, [vp]),
         "csg_build_trace_schnorr": (C.c_int, [vp, _u64p, _u64p]), "csg_build_trace_range": (C.c_int, [C.c_uint64, _u64p, _u64p]),
@@ -264,9 +265,17 @@ class Context:
         self._check(lib().csg_build_trace_transaction_resident(self._h))
 
     def download_batch_records(self, num_tx: int) -> np.ndarray:
-        out = np.zeros((num_tx, 276), dtype=np.uint64)
+        out = np.zeros((num_tx, 278), dtype=np.uint64)
         self._check(lib().csg_download_batch_records(self._h, _p64(out), out.size))
         return out
+
+    def build_merkle_update_trace(self, batch: "TransactionBatch"):
+        """MerkleProver::build_trace on the device (after set_air(AIR_MERKLE_UPDATE, 512 * num_tx, ...))"""
+        self._check(lib().csg_build_trace_merkle_update_device(self._h, batch._h))
+
+    def build_schnorr_trace(self, batch: "SignatureBatch"):
+        """SchnorrProver::build_trace on the device (after set_air(AIR_SCHNORR, 512 * num_sig, ...))"""
+        self._check(lib().csg_build_trace_schnorr_device(self._h, batch._h))
 
     def download_trace(self, width: int, trace_len: int) -> np.ndarray:
         out = np.empty((width, trace_len), dtype=np.uint64)
@@ -460,8 +469,8 @@ class TransactionBatch:
         return trace, pub
 
     def packed_records(self) -> np.ndarray:
-        """the per-transfer records the device witness builder consumes (csg_tx_batch_pack): (num_tx, 276) words"""
-        out = np.zeros((self.num_tx, 276), dtype=np.uint64)
+        """the per-transfer records the device witness builder consumes (csg_tx_batch_pack): (num_tx, 278) words"""
+        out = np.zeros((self.num_tx, 278), dtype=np.uint64)
         lib().csg_tx_batch_pack(self._h, _p64(out))
         return out
 

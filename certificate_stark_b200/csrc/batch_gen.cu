@@ -132,7 +132,8 @@ __global__ void batch_pack_kernel(const uint64_t *__restrict__ tx_words, const i
         v = version(hashes, defaults, R[k])[i];      // slots above the tree's depth refer to the all-zero digest
     } else if (w < WIT_S) v = sigs[(size_t)tx * 14 + (w - WIT_RX)];
     else if (w < WIT_H) v = sigs[(size_t)tx * 14 + 6 + (w - WIT_S)];
-    else v = sigs[(size_t)tx * 14 + 10 + (w - WIT_H)];
+    else if (w < WIT_M26) v = sigs[(size_t)tx * 14 + 10 + (w - WIT_H)];
+    else v = 0;                                                  // the last two message words of a transfer
     records[g] = v;
 }
 

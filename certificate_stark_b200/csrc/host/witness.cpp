@@ -434,8 +434,8 @@ void csg_tx_batch_roots(const csg_tx_batch *b, uint64_t initial_root[7], uint64_
 
 // packed inputs of the device-side witness builder (csrc/witness.cuh): WIT_WORDS words per transaction
 unsigned csg_tx_batch_depth(const csg_tx_batch *b) { return b->tree_depth; }
-size_t csg_tx_batch_pack(const csg_tx_batch *B, uint64_t *out /* 276 words per transaction, or NULL for the size */) {
-    const size_t W = 276, ntx = B->deltas.size();
+size_t csg_tx_batch_pack(const csg_tx_batch *B, uint64_t *out /* 278 words per transaction, or NULL for the size */) {
+    const size_t W = 278, ntx = B->deltas.size();
     if (!out) return W * ntx;
 #pragma omp parallel for schedule(static)
     for (size_t t = 0; t < ntx; t++) {
@@ -453,6 +453,25 @@ size_t csg_tx_batch_pack(const csg_tx_batch *B, uint64_t *out /* 276 words per t
         for (int i = 0; i < 4; i++) r[272 + i] = h.w[i];
     }
     return W * ntx;
+}
+
+// the same record for a standalone signature: the message fills the slots the transfer's message is assembled from (witness.cuh)
+size_t csg_sig_batch_pack(const csg_sig_batch *B, uint64_t *out /* 278 words per signature, or NULL for the size */) {
+    const size_t W = 278, n = B->sigs.size();
+    if (!out) return W * n;
+#pragma omp parallel for schedule(static)
+    for (size_t t = 0; t < n; t++) {
+        uint64_t *r = out + t * W;
+        const Message &m = B->msgs[t];
+        memset(r, 0, W * sizeof(uint64_t));
+        for (int i = 0; i < 12; i++) { r[i] = m[i]; r[14 + i] = m[12 + i]; }
+        r[28] = m[24]; r[13] = m[25]; r[276] = m[26]; r[277] = m[27];
+        for (int i = 0; i < 6; i++) r[262 + i] = B->sigs[t].rx[i];
+        for (int i = 0; i < 4; i++) r[268 + i] = B->sigs[t].s.w[i];
+        U256 h = hash_to_scalar_bits(hash_message(B->sigs[t].rx.data(), m));
+        for (int i = 0; i < 4; i++) r[272 + i] = h.w[i];
+    }
+    return W * n;
 }
 
 int csg_build_trace_transaction(const csg_tx_batch *B, uint64_t *trace, uint64_t pub[14]) {

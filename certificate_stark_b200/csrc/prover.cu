@@ -1260,6 +1260,48 @@ int csg_build_trace_transaction_device(csg_ctx *ctx, const csg_tx_batch *b) {
         ctx->stage = S_TRACE;
     });
 }
+// the standalone provers of the Merkle-update and Schnorr sub-AIRs on the device (same records, same kernels)
+static void upload_records(csg_ctx *ctx, std::vector<uint64_t> &packed) {
+    ctx->d_wit_in.reserve(packed.size());
+    CSG_CUDA(cudaMemcpyAsync(ctx->d_wit_in.p, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice, ctx->st.s));
+    ctx->wit_resident_ntx = 0; ctx->wit_packed_for = nullptr;
+}
+int csg_build_trace_merkle_update_device(csg_ctx *ctx, const csg_tx_batch *b) {
+    return guarded(ctx, [&] {
+        ctx->need(S_AIR, "csg_set_air must be called first");
+        if (!b) throw ArgError("null batch");
+        const size_t ntx = csg_tx_batch_size(b);
+        if (ctx->air.id != CSG_AIR_MERKLE_UPDATE || ctx->n != ntx * 512) throw ArgError("the AIR set on this context is not the Merkle-update AIR of this batch size");
+        std::vector<uint64_t> packed(csg_tx_batch_pack(b, nullptr));
+        csg_tx_batch_pack(b, packed.data());
+        Timer &t = ctx->stage_timer;
+        t.start(ctx->st);
+        upload_records(ctx, packed);
+        ctx->d_io.reserve((size_t)ctx->air.width * ctx->n);
+        build_merkle_update_trace(ctx->d_wit_in.p, ntx, csg_tx_batch_depth(b), ctx->d_io.p, ctx->st);
+        ctx->trace_repr = CSG_REPR_CANONICAL;
+        ctx->tm.h2d = t.stop(ctx->st);
+        ctx->nfri = 0; ctx->stage = S_TRACE;
+    });
+}
+int csg_build_trace_schnorr_device(csg_ctx *ctx, const csg_sig_batch *b) {
+    return guarded(ctx, [&] {
+        ctx->need(S_AIR, "csg_set_air must be called first");
+        if (!b) throw ArgError("null batch");
+        const size_t nsig = csg_sig_batch_size(b);
+        if (ctx->air.id != CSG_AIR_SCHNORR || ctx->n != nsig * 512) throw ArgError("the AIR set on this context is not the Schnorr AIR of this batch size");
+        std::vector<uint64_t> packed(csg_sig_batch_pack(b, nullptr));
+        csg_sig_batch_pack(b, packed.data());
+        Timer &t = ctx->stage_timer;
+        t.start(ctx->st);
+        upload_records(ctx, packed);
+        ctx->d_wit_finals.reserve(nsig * 48); ctx->d_io.reserve((size_t)ctx->air.width * ctx->n);
+        build_schnorr_trace(ctx->d_wit_in.p, nsig, ctx->d_io.p, ctx->d_wit_finals.p, ctx->st);
+        ctx->trace_repr = CSG_REPR_CANONICAL;
+        ctx->tm.h2d = t.stop(ctx->st);
+        ctx->nfri = 0; ctx->stage = S_TRACE;
+    });
+}
 // TransactionMetadata::build_random on the device: plan on the host (draws + tree shape, no hashing), hashes on the GPU
 int csg_tx_batch_build_device(csg_ctx *ctx, uint64_t seed, size_t num_tx, unsigned tree_depth, uint64_t pub[14]) {
     return guarded(ctx, [&] {

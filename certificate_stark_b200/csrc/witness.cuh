@@ -16,11 +16,18 @@ enum : int {
     WIT_RX = 262,       // x coordinate of the signature's R [6]
     WIT_S = 268,        // signature scalar s, 4 little-endian words
     WIT_H = 272,        // message hash h as 4 little-endian words (the bits driving h.P)
-    WIT_WORDS = 276
+    WIT_M26 = 276,      // last two words of the signed message: zero for a transfer (src/lib.rs:467-481), random for SchnorrExample's
+    WIT_WORDS = 278     //   messages (src/schnorr/mod.rs:97-99).  The message is S_OLD[0..12] | R_OLD[0..12] | DELTA | S_OLD[13] | M26 | M27
 };
 
 // canonical column-major trace of ntx transactions (94 x 1024*ntx) into trace_dev; finals_dev: 48 elements per transaction
 void build_transaction_trace(const uint64_t *inputs_dev, size_t ntx, unsigned tree_depth, uint64_t *trace_dev, fe *finals_dev, Stream &st);
+// the standalone provers of the sub-AIRs from the same records and the same kernels:
+//   MerkleProver::build_trace  (src/merkle/update/prover.rs:37-80): 65 x 512*ntx, rows 0..511 of every transfer's Merkle phase,
+//                              plus the two bit cells the reference sets at step 1 (:72-77)
+//   SchnorrProver::build_trace (src/schnorr/prover.rs:52-80): 56 x 512*nsig, the signature phase alone
+void build_merkle_update_trace(const uint64_t *inputs_dev, size_t ntx, unsigned tree_depth, uint64_t *trace_dev, Stream &st);
+void build_schnorr_trace(const uint64_t *inputs_dev, size_t nsig, uint64_t *trace_dev, fe *finals_dev, Stream &st);
 
 // ---- TransactionMetadata::build_random on the device (batch_gen.cu; the plan comes from host/batch_plan.hpp)
 struct BatchDevice {

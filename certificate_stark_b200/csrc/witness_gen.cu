@@ -22,11 +22,17 @@ enum : int {
     SENDER_KEY = 65, DELTA_COPY = 89, PREV_ROOT = 58, SIG_HASH = 42, LIMBS = 37, TX_WIDTH = 94
 };
 
-struct Out {   // canonical column-major trace; transaction t owns rows t*1024 .. t*1024+1023
+struct Out {   // canonical column-major trace; item t (a transfer or a signature) owns rows t*item_rows .. (t+1)*item_rows - 1
     uint64_t *trace;
     unsigned long long n;
+    unsigned item_rows;      // 1024: a transfer of the transaction AIR; 512: a fragment of a standalone sub-AIR
+    unsigned schnorr_row0;   // first row of the signature phase inside an item (512 in a transfer, 0 standalone)
     __device__ __forceinline__ void put(unsigned col, unsigned long long row, fe v) const { trace[col * n + row] = from_mont(v); }
 };
+// word m of the signed message of a record (witness.cuh)
+__device__ __forceinline__ fe message_word(const uint64_t *T, unsigned m) {
+    return m < APW ? T[WIT_S_OLD + m] : m < 2 * APW ? T[WIT_R_OLD + m - APW] : m == 2 * APW ? T[WIT_DELTA] : m == 2 * APW + 1 ? T[WIT_S_OLD + APW + 1] : T[WIT_M26 + m - 26];
+}
 __device__ __forceinline__ bool bit256(const uint64_t *w, unsigned i) { return (w[i >> 6] >> (i & 63)) & 1; }
 
 // ---- the four Merkle-path hash states of a transaction: thread = (transaction, state), rows 0..511 of its 14 columns
@@ -37,7 +43,7 @@ __global__ void __launch_bounds__(64) wit_merkle_kernel(const uint64_t *__restri
     const uint64_t *T = in + (size_t)tx * WIT_WORDS;
     const bool receiver = s >= 2, updated = s & 1;
     const unsigned col0 = 15 * s - (s >> 1);
-    const unsigned long long row0 = (unsigned long long)tx * TX_ROWS;
+    const unsigned long long row0 = (unsigned long long)tx * out.item_rows;
     const uint64_t *acct = T + (receiver ? WIT_R_OLD : WIT_S_OLD), *path = T + (receiver ? WIT_R_PATH : WIT_S_PATH);
     const uint64_t index = T[receiver ? WIT_R_IDX : WIT_S_IDX];
     const fe delta = T[WIT_DELTA];
@@ -76,7 +82,7 @@ __global__ void __launch_bounds__(64) wit_merkle_kernel(const uint64_t *__restri
         if (owns_root) for (int i = 0; i < HRW; i++) out.put(PREV_ROOT + i, row, root[i]);
     }
     if (owns_root)   // the root register is not touched by the Schnorr half of the fragment (src/trace.rs:89-100)
-        for (unsigned r = MERKLE_ROWS; r < TX_ROWS; r++) for (int i = 0; i < HRW; i++) out.put(PREV_ROOT + i, row0 + r, root[i]);
+        for (unsigned r = MERKLE_ROWS; r < out.item_rows; r++) for (int i = 0; i < HRW; i++) out.put(PREV_ROOT + i, row0 + r, root[i]);
 }
 
 // ---- Rescue state hashing R.x and the message (columns 42..55, rows 512..1023): thread = transaction
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(64) wit_sig_hash_kernel(const uint64_t *__rest
     const unsigned tx = blockIdx.x * blockDim.x + threadIdx.x;
     if (tx >= ntx) return;
     const uint64_t *T = in + (size_t)tx * WIT_WORDS;
-    const unsigned long long row0 = (unsigned long long)tx * TX_ROWS + MERKLE_ROWS;
+    const unsigned long long row0 = (unsigned long long)tx * out.item_rows + out.schnorr_row0;
     fe st[14];
     for (int i = 0; i < 14; i++) st[i] = i < 6 ? T[WIT_RX + i] : 0;      // src/schnorr/trace.rs:18-30
     for (int i = 0; i < 14; i++) out.put(SIG_HASH + i, row0, st[i]);
@@ -92,11 +98,7 @@ __global__ void __launch_bounds__(64) wit_sig_hash_kernel(const uint64_t *__rest
         if (ss < 8 * NUM_HASH_ITER) {
             if (ss % 8 < 7) rescue::apply_round(st, ss);
             else if (ss < 8 * (NUM_HASH_ITER - 1)) {
-                for (int i = 0; i < HRW; i++) {   // message = sender key | receiver key | delta | nonce | 0 | 0   (src/lib.rs:467-481)
-                    const unsigned m = HRW * (ss / 8) + i;
-                    st[HRW + i] = m < APW ? T[WIT_S_OLD + m] : m < 2 * APW ? T[WIT_R_OLD + m - APW] : m == 2 * APW ? T[WIT_DELTA]
-                                  : m == 2 * APW + 1 ? T[WIT_S_OLD + APW + 1] : 0;
-                }
+                for (int i = 0; i < HRW; i++) st[HRW + i] = message_word(T, HRW * (ss / 8) + i);   // sender key | receiver key | delta | nonce | 0 | 0 for a transfer (src/lib.rs:467-481)
             } else for (int i = 0; i < HRW; i++) st[HRW + i] = 0;
         }
         for (int i = 0; i < 14; i++) out.put(SIG_HASH + i, row0 + ss + 1, st[i]);
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(64) wit_scalar_mult_kernel(const uint64_t *__r
     const unsigned tx = g >> 1, bank = g & 1, col0 = bank * (PPW + 1);
     const uint64_t *T = in + (size_t)tx * WIT_WORDS;
     const uint64_t *bits = T + (bank ? WIT_H : WIT_S);
-    const unsigned long long row0 = (unsigned long long)tx * TX_ROWS + MERKLE_ROWS;
+    const unsigned long long row0 = (unsigned long long)tx * out.item_rows + out.schnorr_row0;
     ecc::fp6 qx, qy;
     {
         const uint64_t *q = bank ? T + WIT_S_OLD : CSG_TABLE(CSG_GENERATOR);   // h multiplies the sender's public key
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(64) wit_final_kernel(const uint64_t *__restric
     const unsigned tx = blockIdx.x * blockDim.x + threadIdx.x;
     if (tx >= ntx) return;
     const uint64_t *T = in + (size_t)tx * WIT_WORDS;
-    const unsigned long long row0 = (unsigned long long)tx * TX_ROWS, last = row0 + TX_ROWS - 1;
+    const unsigned long long row0 = (unsigned long long)tx * out.item_rows, last = row0 + out.item_rows - 1;
     {   // src/schnorr/trace.rs:105-119
         const fe *A = finals + (size_t)tx * 48, *B = A + 24;
         ecc::point s, hp;
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(64) wit_final_kernel(const uint64_t *__restric
         out.put(LIMBS, last, B[18]);
         for (int i = 0; i < 4; i++) out.put(LIMBS + 1 + i, last, B[19 + i]);
     }
+    if (out.item_rows != TX_ROWS) return;   // a standalone signature has no copy or range-proof columns
     const fe delta = T[WIT_DELTA], sigma = sub(T[WIT_S_OLD + APW], delta), nonce = T[WIT_S_OLD + APW + 1];
     const uint64_t dbits = from_mont(delta), sbits = from_mont(sigma);
     fe dacc = 0, sacc = 0, dbit = 0, sbit = 0;
@@ -183,8 +186,26 @@ __global__ void __launch_bounds__(64) wit_final_kernel(const uint64_t *__restric
 
 }  // namespace
 
+__global__ void wit_set_one_kernel(uint64_t *a, uint64_t *b) { *a = 1; *b = 1; }
+
+void build_merkle_update_trace(const uint64_t *inputs_dev, size_t ntx, unsigned tree_depth, uint64_t *trace_dev, Stream &st) {
+    const unsigned long long n = (unsigned long long)ntx * MERKLE_ROWS;
+    Out out{trace_dev, n, MERKLE_ROWS, 0};
+    const unsigned T = 64;
+    CSG_LAUNCH(st, wit_merkle_kernel, (unsigned)((ntx * 4 + T - 1) / T), T, 0, inputs_dev, (unsigned)ntx, tree_depth, out);
+    // trace.set(SENDER_BIT_POS, 1, ONE); trace.set(RECEIVER_BIT_POS, 1, ONE)   (src/merkle/update/prover.rs:72-77; canonical 1)
+    CSG_LAUNCH(st, wit_set_one_kernel, 1, 1, 0, trace_dev + 14 * n + 1, trace_dev + 43 * n + 1);
+}
+void build_schnorr_trace(const uint64_t *inputs_dev, size_t nsig, uint64_t *trace_dev, fe *finals_dev, Stream &st) {
+    Out out{trace_dev, (unsigned long long)nsig * MERKLE_ROWS, MERKLE_ROWS, 0};
+    const unsigned T = 64;
+    CSG_LAUNCH(st, wit_sig_hash_kernel, (unsigned)((nsig + T - 1) / T), T, 0, inputs_dev, (unsigned)nsig, out);
+    CSG_LAUNCH(st, wit_scalar_mult_kernel, (unsigned)((nsig * 2 + T - 1) / T), T, 0, inputs_dev, (unsigned)nsig, out, finals_dev);
+    CSG_LAUNCH(st, wit_final_kernel, (unsigned)((nsig + T - 1) / T), T, 0, inputs_dev, (unsigned)nsig, out, (const fe *)finals_dev);
+}
+
 void build_transaction_trace(const uint64_t *inputs_dev, size_t ntx, unsigned tree_depth, uint64_t *trace_dev, fe *finals_dev, Stream &st) {
-    Out out{trace_dev, (unsigned long long)ntx * TX_ROWS};
+    Out out{trace_dev, (unsigned long long)ntx * TX_ROWS, TX_ROWS, MERKLE_ROWS};
     const unsigned T = 64;
     CSG_LAUNCH(st, wit_merkle_kernel, (unsigned)((ntx * 4 + T - 1) / T), T, 0, inputs_dev, (unsigned)ntx, tree_depth, out);
     CSG_LAUNCH(st, wit_sig_hash_kernel, (unsigned)((ntx + T - 1) / T), T, 0, inputs_dev, (unsigned)ntx, out);

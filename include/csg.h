@@ -187,8 +187,13 @@ int csg_download_trace(csg_ctx *ctx, uint64_t *trace /* width x trace_len */);
  * the records back: csg_tx_batch_pack(csg_tx_batch_new(seed, ...)) bit for bit. */
 int csg_tx_batch_build_device(csg_ctx *ctx, uint64_t seed, size_t num_tx, unsigned tree_depth, uint64_t pub[14]);
 int csg_build_trace_transaction_resident(csg_ctx *ctx);
-int csg_download_batch_records(csg_ctx *ctx, uint64_t *out /* 276 words per transfer */, size_t cap_words);
+int csg_download_batch_records(csg_ctx *ctx, uint64_t *out /* 278 words per transfer */, size_t cap_words);
 size_t csg_tx_batch_pack(const csg_tx_batch *b, uint64_t *out /* NULL: returns the word count */);
+size_t csg_sig_batch_pack(const csg_sig_batch *b, uint64_t *out /* NULL: returns the word count */);
+/* MerkleProver::build_trace (src/merkle/update/prover.rs:37-80) and SchnorrProver::build_trace (src/schnorr/prover.rs:52-80) on the
+ * device, into the resident trace: call after csg_set_air for that AIR with trace_len = 512 * (transfers | signatures) */
+int csg_build_trace_merkle_update_device(csg_ctx *ctx, const csg_tx_batch *b);
+int csg_build_trace_schnorr_device(csg_ctx *ctx, const csg_sig_batch *b);
 unsigned csg_tx_batch_depth(const csg_tx_batch *b);
 int csg_build_trace_merkle_update(const csg_tx_batch *b, uint64_t *trace /* 65 x 512*num_tx */, uint64_t pub[14]); /* src/merkle/update/prover.rs:37-80 */
 int csg_build_trace_merkle_init(const uint64_t s_inputs[14], const uint64_t r_inputs[14], uint64_t delta,

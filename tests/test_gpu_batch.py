@@ -48,3 +48,35 @@ def test_device_batch_errors(ctx, csg):
         fresh.set_air(csg.AIR_TRANSACTION, 1024, pub, csg.ProofOptions())
         with pytest.raises(csg.CsgError):   # the resident batch has 2 transfers, the AIR was set for 1
             fresh.build_transaction_trace_resident()
+
+
+@pytest.mark.parametrize("num_tx", [1, 4, 32])
+def test_device_merkle_update_witness_matches_host_builder(csg, oracle, num_tx):
+    # SURVEY.md 8(f).1 for MerkleProver::build_trace (src/merkle/update/prover.rs:37-80), bit tweak at step 1 included
+    batch = csg.TransactionBatch(seed=31 + num_tx, num_tx=num_tx)
+    want, pub = batch.merkle_update_trace()
+    with csg.Context(0) as c:
+        c.set_air(csg.AIR_MERKLE_UPDATE, 512 * num_tx, pub, csg.ProofOptions())
+        c.build_merkle_update_trace(batch)
+        got = c.download_trace(65, 512 * num_tx)
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, f"first differing (column, row): {bad[0]}"
+        proof = c.prove_loaded()
+    assert proof == oracle.prove(oracle.AIR_MERKLE_UPDATE, want, pub, oracle.options())
+
+
+@pytest.mark.parametrize("num_sig", [1, 2, 16])
+def test_device_schnorr_witness_matches_host_builder(csg, oracle, num_sig):
+    # SURVEY.md 8(f).1 for SchnorrProver::build_trace (src/schnorr/prover.rs:52-80): messages with 16 random elements
+    batch = csg.SignatureBatch(seed=41 + num_sig, num_sig=num_sig)
+    want, pub = batch.schnorr_trace()
+    with csg.Context(0) as c:
+        c.set_air(csg.AIR_SCHNORR, 512 * num_sig, pub, csg.ProofOptions())
+        c.build_schnorr_trace(batch)
+        got = c.download_trace(56, 512 * num_sig)
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, f"first differing (column, row): {bad[0]}"
+        proof = c.prove_loaded()
+        with pytest.raises(csg.CsgError):       # a batch of another size
+            c.build_schnorr_trace(csg.SignatureBatch(seed=1, num_sig=num_sig * 2))
+    assert proof == oracle.prove(oracle.AIR_SCHNORR, want, pub, oracle.options())
