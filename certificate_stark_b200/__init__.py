@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     sig = {
         "csg_create": (vp, [C.c_int]), "csg_destroy": (None, [vp]), "csg_last_error": (C.c_char_p, [vp]), "csg_free": (None, [vp]),
         "csg_prove": (C.c_int, [vp, C.c_int, _u64p, C.c_int, C.c_size_t, _u64p, C.c_size_t, opt, C.POINTER(_u8p), _szp]),
+        "csg_prove_columns": (C.c_int, [vp, C.c_int, C.POINTER(_u64p), C.c_int, C.c_size_t, _u64p, C.c_size_t, opt, C.POINTER(_u8p), _szp]),
         "csg_set_air": (C.c_int, [vp, C.c_int, C.c_size_t, opt, _u64p, C.c_size_t]),
         "csg_load_trace": (C.c_int, [vp, _u64p, C.c_int]), "csg_reload_resident_trace": (C.c_int, [vp]),
         "csg_prove_loaded": (C.c_int, [vp, C.POINTER(_u8p), _szp]),
@@ -220,6 +221,17 @@ class Context:
             raise CsgError(f"trace must be ({TRACE_WIDTH[air_id]}, n)")
         out, n = _u8p(), C.c_size_t()
         self._check(lib().csg_prove(self._h, air_id, _p64(trace), repr, trace.shape[1], _p64(pub), pub.size, C.byref(options), C.byref(out), C.byref(n)))
+        return self._take_proof(out, n)
+
+    def prove_columns(self, air_id: int, columns, pub: np.ndarray, options: ProofOptions, repr: int = REPR_CANONICAL) -> bytes:
+        """csg_prove_columns: one separately allocated array per trace column (how a winterfell TraceTable holds them)"""
+        columns = [np.ascontiguousarray(c, dtype=np.uint64) for c in columns]
+        if len(columns) != TRACE_WIDTH[air_id] or len({c.size for c in columns}) != 1:
+            raise CsgError(f"{TRACE_WIDTH[air_id]} columns of equal length expected")
+        pub = np.ascontiguousarray(pub, dtype=np.uint64)
+        ptrs = (_u64p * len(columns))(*[_p64(c) for c in columns])
+        out, n = _u8p(), C.c_size_t()
+        self._check(lib().csg_prove_columns(self._h, air_id, ptrs, repr, columns[0].size, _p64(pub), pub.size, C.byref(options), C.byref(out), C.byref(n)))
         return self._take_proof(out, n)
 
     # ---- level 2 pieces used by benchmarks: trace resident in HBM, proved repeatedly

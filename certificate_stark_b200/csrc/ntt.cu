@@ -15,6 +15,12 @@ namespace {
 constexpr unsigned TILE_LOG = CSG_NTT_TILE_LOG;   // elements staged per CTA (2^13 = 64 KB of shared memory + padding)
 constexpr unsigned MAX_SUB_LOG = 11;   // largest single sub-transform
 constexpr unsigned NTT_THREADS = 256;
+#ifndef CSG_NTT_SHAPE_A_DEFAULT
+#define CSG_NTT_SHAPE_A_DEFAULT 8
+#endif
+#ifndef CSG_NTT_SHAPE_B_DEFAULT
+#define CSG_NTT_SHAPE_B_DEFAULT 8
+#endif
 
 struct PassArgs {
     const fe *in; fe *out;
@@ -151,6 +157,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
 // straight from global memory; strided lanes (pass A) are staged as a tile of 8 adjacent lanes, as are all outputs.
 struct Fft32Tw { fe w[16]; };   // w32^j, j < 16 (forward or inverse)
 
+
 // 32-point transform in registers, decimation in time: v[r] = x[brev5(r)] on entry, v[k] = X[k] on exit; values in [0, 2p)
 __device__ __forceinline__ void fft32_dit(uint64_t (&v)[32], const Fft32Tw &tw) {
 #pragma unroll
@@ -178,8 +185,10 @@ __device__ __forceinline__ constexpr int brev5(int r) { return ((r & 1) << 4) | 
 // F_LANES lanes (= warps) per CTA; lane pitch chosen so that the staged accesses (lane fastest) of a half-warp hit distinct banks
 template <int F_LANES> struct FastShape { static constexpr unsigned SP = F_LANES == 8 ? 1024 + 2 : 1024 + 4, THREADS = 32 * F_LANES, LOG = F_LANES == 8 ? 3 : 2; };
 
-template <bool STAGE_IN, int F_LANES>
-__global__ void __launch_bounds__(32 * F_LANES, 512 / (32 * F_LANES)) ntt1024_kernel(PassArgs a, Fft32Tw tw32) {
+// MINB: resident CTAs per SM the register allocation is sized for (2 x 8 lanes and 4 x 4 lanes = 16 warps at 128 registers;
+// 5 x 4 lanes = 20 warps at 102 registers, still without spills; shared memory allows no more than 5 CTAs of 4 lanes)
+template <bool STAGE_IN, int F_LANES, int MINB>
+__global__ void __launch_bounds__(32 * F_LANES, MINB) ntt1024_kernel(PassArgs a, Fft32Tw tw32) {
     constexpr unsigned F_SP = FastShape<F_LANES>::SP, NTH = FastShape<F_LANES>::THREADS, LLOG = FastShape<F_LANES>::LOG;
     extern __shared__ fe sm[];
     fe *T2 = sm + (size_t)F_LANES * F_SP;          // w1024^(+-b c) at [c*32 + b]
@@ -321,12 +330,12 @@ bool fast1024_applies(const PassArgs &a) {
     if (off || a.logS != 10 || a.out_sl != 1 || a.nlanes < 8) return false;
     return a.in_sl == 1 || a.in_se == 1;
 }
-template <bool STAGE_IN, int F_LANES>
+template <bool STAGE_IN, int F_LANES, int MINB>
 void launch_fast1024_as(const PassArgs &a, const Fft32Tw &tw, unsigned ncols, unsigned ncosets, Stream &st) {
     const size_t smem = ((size_t)F_LANES * FastShape<F_LANES>::SP + 1024 + 3 * FastShape<F_LANES>::THREADS) * sizeof(fe);
     dim3 grid((a.nlanes + F_LANES - 1) / F_LANES, ncols, ncosets);
-    CSG_CUDA(cudaFuncSetAttribute(ntt1024_kernel<STAGE_IN, F_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CSG_LAUNCH(st, (ntt1024_kernel<STAGE_IN, F_LANES>), grid, FastShape<F_LANES>::THREADS, smem, a, tw);
+    CSG_CUDA(cudaFuncSetAttribute(ntt1024_kernel<STAGE_IN, F_LANES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CSG_LAUNCH(st, (ntt1024_kernel<STAGE_IN, F_LANES, MINB>), grid, FastShape<F_LANES>::THREADS, smem, a, tw);
 }
 void launch_fast1024(const PassArgs &a, unsigned ncols, unsigned ncosets, Stream &st) {
     Fft32Tw tw;
@@ -334,10 +343,18 @@ void launch_fast1024(const PassArgs &a, unsigned ncols, unsigned ncosets, Stream
     if (a.inverse) w32 = inv(w32);
     fe acc = ONE;
     for (int j = 0; j < 16; j++) { tw.w[j] = acc; acc = mul(acc, w32); }
-    static const int lanes_a = getenv("CSG_NTT_LANES_A") ? atoi(getenv("CSG_NTT_LANES_A")) : 8;   // tuning knobs (A/B runs)
-    static const int lanes_b = getenv("CSG_NTT_LANES_B") ? atoi(getenv("CSG_NTT_LANES_B")) : 8;
-    if (a.in_sl == 1) { if (lanes_a == 8) launch_fast1024_as<true, 8>(a, tw, ncols, ncosets, st); else launch_fast1024_as<true, 4>(a, tw, ncols, ncosets, st); }
-    else { if (lanes_b == 8) launch_fast1024_as<false, 8>(a, tw, ncols, ncosets, st); else launch_fast1024_as<false, 4>(a, tw, ncols, ncosets, st); }
+    // shape of a pass: 8 = two CTAs of 8 lanes, 4 = four CTAs of 4 lanes, 5 = five CTAs of 4 lanes per SM (tuning knobs for A/B runs)
+    static const int shape_a = getenv("CSG_NTT_SHAPE_A") ? atoi(getenv("CSG_NTT_SHAPE_A")) : CSG_NTT_SHAPE_A_DEFAULT;
+    static const int shape_b = getenv("CSG_NTT_SHAPE_B") ? atoi(getenv("CSG_NTT_SHAPE_B")) : CSG_NTT_SHAPE_B_DEFAULT;
+    if (a.in_sl == 1) {
+        if (shape_a == 8) launch_fast1024_as<true, 8, 2>(a, tw, ncols, ncosets, st);
+        else if (shape_a == 4) launch_fast1024_as<true, 4, 4>(a, tw, ncols, ncosets, st);
+        else launch_fast1024_as<true, 4, 5>(a, tw, ncols, ncosets, st);
+    } else {
+        if (shape_b == 8) launch_fast1024_as<false, 8, 2>(a, tw, ncols, ncosets, st);
+        else if (shape_b == 4) launch_fast1024_as<false, 4, 4>(a, tw, ncols, ncosets, st);
+        else launch_fast1024_as<false, 4, 5>(a, tw, ncols, ncosets, st);
+    }
 }
 
 void launch_pass(const PassArgs &a, unsigned ncols, unsigned ncosets, Stream &st) {

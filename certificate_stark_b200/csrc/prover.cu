@@ -276,8 +276,18 @@ struct csg_ctx {
     // Stage 1 runs column chunk by column chunk: representation change, interpolation and the `blowup` coset transforms of
     // a chunk need nothing from the other columns, so when the trace still lives in host memory (csg_prove) the H2D copy
     // of chunk c+1 overlaps the extension of chunk c.  host == nullptr: the canonical trace is already in d_io.
-    void extend_and_commit_trace(uint8_t root[32], const uint64_t *host = nullptr, int host_repr = CSG_REPR_CANONICAL) {
-        if (host) { check_repr(host_repr); trace_repr = host_repr; }
+    // host: the whole trace, column-major, in one allocation; host_cols: one pointer per column (a TraceTable's Vec<Vec<_>>)
+    void extend_and_commit_trace(uint8_t root[32], const uint64_t *host = nullptr, int host_repr = CSG_REPR_CANONICAL, const uint64_t *const *host_cols = nullptr) {
+        std::vector<const uint64_t *> colptr;
+        if (host || host_cols) {
+            check_repr(host_repr); trace_repr = host_repr;
+            colptr.resize(air.width);
+            for (size_t c = 0; c < air.width; c++) {
+                colptr[c] = host_cols ? host_cols[c] : host + c * n;
+                if (!colptr[c]) throw ArgError("null trace column");
+            }
+            if (!host) host = colptr[0];
+        }
         if (!host) need(S_TRACE, "csg_load_trace must be called first");
         else need(S_AIR, "csg_set_air must be called first");
         const size_t w = air.width;
@@ -290,7 +300,9 @@ struct csg_ctx {
         Timer &t = stage_timer;
         t.start(st);
         d_io.reserve(w * n); d_polys.reserve(wpad * n); scratch.reserve(wpad * n); d_lde.reserve(w * n * bl);
-        const bool staged = host && is_pageable(host);
+        bool any_pageable = false;
+        if (host) for (size_t c = c_lo; c < c_hi && !any_pageable; c++) any_pageable = is_pageable(colptr[c]);
+        const bool staged = host && any_pageable;
         if (host) {
             if (!copy_stream) CSG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
             while (chunk_ev.size() < (cpr + CHUNK - 1) / CHUNK + 1) { cudaEvent_t e; CSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); chunk_ev.push_back(e); }
@@ -309,20 +321,24 @@ struct csg_ctx {
         for (size_t c0 = c_lo, k = 0; c0 < c_hi; c0 += CHUNK, k++) {
             const size_t nc = std::min(CHUNK, c_hi - c0);
             if (host) {
-                const uint64_t *src = host + c0 * n;
+                bool contiguous = true;
+                for (size_t j = 1; j < nc; j++) contiguous = contiguous && colptr[c0 + j] == colptr[c0] + j * n;
+                const uint64_t *src = colptr[c0];
                 if (staged) {   // host threads fill a pinned buffer while the GPU extends the previous chunks
                     uint64_t *buf = stage_buf[k % STAGE_BUFS];
                     if (k >= STAGE_BUFS) CSG_CUDA(cudaEventSynchronize(stage_ev[k % STAGE_BUFS]));
-                    const size_t words = nc * n, SL = (size_t)1 << 17;   // 1 MB slices
-                    const long long nsl = (long long)((words + SL - 1) / SL);
+                    const size_t SL = (size_t)1 << 17, per_col = (n + SL - 1) / SL;   // 1 MB slices of each column
+                    const long long nsl = (long long)(per_col * nc);
 #pragma omp parallel for schedule(static)
                     for (long long sl = 0; sl < nsl; sl++) {
-                        const size_t o = (size_t)sl * SL;
-                        memcpy(buf + o, src + o, std::min(SL, words - o) * sizeof(uint64_t));
+                        const size_t j = (size_t)sl / per_col, o = ((size_t)sl % per_col) * SL;
+                        memcpy(buf + j * n + o, colptr[c0 + j] + o, std::min(SL, n - o) * sizeof(uint64_t));
                     }
-                    src = buf;
+                    src = buf; contiguous = true;
                 }
-                CSG_CUDA(cudaMemcpyAsync(d_io.p + c0 * n, src, nc * n * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
+                if (contiguous) CSG_CUDA(cudaMemcpyAsync(d_io.p + c0 * n, src, nc * n * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
+                else for (size_t j = 0; j < nc; j++)
+                    CSG_CUDA(cudaMemcpyAsync(d_io.p + (c0 + j) * n, colptr[c0 + j], n * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
                 if (staged) CSG_CUDA(cudaEventRecord(stage_ev[k % STAGE_BUFS], copy_stream));
                 CSG_CUDA(cudaEventRecord(chunk_ev[k], copy_stream));
                 if (c0 + CHUNK >= c_hi) CSG_CUDA(cudaEventRecord(h2d_b, copy_stream));
@@ -811,8 +827,8 @@ struct csg_ctx {
         for (const xe &e : v) for (int j = 0; j < d; j++) out.push_back(e.c[j]);
         return out;
     }
-    void prove_loaded(uint8_t **proof, size_t *proof_len, const uint64_t *host = nullptr, int host_repr = CSG_REPR_CANONICAL) {
-        if (!host) need(S_TRACE, "csg_load_trace must be called first");
+    void prove_loaded(uint8_t **proof, size_t *proof_len, const uint64_t *host = nullptr, int host_repr = CSG_REPR_CANONICAL, const uint64_t *const *host_cols = nullptr) {
+        if (!host && !host_cols) need(S_TRACE, "csg_load_trace must be called first");
         auto t0 = std::chrono::steady_clock::now();
         const unsigned long long launches0 = st.launches;
         comm_used = 0;
@@ -825,7 +841,7 @@ struct csg_ctx {
         auto base = [](const std::vector<xe> &v) { std::vector<fe> o; for (const xe &e : v) o.push_back(e.c[0]); return o; };
 
         uint8_t trace_root[32], comp_root[32];
-        extend_and_commit_trace(trace_root, host, host_repr);
+        extend_and_commit_trace(trace_root, host, host_repr, host_cols);
         coin.reseed(trace_root);
         std::vector<xe> t_ab(2 * nc), b_ab(2 * na + 2, x_zero());
         for (size_t i = 0; i < 2 * nc; i++) t_ab[i] = coin.draw_x(d);
@@ -1081,6 +1097,16 @@ int csg_prove_trace(csg_ctx *ctx, const uint64_t *trace, int repr, uint8_t **pro
         csg_ctx::check_repr(repr);
         ctx->need(S_AIR, "csg_set_air must be called first");
         ctx->prove_loaded(proof, proof_len, trace, repr);
+    });
+}
+// the same with one pointer per column: a winterfell TraceTable keeps each column in its own Vec
+int csg_prove_columns(csg_ctx *ctx, int air_id, const uint64_t *const *columns, int repr, size_t trace_len, const uint64_t *pub, size_t npub,
+                      const csg_options *opt, uint8_t **proof, size_t *proof_len) {
+    return guarded(ctx, [&] {
+        if (!columns || !proof || !proof_len) throw ArgError("null argument");
+        csg_ctx::check_repr(repr);
+        ctx->set_air(air_id, trace_len, opt, pub, npub);
+        ctx->prove_loaded(proof, proof_len, nullptr, repr, columns);
     });
 }
 // page-locked host memory for traces: the H2D copy of csg_prove / csg_prove_trace then runs at link speed under the extension

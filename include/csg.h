@@ -82,6 +82,12 @@ int csg_host_unregister(void *p);
 int csg_prove(csg_ctx *ctx, int air_id, const uint64_t *trace, int repr, size_t trace_len, const uint64_t *pub, size_t npub,
               const csg_options *opt, uint8_t **proof, size_t *proof_len);
 
+/* the same with one pointer per column (columns[c] -> trace_len words): a winterfell TraceTable keeps every column in its own
+ * Vec<BaseElement> (TraceTable::get_column, used at src/prover.rs:107-127), so its memory crosses the boundary without being copied
+ * together first */
+int csg_prove_columns(csg_ctx *ctx, int air_id, const uint64_t *const *columns, int repr, size_t trace_len, const uint64_t *pub, size_t npub,
+                      const csg_options *opt, uint8_t **proof, size_t *proof_len);
+
 /* ---- verification: replaces `winterfell::verify::<Air>(proof, pub_inputs)` (src/lib.rs:144-150).  Host-only, as in the
  * reference; needs no context and no GPU.  Returns CSG_OK or one of CSG_VERIFY_*. */
 int csg_verify(int air_id, const uint64_t *pub, size_t npub, const uint8_t *proof, size_t proof_len);

@@ -121,6 +121,10 @@ def test_trace_representations_and_memory_kinds_small(ctx, oracle, csg):
     assert ctx.prove(csg.AIR_TRANSACTION, mh, pub, csg.ProofOptions(), repr=csg.REPR_MONTGOMERY) == want
     with pytest.raises(csg.CsgError):
         ctx.prove(csg.AIR_TRANSACTION, trace, pub, csg.ProofOptions(), repr=2)
+    # one separately allocated array per column, as a winterfell TraceTable holds them (csg_prove_columns)
+    columns = [np.array(mont[c]) for c in range(94)]
+    assert ctx.prove_columns(csg.AIR_TRANSACTION, columns, pub, csg.ProofOptions(), repr=csg.REPR_MONTGOMERY) == want
+    assert ctx.prove_columns(csg.AIR_TRANSACTION, [np.array(trace[c]) for c in range(94)], pub, csg.ProofOptions()) == want
     hb = csg.HostBuffer(94, trace.shape[1])
     try:
         hb.array[:] = trace

@@ -37,7 +37,8 @@ template <int V> __device__ __forceinline__ void bfly(uint64_t &x, uint64_t &y, 
         uint64_t s = add64_fma(a, t, one);
         x = s >= 2 * P ? s - 2 * P : s;
         y = sub_2p(a, t);
-    } else if (V == 3) {   // mask form of the conditional corrections (shift + and instead of compare + select)
+    } else if (V == 3) {   // mask form of the conditional corrections (shift + and instead of compare + select).  NOT EXACT: the sign test
+                           // misreads a + t < 2p - 2^63 (e.g. both zero); timed only to see what three instructions fewer would buy (8 %)
         const uint64_t t = mul_2p(y, w), a = x;
         uint64_t s = a + t - 2 * P;                                  // a + t < 3.52p: s "negative" exactly when a + t < 2p
         uint64_t m = (uint64_t)((int64_t)s >> 63);                    // wrong when s >= 2^63 legitimately: s < 1.52p < 2^63, fine
@@ -130,6 +131,30 @@ template <int V, int THREADS> __global__ void __launch_bounds__(THREADS, 1) kbo(
     if (s == 0x12345678u) out[threadIdx.x] = s;
 }
 
+// FP64 pipe: is it a third pipe next to fmaheavy (IMAD) and alu?  DFMA alone, DFMA interleaved with IMAD.WIDE, and the int <-> double conversions
+template <int KIND> __global__ void __launch_bounds__(1024, 1) kd(uint64_t *out, uint32_t seed, double dscale) {
+    double acc[8], x = 1.0 + seed * 1e-9, y = dscale;
+    uint64_t q[8];
+    uint32_t c = seed | 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i] = threadIdx.x + i; q[i] = ((uint64_t)(seed + i) << 32) | threadIdx.x; }
+    for (int it = 0; it < ITER; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (KIND == 0) acc[i] = fma(acc[i], x, y);                                                   // DFMA
+            else if (KIND == 1) { acc[i] = fma(acc[i], x, y); q[i] = (uint64_t)(uint32_t)q[i] * c + q[i]; }   // DFMA + IMAD.WIDE 1:1
+            else if (KIND == 2) { acc[i] = fma(acc[i], x, y); acc[i] = fma(acc[i], y, x); q[i] = (uint64_t)(uint32_t)q[i] * c + q[i]; }   // 2:1
+            else if (KIND == 3) { acc[i] = (double)(uint32_t)(q[i] >> 11) * x + acc[i]; q[i] += c; }      // I2F.F64.U32 + DFMA
+            else if (KIND == 4) { q[i] += (uint64_t)(long long)(acc[i]); acc[i] = fma(acc[i], x, y); }    // F2I.S64.F64 + DFMA
+            else if (KIND == 5) { acc[i] = fma(acc[i], x, y); q[i] = ((uint32_t)q[i] + c) ^ (uint32_t)(q[i] >> 32); }   // DFMA + ALU
+        }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= (uint64_t)__double_as_longlong(acc[i]) ^ q[i];
+    if (s == 0x12345678u) out[threadIdx.x] = s;
+}
+
 template <class F> int timed(const char *name, F launch) {
     cudaEvent_t a, b;
     CHK(cudaEventCreate(&a)); CHK(cudaEventCreate(&b));
@@ -158,6 +183,12 @@ int main() {
     RUNK(0) RUNK(1) RUNK(2) RUNK(3) RUNK(4) RUNK(5) RUNK(6) RUNK(7) RUNK(8) RUNK(9) RUNK(10) RUNK(11) RUNK(12) RUNK(13)
 #define RUNB(V) timed("butterfly " #V, [&](int r) { kb<V><<<s, 1024>>>(d, 12345 + r, 1); });
     RUNB(0) RUNB(1) RUNB(2) RUNB(3)
+    timed("dfma", [&](int r) { kd<0><<<s, 1024>>>(d, 12345 + r, 0.5); });
+    timed("dfma+wide", [&](int r) { kd<1><<<s, 1024>>>(d, 12345 + r, 0.5); });
+    timed("2dfma+wide", [&](int r) { kd<2><<<s, 1024>>>(d, 12345 + r, 0.5); });
+    timed("i2f+dfma", [&](int r) { kd<3><<<s, 1024>>>(d, 12345 + r, 0.5); });
+    timed("f2i+dfma", [&](int r) { kd<4><<<s, 1024>>>(d, 12345 + r, 0.5); });
+    timed("dfma+alu", [&](int r) { kd<5><<<s, 1024>>>(d, 12345 + r, 0.5); });
     timed("mac x2", [&](int r) { kmac<2><<<s, 1024>>>(d, 12345 + r); });
     timed("mac x4", [&](int r) { kmac<4><<<s, 1024>>>(d, 12345 + r); });
     timed("mac x8", [&](int r) { kmac<8><<<s, 1024>>>(d, 12345 + r); });
