@@ -7,6 +7,8 @@
  *   SchnorrAir       src/schnorr/air.rs:47-585
  *   RangeProofAir    src/range/air.rs:43-105
  *   RescueAir        benches/rescue.rs:163-268
+ * Pinned against a second, independent restatement of the same files (oracle/pyair.py): tests/golden/air_vectors.txt holds result[]
+ * vectors, degrees, periodic-column fingerprints and assertions for all six AIRs; tests/host_harness.cpp checks this file against them.
  */
 #ifndef ORACLE_AIR_H
 #define ORACLE_AIR_H
