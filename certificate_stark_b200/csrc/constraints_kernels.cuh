@@ -19,6 +19,22 @@ struct RowCtx {
     airs::Periodic pv;
     fe x;
 };
+// The row kernels read each LDE column once, a value at a time, as the straight-line constraint code reaches it: every first touch
+// of a column is an exposed trip to HBM (ncu: long_scoreboard 3.4-7.6 warps per issue in the linear-rest, merge and final kernels).
+// One TMA bulk prefetch per column at the top of the CTA (cp.async.bulk.prefetch.L2: no destination, no barrier, one instruction
+// per 1 KB segment, issued by the first warps) brings the CTA's 128-row segment of every column it will read into L2 while the
+// prologue runs; the loads then cost an L2 hit.  Segments are 1 KB-aligned (row index a multiple of 128) and clamped to the column.
+__device__ __forceinline__ void prefetch_tile_l2(const fe *base, unsigned long long col_stride, unsigned col0, unsigned ncols, unsigned long long i0,
+                                                 unsigned long long n) {
+#ifndef CSG_NO_TILE_PREFETCH
+    const unsigned long long rows = n - i0 < (unsigned long long)CONS_THREADS + 2 ? n - i0 : (unsigned long long)CONS_THREADS + 2;
+    const unsigned bytes = (unsigned)(rows * sizeof(fe)) & ~15u;
+    if (!bytes) return;
+    for (unsigned c = threadIdx.x; c < ncols; c += CONS_THREADS)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (unsigned long long)(col0 + c) * col_stride + i0), "r"(bytes) : "memory");
+#endif
+}
+
 // common prologue: frame, periodic accessor, x and the x^adj table of this thread's row
 __device__ __forceinline__ RowCtx row_setup(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ W,
                                             const fe *__restrict__ ptab, unsigned kc, unsigned long long i, fe (*xp_s)[CONS_THREADS]) {
@@ -184,6 +200,7 @@ cons_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, cons
     if (i >= n) return;
     const unsigned long long inext = (i + 1) & (n - 1);
     const fe *base = lde + A->lde_coset_stride[kc];
+    if (KIND == 3) prefetch_tile_l2(base, A->col_stride, 0, A->width, blockIdx.x * (unsigned long long)CONS_THREADS, n);
     airs::Frame f{base + i, base + inext, (size_t)A->col_stride};
     airs::Periodic pv{ptab + kc * A->ptab_coset_stride, A->poff, A->pmask, (uint32_t)i};
     for (unsigned k = 0; k < 3 * airs::MAX_SPLIT_GROUPS * DEG; k++) part_dyn[k * CONS_THREADS + threadIdx.x] = 0;
@@ -204,6 +221,7 @@ cons_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, cons
 // mixed-addition formula of each bank -- 4 variants -- on the even cosets, as an alpha polynomial and one beta polynomial per
 // degree group the bank's slots fall into, per component.
 constexpr unsigned ECC_SPLIT_MAX_POLYS = 16;
+constexpr unsigned ECC_SUPER = 512;   // row tiles per turn of a variant (cons_ecc_low_kernel)
 struct EccSplitMap {
     unsigned npolys[2];                                // bank b: 1 + number of groups among its point slots
     unsigned char groups[2][airs::MAX_SPLIT_GROUPS];   // those groups
@@ -215,8 +233,14 @@ template <int AIR, int DEG>
 __global__ void __launch_bounds__(CONS_THREADS, CSG_ECC_MINBLOCKS)
 cons_ecc_low_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, const fe *__restrict__ ptab, EccSplitMap M, fe *__restrict__ eccl) {
     extern __shared__ uint64_t part_dyn[];
-    const unsigned j = blockIdx.y, kc = 2 * j, v = blockIdx.z, bank = v >> 1, L = A->ncosets / 2, npb = M.npolys[bank];
-    const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
+    // The two formulas of a bank read the same 18 point columns.  Launched as separate grid planes the second read came from
+    // DRAM again (ncu, round 1: 3.56 GB of traffic against 1.95 GB algorithmic); with the four variants of one tile as
+    // neighbouring CTAs it is an L2 hit but four instruction streams share every SM (+2 % time).  So the grid runs the variants
+    // in turns over super-tiles of ECC_SUPER row tiles: one code stream at a time, and the re-read is ~16 MB later, inside L2.
+    const unsigned j = blockIdx.y, kc = 2 * j, L = A->ncosets / 2;
+    const unsigned rem = blockIdx.x % (4 * ECC_SUPER), v = rem / ECC_SUPER, bank = v >> 1, npb = M.npolys[bank];
+    const unsigned long long n = 1ULL << A->logn, tile = (unsigned long long)(blockIdx.x / (4 * ECC_SUPER)) * ECC_SUPER + rem % ECC_SUPER;
+    const unsigned long long i = tile * CONS_THREADS + threadIdx.x;
     if (i >= n) return;
     const unsigned long long inext = (i + 1) & (n - 1);
     const fe *base = lde + A->lde_coset_stride[kc];
@@ -242,6 +266,13 @@ cons_ecc_merge_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde
     const unsigned kc = blockIdx.y, bank = blockIdx.z, L = A->ncosets / 2, npb = M.npolys[bank];
     const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
     if (i >= n) return;
+    {   // this CTA's segment of the bank's point and bit columns, and of the extended formula polynomials
+        const unsigned long long i0 = blockIdx.x * (unsigned long long)CONS_THREADS;
+        prefetch_tile_l2(lde + A->lde_coset_stride[kc], A->col_stride, bank * (airs::PPW + 1), airs::PPW + 1, i0, n);
+        const fe *lp = ((kc & 1) ? odd : even) + (unsigned long long)(kc >> 1) * n;
+        for (unsigned formula = 0; formula < 2; formula++)
+            prefetch_tile_l2(lp + (unsigned long long)M.base[2 * bank + formula] * DEG * L * n, (unsigned long long)L * n, 0, DEG * npb, i0, n);
+    }
     RowCtx r = row_setup(A, lde, W, ptab, kc, i, xp_s);
     airs::CombT<false, DEG> C{A->alpha, A->beta, A->group, &xp_s[0][threadIdx.x], (size_t)CONS_THREADS, acc192(), nullptr, 0,
                               &A->alpha_x[0][0], &A->beta_x[0][0], (size_t)CONS_MAX_CONSTRAINTS};
@@ -270,6 +301,12 @@ cons_final_kernel(const ConsArgs *__restrict__ A, const fe *__restrict__ lde, co
     const unsigned kc = blockIdx.y, L = A->ncosets / 2, NP = 1 + A->ngroups;
     const unsigned long long n = 1ULL << A->logn, i = blockIdx.x * (unsigned long long)CONS_THREADS + threadIdx.x;
     if (i >= n) return;
+    {   // the CTA's segment of every array it sums: A and the B_g of every component, the curve partial sums, the divisor inverses
+        const unsigned long long i0 = blockIdx.x * (unsigned long long)CONS_THREADS;
+        prefetch_tile_l2(((kc & 1) ? low_odd : low_even) + (unsigned long long)(kc >> 1) * n, (unsigned long long)L * n, 0, DEG * NP, i0, n);
+        prefetch_tile_l2(hi + (unsigned long long)kc * n, (unsigned long long)A->ncosets * n, 0, DEG * nhi, i0, n);
+        prefetch_tile_l2(binv + (unsigned long long)kc * n, (unsigned long long)A->ncosets * n, 0, A->nbgroups, i0, n);
+    }
     const fe x = mul(A->shift[kc], W[i]);
     const fe *low0 = ((kc & 1) ? low_odd : low_even) + (unsigned long long)(kc >> 1) * n + i;   // component c: + c * NP * L * n
     const unsigned long long comp_stride = (unsigned long long)NP * L * n;
@@ -384,7 +421,7 @@ void launch_split(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, co
     CSG_LAUNCH(st, (cons_low_kernel<AIR, 0, DEG>), dim3(gx, L, NR), CONS_THREADS, smem, args_dev, lde, W, ptab, low_parts, 0u);
     mark(1);
     if (ecc_split) {
-        CSG_LAUNCH(st, (cons_ecc_low_kernel<AIR, DEG>), dim3(gx, L, 4), CONS_THREADS, smem, args_dev, lde, ptab, M, eccl_even);
+        CSG_LAUNCH(st, (cons_ecc_low_kernel<AIR, DEG>), dim3((gx + ECC_SUPER - 1) / ECC_SUPER * 4 * ECC_SUPER, L, 1), CONS_THREADS, smem, args_dev, lde, ptab, M, eccl_even);
         mark(5);   // ev[1] .. ev[5]: the curve-formula kernel alone, the largest single launch of a proof
         extend(eccl_even, eccl_coef, eccl_mix, eccl_odd, DEG * M.total);
         CSG_LAUNCH(st, (cons_ecc_merge_kernel<AIR, DEG>), dim3(gx, ce, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, M, (const fe *)eccl_even, (const fe *)eccl_odd, hi,
