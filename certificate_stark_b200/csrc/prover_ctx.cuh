@@ -411,6 +411,25 @@ struct csg_ctx {
         }
         return total;
     }
+    // Out-of-domain evaluation of a sharded proof: every context evaluates the column block it interpolated (the same block of
+    // csg_dist_plan), the few hundred values are all-gathered.  vals: `per_col` values for each of this rank's columns; returns
+    // the values of all `ncols` columns in column order.
+    DBuf<fe> d_ood_xch;
+    std::vector<fe> gather_column_values(const std::vector<fe> &mine, size_t per_col, size_t ncols) {
+        csg_shard_plan plan;
+        shard_plan(rank, G, b, ce, ncols, &plan);
+        const size_t cpr = plan.columns_per_rank, slice = cpr * per_col;
+        d_ood_xch.reserve(std::max<size_t>(slice * G, 64));
+        std::vector<fe> padded(slice, 0);
+        std::copy(mine.begin(), mine.end(), padded.begin());
+        CSG_CUDA(cudaMemcpyAsync(d_ood_xch.p + rank * slice, padded.data(), slice * sizeof(fe), cudaMemcpyHostToDevice, st.s));
+        gather(d_ood_xch.p, slice * sizeof(fe));
+        std::vector<fe> all(slice * G);
+        CSG_CUDA(cudaMemcpyAsync(all.data(), d_ood_xch.p, all.size() * sizeof(fe), cudaMemcpyDeviceToHost, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+        all.resize(ncols * per_col);   // blocks are consecutive columns; only the last one is padded
+        return all;
+    }
     // Row digests of a coset-major matrix into the leaves of `nodes`, then the tree.  Sharded: each context hashes the rows
     // of its cosets, the digests are all-gathered and put in natural order, and every context builds the whole tree --
     // 2^23 leaves take 0.35 ms, less than the second exchange that per-GPU subtrees would need to answer the queries.
@@ -587,7 +606,17 @@ struct csg_ctx {
         const size_t w = air.width;
         const fe pts[2] = {z, mul(z, root_of_unity(logn))};
         std::vector<fe> vals(2 * w);
-        eval_polys_at(d_polys.p, n, w, n, pts, 2, vals.data(), scratch2, st);
+        if (G == 1) eval_polys_at(d_polys.p, n, w, n, pts, 2, vals.data(), scratch2, st);
+        else {   // own column block only (1/G of the 0.8 GB of coefficients), then a tiny all-gather: [column][point]
+            csg_shard_plan plan;
+            shard_plan(rank, G, b, ce, w, &plan);
+            const size_t c_lo = plan.first_column, nc = plan.num_columns;
+            std::vector<fe> blk(2 * nc), mine(2 * nc);
+            if (nc) eval_polys_at(d_polys.p + c_lo * n, n, nc, n, pts, 2, blk.data(), scratch2, st);   // [point][column]
+            for (size_t c = 0; c < nc; c++) { mine[2 * c] = blk[c]; mine[2 * c + 1] = blk[nc + c]; }
+            const std::vector<fe> all = gather_column_values(mine, 2, w);
+            for (size_t c = 0; c < w; c++) { vals[c] = all[2 * c]; vals[w + c] = all[2 * c + 1]; }
+        }
         ood_cur.assign(vals.begin(), vals.begin() + w);
         ood_next.assign(vals.begin() + w, vals.end());
         const fe zm = f63::pow(z, ce);
@@ -642,7 +671,15 @@ struct csg_ctx {
         d_pw.reserve(2 * (size_t)d * n);
         ext_power_table(d, pts, 2, n, d_pw.p, st);
         std::vector<fe> vals(w * 2 * d);
-        dot_columns(d_polys.p, n, w, n, d_pw.p, 2 * d, vals.data(), scratch2, st);
+        if (G == 1) dot_columns(d_polys.p, n, w, n, d_pw.p, 2 * d, vals.data(), scratch2, st);
+        else {   // own column block, then the all-gather of [column][2 d] values
+            csg_shard_plan plan;
+            shard_plan(rank, G, b, ce, w, &plan);
+            const size_t c_lo = plan.first_column, nc = plan.num_columns;
+            std::vector<fe> mine(nc * 2 * d);
+            if (nc) dot_columns(d_polys.p + c_lo * n, n, nc, n, d_pw.p, 2 * d, mine.data(), scratch2, st);
+            vals = gather_column_values(mine, 2 * (size_t)d, w);
+        }
         xood_cur.assign(w, x_zero()); xood_next.assign(w, x_zero());
         for (size_t c = 0; c < w; c++)
             for (int j = 0; j < d; j++) { xood_cur[c].c[j] = vals[c * 2 * d + j]; xood_next[c].c[j] = vals[c * 2 * d + d + j]; }
