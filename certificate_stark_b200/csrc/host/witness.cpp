@@ -426,6 +426,48 @@ csg_tx_batch *csg_tx_batch_new(uint64_t seed, size_t num_tx, unsigned tree_depth
     }
     return B;
 }
+// Test helper (no GPU needed): executes the device builder's plan (batch_plan.hpp) on the host, step for step what batch_gen.cu's
+// kernels do -- leaf hashes, one merge per node version level by level, path gathers, signatures -- and writes the packed records.
+// tests/test_host.py compares them with csg_tx_batch_pack of the sequential host builder: that pins the PLAN (which versions exist,
+// which children they merge, which versions the paths read) in the CPU suite; the kernels themselves are pinned on the GPU.
+int csg_debug_tx_batch_plan_records(uint64_t seed, size_t num_tx, unsigned tree_depth, uint64_t *out /* 278 words per transfer */, uint64_t pub[14]) {
+    csg::BatchPlan P;
+    try { P = csg::plan_tx_batch(seed, num_tx, tree_depth); } catch (const std::exception &) { return CSG_ERR_ARG; }
+    const size_t total = P.level_off[P.depth + 1];
+    std::vector<Hash7> hashes(total), defaults(P.depth + 1);
+    defaults[0].fill(0);
+    for (unsigned l = 0; l < P.depth; l++) rescue::merge(defaults[l].data(), defaults[l].data(), defaults[l + 1].data());
+    auto version = [&](int32_t ref) -> const Hash7 & { return ref >= 0 ? hashes[ref] : defaults[-ref - 1]; };
+#pragma omp parallel for schedule(static)
+    for (long g = 0; g < (long)P.level_off[1]; g++) rescue::merge(&P.accounts[14 * g], &P.accounts[14 * g + 7], hashes[g].data());
+    for (unsigned l = 1; l <= P.depth; l++) {
+#pragma omp parallel for schedule(static)
+        for (long id = P.level_off[l]; id < (long)P.level_off[l + 1]; id++) rescue::merge(version(P.left[id]).data(), version(P.right[id]).data(), hashes[id].data());
+    }
+    const size_t W = 278;
+#pragma omp parallel for schedule(dynamic)
+    for (size_t t = 0; t < num_tx; t++) {
+        const uint64_t *w = &P.tx_words[(size_t)csg::BatchPlan::TX_WORDS * t];
+        const int32_t *rf = &P.tx_refs[(size_t)csg::BatchPlan::TX_REFS * t];
+        uint64_t *r = out + t * W;
+        memset(r, 0, W * sizeof(uint64_t));
+        for (int i = 0; i < 28; i++) r[i] = w[i];
+        r[28] = w[28]; r[36] = w[29]; r[37] = w[30];
+        for (int i = 0; i < 7; i++) r[29 + i] = version(rf[32])[i];
+        for (int k = 0; k < 32; k++) for (int i = 0; i < 7; i++) r[38 + 7 * k + i] = version(rf[k])[i];
+        Account s_old, r_old;
+        for (int i = 0; i < 14; i++) { s_old[i] = w[i]; r_old[i] = w[14 + i]; }
+        const Message msg = build_tx_message(s_old, r_old, w[28], s_old[13]);
+        SplitMix64 r2{w[32]};
+        const Signature sig = sign(msg, (unsigned)w[31], r2);
+        for (int i = 0; i < 6; i++) r[262 + i] = sig.rx[i];
+        for (int i = 0; i < 4; i++) r[268 + i] = sig.s.w[i];
+        U256 h = hash_to_scalar_bits(hash_message(sig.rx.data(), msg));
+        for (int i = 0; i < 4; i++) r[272 + i] = h.w[i];
+    }
+    for (int i = 0; i < 7; i++) { pub[i] = f63::from_mont(version(P.tx_refs[32])[i]); pub[7 + i] = f63::from_mont(version(P.final_root)[i]); }
+    return CSG_OK;
+}
 void csg_tx_batch_free(csg_tx_batch *b) { delete b; }
 size_t csg_tx_batch_size(const csg_tx_batch *b) { return b->deltas.size(); }
 void csg_tx_batch_roots(const csg_tx_batch *b, uint64_t initial_root[7], uint64_t final_root[7]) {

@@ -148,6 +148,23 @@ def test_verifier_rejects_weak_or_malformed_contexts(csg, oracle):
     assert csg.verify(csg.AIR_RESCUE, pub, proof, csg.ProofOptions(blowup_factor=2, num_queries=10, fri_max_remainder_size=1024)) == 0
 
 
+@pytest.mark.parametrize("seed,num_tx,depth", [(1, 1, 15), (7, 8, 15), (5, 4, 3), (9, 16, 7), (3, 64, 15)])
+def test_device_batch_plan_executed_on_the_host_gives_the_host_builders_records(csg, seed, num_tx, depth):
+    # the plan of the device-side batch builder (csrc/host/batch_plan.hpp: node versions of the account tree, the children each
+    # merges, the versions every path reads) executed with host hashes must reproduce the sequential builder bit for bit;
+    # depth 3 (the reference's cfg(test) tree) makes slots collide: repeated accounts, senders that were receivers before
+    L = csg.lib()
+    L.csg_debug_tx_batch_plan_records.restype = C.c_int
+    L.csg_debug_tx_batch_plan_records.argtypes = [C.c_uint64, C.c_size_t, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    got, pub = np.zeros((num_tx, 278), dtype=np.uint64), np.zeros(14, dtype=np.uint64)
+    assert L.csg_debug_tx_batch_plan_records(seed, num_tx, depth, got.ctypes.data_as(C.POINTER(C.c_uint64)), pub.ctypes.data_as(C.POINTER(C.c_uint64))) == 0
+    want = csg.TransactionBatch(seed=seed, num_tx=num_tx, tree_depth=depth)
+    assert np.array_equal(pub, want.public_inputs())
+    bad = np.argwhere(got != want.packed_records())
+    assert bad.size == 0, f"first differing (transfer, word): {bad[0]}"
+    assert L.csg_debug_tx_batch_plan_records(seed, 0, depth, got.ctypes.data_as(C.POINTER(C.c_uint64)), pub.ctypes.data_as(C.POINTER(C.c_uint64))) != 0
+
+
 def test_bench_stage_roofline_arithmetic():
     # bench.py's HBM view of the LDE and commitment stages: SURVEY.md 8(d) bytes / stage time, on the round-1 stage times
     import bench
