@@ -24,6 +24,10 @@ struct NcclApi {
     int (*CommDestroy)(void *) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 constexpr int NCCL_UINT8 = 1, NCCL_UINT64 = 5, NCCL_SUM = 0;
@@ -45,9 +49,13 @@ NcclApi &nccl() {
         api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
         api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
         api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.Send = (decltype(api.Send))sym("ncclSend");
+        api.Recv = (decltype(api.Recv))sym("ncclRecv");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
         api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     });
-    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.AllReduce || !api.GetErrorString)
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.AllReduce || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd || !api.GetErrorString)
         throw std::runtime_error("NCCL is not available: libnccl.so.2 could not be loaded (set CSG_NCCL_LIB to its path)");
     return api;
 }
@@ -60,6 +68,14 @@ struct NcclComm final : Comm {
     ~NcclComm() override { if (comm) nccl().CommDestroy(comm); }
     void all_gather(void *buf, size_t bytes, Stream &st) override {
         nccl_check(nccl().AllGather((const char *)buf + (size_t)rank * bytes, buf, bytes, NCCL_UINT8, comm, st.s), "ncclAllGather");
+    }
+    void all_to_all(const void *send, void *recv, size_t bytes, Stream &st) override {
+        nccl_check(nccl().GroupStart(), "ncclGroupStart");
+        for (int p = 0; p < world; p++) {
+            nccl_check(nccl().Send((const char *)send + (size_t)p * bytes, bytes, NCCL_UINT8, p, comm, st.s), "ncclSend");
+            nccl_check(nccl().Recv((char *)recv + (size_t)p * bytes, bytes, NCCL_UINT8, p, comm, st.s), "ncclRecv");
+        }
+        nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
     }
     void all_reduce_sum_u64(uint64_t *buf, size_t count, Stream &st) override {
         nccl_check(nccl().AllReduce(buf, buf, count, NCCL_UINT64, NCCL_SUM, comm, st.s), "ncclAllReduce");
@@ -101,6 +117,15 @@ struct LocalComm final : Comm {
                 CSG_CUDA(cudaMemcpyAsync((char *)buf + (size_t)p * bytes, (const char *)grp->ptr[p] + (size_t)p * bytes, bytes, cudaMemcpyDefault, st.s));
         CSG_CUDA(cudaStreamSynchronize(st.s));
         grp->barrier();                                  // nobody reuses a buffer a peer is still reading
+    }
+    void all_to_all(const void *send, void *recv, size_t bytes, Stream &st) override {
+        CSG_CUDA(cudaStreamSynchronize(st.s));           // own send buffer is complete
+        grp->ptr[rank] = const_cast<void *>(send);
+        grp->barrier();
+        for (int p = 0; p < world; p++)
+            CSG_CUDA(cudaMemcpyAsync((char *)recv + (size_t)p * bytes, (const char *)grp->ptr[p] + (size_t)rank * bytes, bytes, cudaMemcpyDefault, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+        grp->barrier();
     }
     void all_reduce_sum_u64(uint64_t *buf, size_t count, Stream &st) override {
         tmp.reserve(count * (size_t)world);

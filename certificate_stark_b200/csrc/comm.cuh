@@ -1,7 +1,8 @@
 // Collectives of the coset-sharded proof: one proof split over G GPUs by LDE coset.
 //
-// Every exchange of the split is an all-gather of equal slices (trace coefficients by column block, leaf digests,
-// per-coset composition interpolants, DEEP evaluations) or a sum of vectors with disjoint support (opened rows).
+// The exchanges of the split: all-gathers of equal slices (trace coefficients by column block, per-coset composition
+// interpolants, DEEP evaluations, subtree roots), one all-to-all (leaf digests into contiguous leaf ranges, so that every GPU
+// builds the Merkle subtree of its range) and sums of vectors with disjoint support (opened rows and path nodes).
 // Two transports implement them:
 //   * NcclComm  -- one process per GPU (torchrun): NCCL over NVLink/NVSwitch on the proving stream.  libnccl is
 //                  dlopen'ed when the communicator is created, so single-GPU deployments need no NCCL at all.
@@ -21,6 +22,9 @@ struct Comm {
     // in place: buf holds `world` slices of `bytes`; slice `rank` has been produced on stream s; on return (stream order)
     // every slice is filled
     virtual void all_gather(void *buf, size_t bytes, Stream &st) = 0;
+    // recv slice p <- slice `rank` of peer p's send buffer; `world` slices of `bytes` each on both sides (send != recv).
+    // The digest exchange of a commitment: every rank hashed the rows of its cosets and needs the leaves of a contiguous range.
+    virtual void all_to_all(const void *send, void *recv, size_t bytes, Stream &st) = 0;
     // buf[i] = sum over ranks of buf[i]  (u64 wrap-around; callers keep the supports disjoint)
     virtual void all_reduce_sum_u64(uint64_t *buf, size_t count, Stream &st) = 0;
     virtual const char *transport() const = 0;

@@ -63,10 +63,13 @@ __global__ void __launch_bounds__(512) merkle_top_kernel(uint32_t *nodes, unsign
         __syncthreads();
     }
 }
-__global__ void gather_digests_kernel(const uint32_t *nodes, const uint32_t *idx, unsigned count, uint32_t *out) {
+// idx: a node of `nodes`; 0x80000000 | i: node i of `top` (the replicated top levels of a sharded tree); 0xFFFFFFFF: a node another
+// rank owns -- zeros, the digests of all ranks are summed afterwards
+__global__ void gather_digests_kernel(const uint32_t *nodes, const uint32_t *top, const uint32_t *idx, unsigned count, uint32_t *out) {
     unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count * 8) return;
-    out[t] = nodes[8ULL * idx[t >> 3] + (t & 7)];
+    const uint32_t i = idx[t >> 3];
+    out[t] = i == 0xFFFFFFFFu ? 0u : (i & 0x80000000u) ? top[8ULL * (i & 0x7FFFFFFFu) + (t & 7)] : nodes[8ULL * i + (t & 7)];
 }
 
 }  // namespace
@@ -95,9 +98,9 @@ void merkle_build(uint32_t *nodes, size_t nleaves, int hash_fn, Stream &st) {
     else CSG_LAUNCH(st, merkle_top_kernel<hashes::BLAKE3_256>, 1, 512, 0, nodes, (unsigned)m);
 }
 
-void gather_digests(const uint32_t *nodes, const uint32_t *idx_dev, size_t count, uint32_t *out_dev, Stream &st) {
+void gather_digests(const uint32_t *nodes, const uint32_t *idx_dev, size_t count, uint32_t *out_dev, Stream &st, const uint32_t *top) {
     if (!count) return;
-    CSG_LAUNCH(st, gather_digests_kernel, (unsigned)((count * 8 + 255) / 256), 256, 0, nodes, idx_dev, (unsigned)count, out_dev);
+    CSG_LAUNCH(st, gather_digests_kernel, (unsigned)((count * 8 + 255) / 256), 256, 0, nodes, top, idx_dev, (unsigned)count, out_dev);
 }
 
 }  // namespace csg

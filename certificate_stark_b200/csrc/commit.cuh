@@ -16,7 +16,8 @@ void hash_rows(const fe *data, unsigned width, size_t n, unsigned ncosets, size_
                uint32_t *leaves, Stream &st, unsigned sub = 1, size_t sub_stride = 0);
 // interior nodes of the tree whose leaves are already in nodes[8*L ..)
 void merkle_build(uint32_t *nodes, size_t nleaves, int hash_fn, Stream &st);
-// out[8*t ..] = nodes[8*idx[t] ..]
-void gather_digests(const uint32_t *nodes, const uint32_t *idx_dev, size_t count, uint32_t *out_dev, Stream &st);
+// out[8*t ..] = nodes[8*idx[t] ..]; for the per-GPU subtrees of a sharded proof idx may also name a node of `top`
+// (0x80000000 | i) or a node another rank owns (0xFFFFFFFF: zeros)
+void gather_digests(const uint32_t *nodes, const uint32_t *idx_dev, size_t count, uint32_t *out_dev, Stream &st, const uint32_t *top = nullptr);
 
 }  // namespace csg

@@ -174,7 +174,7 @@ int csg_open_trace(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_
         ctx->need(S_COMMITTED, "the trace must be committed first");
         std::vector<size_t> pos = checked_positions(positions, npos, ctx->lde_n);
         const size_t w = ctx->air.width;
-        copy_opening(ctx->open_rows(ctx->d_lde.p, (unsigned)w, (unsigned)ctx->b, w * ctx->n, ctx->n, pos, true), ctx->open_paths(ctx->d_tnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
+        copy_opening(ctx->open_rows(ctx->d_lde.p, (unsigned)w, (unsigned)ctx->b, w * ctx->n, ctx->n, pos, true), ctx->open_paths(ctx->d_tnodes, ctx->lde_n, pos, ctx->subtrees() ? &ctx->d_ttop : nullptr), rows, paths, cap, paths_len);
     });
 }
 int csg_open_composition(csg_ctx *ctx, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {
@@ -182,7 +182,7 @@ int csg_open_composition(csg_ctx *ctx, const uint64_t *positions, size_t npos, u
         ctx->need(S_COMPOSED, "the composition polynomial must be committed first");
         std::vector<size_t> pos = checked_positions(positions, npos, ctx->lde_n);
         const size_t cw = ctx->ce * ctx->d;
-        copy_opening(ctx->open_rows(ctx->d_clde.p, (unsigned)cw, (unsigned)ctx->b, cw * ctx->n, ctx->n, pos, true), ctx->open_paths(ctx->d_cnodes, ctx->lde_n, pos), rows, paths, cap, paths_len);
+        copy_opening(ctx->open_rows(ctx->d_clde.p, (unsigned)cw, (unsigned)ctx->b, cw * ctx->n, ctx->n, pos, true), ctx->open_paths(ctx->d_cnodes, ctx->lde_n, pos, ctx->subtrees() ? &ctx->d_ctop : nullptr), rows, paths, cap, paths_len);
     });
 }
 int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, size_t npos, uint64_t *rows, uint8_t *paths, size_t cap, size_t *paths_len) {

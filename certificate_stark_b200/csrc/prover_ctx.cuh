@@ -125,6 +125,21 @@ struct csg_ctx {
     DBuf<uint32_t> d_idx, d_dig;
     DBuf<fe> d_parts, d_polys, d_lde, d_comb, d_e, d_eg, d_cpolys, d_clde, d_abc, d_abc_lde, d_deep, d_ptab, d_apoly;
     DBuf<uint32_t> d_tnodes, d_cnodes;
+    // Sharded proof: each context holds the Merkle SUBTREE over its contiguous range of lde_n / G leaves (in d_tnodes / d_cnodes,
+    // same heap layout, root at node 1) and a replicated copy of the top log2(G) levels (2G digests: node 1 = the root, nodes
+    // G .. 2G-1 = the subtree roots of ranks 0 .. G-1).  Off for a single GPU and for traces shorter than the group.
+    DBuf<uint32_t> d_ttop, d_ctop;
+    bool subtrees() const { return G > 1 && n >= G; }
+    // node `idx` of the whole tree (heap index) as this context can read it: see gather_digests
+    uint32_t tree_ref(size_t idx) const {
+        if (!subtrees()) return (uint32_t)idx;
+        if (idx < 2 * G) return rank == 0 ? (0x80000000u | (uint32_t)idx) : 0xFFFFFFFFu;   // replicated: one contribution to the sum
+        unsigned l = 0;
+        while (((size_t)2 << l) <= idx) l++;
+        const unsigned ls = l - ilog2(G);
+        const size_t p = idx - ((size_t)1 << l);
+        return (p >> ls) == rank ? (uint32_t)(((size_t)1 << ls) + (p & (((size_t)1 << ls) - 1))) : 0xFFFFFFFFu;
+    }
     DBuf<ConsArgs> d_cargs;
     std::unique_ptr<ConsArgs> h_cargs;
     std::vector<std::unique_ptr<FriLayer>> fri;   // pool: buffers survive from proof to proof; nfri layers are live
@@ -275,6 +290,12 @@ struct csg_ctx {
         CSG_CUDA(cudaMemcpyAsync(root, nodes.p + 8, 32, cudaMemcpyDeviceToHost, st.s));
         CSG_CUDA(cudaStreamSynchronize(st.s));
     }
+    void all_to_all(const void *send, void *recv, size_t bytes) {
+        comm_events();
+        CSG_CUDA(cudaEventRecord(comm_ev[comm_used].first, st.s));
+        comm->all_to_all(send, recv, bytes, st);
+        CSG_CUDA(cudaEventRecord(comm_ev[comm_used++].second, st.s));
+    }
 
     // ------------------------------------------------------------------------------------------ stage 1 + 2
     // Stage 1 runs column chunk by column chunk: representation change, interpolation and the `blowup` coset transforms of
@@ -374,8 +395,8 @@ struct csg_ctx {
             if (c_hi > c_lo) { CSG_CUDA(cudaEventSynchronize(h2d_b)); CSG_CUDA(cudaEventElapsedTime(&tm.h2d, h2d_a, h2d_b)); }
         }
         t.start(st);
-        commit_rows(d_lde.p, (unsigned)w, w * n, d_tnodes);
-        download_root(d_tnodes, root);
+        commit_rows(d_lde.p, (unsigned)w, w * n, d_tnodes, d_ttop);
+        download_root(subtrees() ? d_ttop : d_tnodes, root);
         tm.commit_trace = t.stop(st); tm.stage_launches[1] = t.launches;
         stage = S_COMMITTED;
     }
@@ -433,17 +454,38 @@ struct csg_ctx {
     // Row digests of a coset-major matrix into the leaves of `nodes`, then the tree.  Sharded: each context hashes the rows
     // of its cosets, the digests are all-gathered and put in natural order, and every context builds the whole tree --
     // 2^23 leaves take 0.35 ms, less than the second exchange that per-GPU subtrees would need to answer the queries.
-    void commit_rows(const fe *data, unsigned width, size_t coset_stride, DBuf<uint32_t> &nodes) {
+    void commit_rows(const fe *data, unsigned width, size_t coset_stride, DBuf<uint32_t> &nodes, DBuf<uint32_t> &top) {
         const int hf = (int)opt.hash_fn;
-        nodes.reserve(16 * lde_n);
-        if (G == 1) hash_rows(data, width, n, (unsigned)b, coset_stride, n, hf, nodes.p + 8 * lde_n, st);
-        else {
+        if (G == 1) {
+            nodes.reserve(16 * lde_n);
+            hash_rows(data, width, n, (unsigned)b, coset_stride, n, hf, nodes.p + 8 * lde_n, st);
+            merkle_build(nodes.p, lde_n, hf, st);
+            return;
+        }
+        if (!subtrees()) {   // a trace shorter than the group: digests all-gathered, the whole (tiny) tree on every context
+            nodes.reserve(16 * lde_n);
             d_gather.reserve(4 * lde_n);
             hash_rows(data, width, n, (unsigned)bl, coset_stride, n, hf, (uint32_t *)d_gather.p + 8 * rank * bl * n, st);
             gather(d_gather.p, bl * n * 32);
             interleave_slices(d_gather.p, (uint64_t *)(nodes.p + 8 * lde_n), n, (unsigned)bl, (unsigned)G, 4, st);
+            merkle_build(nodes.p, lde_n, hf, st);
+            return;
         }
-        merkle_build(nodes.p, lde_n, hf, st);
+        // Merkle subtrees per GPU: this context hashed the rows of its cosets, i.e. the leaves j = k + b i of ALL
+        // i; the leaves of i in [q n/G, (q+1) n/G) form the contiguous range of rank q, and as hashed ([i][k]) they are one
+        // contiguous chunk of the send buffer.  One all-to-all (1/G of the bytes of the all-gather it replaces), the subtree of
+        // the own range, an all-gather of the G roots, and the top log2(G) levels on every context.
+        const size_t nl = lde_n / G, chunk = (n / G) * bl * 32;
+        nodes.reserve(16 * nl); top.reserve(16 * G);
+        d_gather.reserve(8 * bl * n);                                      // send and receive buffer: n * bl digests of 4 words each
+        uint64_t *send = d_gather.p, *recv = d_gather.p + 4 * bl * n;
+        hash_rows(data, width, n, (unsigned)bl, coset_stride, n, hf, (uint32_t *)send, st);
+        all_to_all(send, recv, chunk);
+        interleave_slices(recv, (uint64_t *)(nodes.p + 8 * nl), n / G, (unsigned)bl, (unsigned)G, 4, st);
+        merkle_build(nodes.p, nl, hf, st);
+        CSG_CUDA(cudaMemcpyAsync(top.p + 8 * (G + rank), nodes.p + 8, 32, cudaMemcpyDeviceToDevice, st.s));
+        gather(top.p + 8 * G, 32);
+        merkle_build(top.p, G, hf, st);
     }
 
     // ------------------------------------------------------------------------------------------ stage 3
@@ -591,8 +633,8 @@ struct csg_ctx {
         const size_t cw = ce * d;
         d_clde.reserve(cw * n * bl);
         coset_ntt_columns(roots, ntt, d_cpolys.p, n, d_clde.p, n, cw * n, cw, logn, lde_shift.data(), bl, st);
-        commit_rows(d_clde.p, (unsigned)cw, cw * n, d_cnodes);
-        download_root(d_cnodes, root);
+        commit_rows(d_clde.p, (unsigned)cw, cw * n, d_cnodes, d_ctop);
+        download_root(subtrees() ? d_ctop : d_cnodes, root);
         tm.composition = t.stop(st); tm.stage_launches[3] = t.launches;
         stage = S_COMPOSED;
     }
@@ -825,16 +867,19 @@ struct csg_ctx {
         return rows;
     }
     // BatchMerkleProof::serialize_nodes() of the opening of `pos` in the tree `nodes` over nleaves leaves
-    std::vector<uint8_t> open_paths(const DBuf<uint32_t> &nodes, size_t nleaves, const std::vector<size_t> &pos) {
+    // top != nullptr: `nodes` is this context's subtree of a sharded tree (commit_rows); the path nodes are summed across the ranks
+    std::vector<uint8_t> open_paths(const DBuf<uint32_t> &nodes, size_t nleaves, const std::vector<size_t> &pos, const DBuf<uint32_t> *top = nullptr) {
         std::vector<std::vector<uint32_t>> slots = batch_opening_nodes(nleaves, pos);
         std::vector<uint32_t> flat;
         for (auto &s : slots) flat.insert(flat.end(), s.begin(), s.end());
+        if (top) for (auto &v : flat) v = tree_ref(v);
         std::vector<uint8_t> dig(flat.size() * 32);
         if (!flat.empty()) {
             d_idx.reserve(std::max<size_t>(flat.size(), 4096));
             d_dig.reserve(std::max<size_t>(flat.size() * 8, 8 * 4096));
             CSG_CUDA(cudaMemcpyAsync(d_idx.p, flat.data(), flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st.s));
-            gather_digests(nodes.p, d_idx.p, flat.size(), d_dig.p, st);
+            gather_digests(nodes.p, d_idx.p, flat.size(), d_dig.p, st, top ? top->p : nullptr);
+            if (top) reduce_rows((uint64_t *)d_dig.p, flat.size() * 4);
             CSG_CUDA(cudaMemcpyAsync(dig.data(), d_dig.p, dig.size(), cudaMemcpyDeviceToHost, st.s));
             CSG_CUDA(cudaStreamSynchronize(st.s));
         }
@@ -937,8 +982,8 @@ struct csg_ctx {
         // planned on the host first and fetched in ONE round trip (one index upload, a handful of gather launches, one download)
         OpenBatch B;
         const size_t cw = ce * d;
-        const Opening o_trace = plan_opening(B, d_lde.p, (unsigned)w, (unsigned)b, w * n, n, 1, 0, true, d_tnodes.p, lde_n, pos);
-        const Opening o_comp = plan_opening(B, d_clde.p, (unsigned)cw, (unsigned)b, cw * n, n, 1, 0, true, d_cnodes.p, lde_n, pos);
+        const Opening o_trace = plan_opening(B, d_lde.p, (unsigned)w, (unsigned)b, w * n, n, 1, 0, true, d_tnodes.p, lde_n, pos, subtrees() ? d_ttop.p : nullptr);
+        const Opening o_comp = plan_opening(B, d_clde.p, (unsigned)cw, (unsigned)b, cw * n, n, 1, 0, true, d_cnodes.p, lde_n, pos, subtrees() ? d_ctop.p : nullptr);
         std::vector<Opening> o_fri;
         {
             std::vector<size_t> fp = pos;
@@ -994,16 +1039,16 @@ struct csg_ctx {
     struct Opening { size_t rows_off = 0, rows_len = 0, dig_off = 0; std::vector<std::vector<uint32_t>> slots; };
     struct OpenBatch {
         struct Rows { const fe *data; unsigned width, ncosets; size_t coset_stride, col_stride; unsigned sub; size_t sub_stride, idx_off, npos, rows_off; };
-        struct Digs { const uint32_t *nodes; size_t idx_off, count, dig_off; };
+        struct Digs { const uint32_t *nodes, *top; size_t idx_off, count, dig_off; };
         std::vector<uint32_t> idx;   // row positions and node indices of every job, concatenated
         std::vector<Rows> rows;
         std::vector<Digs> digs;
-        size_t rows_words = 0, dig_count = 0, sharded_words = 0;
+        size_t rows_words = 0, dig_count = 0, sharded_words = 0, sharded_digs = 0;   // sharded_*: leading parts summed across the ranks
     };
     // rows of `data` at `pos` (sharded matrices first: their rows are summed across the ranks in one go) and the batch opening
     // of the same positions in the tree `nodes`
     Opening plan_opening(OpenBatch &B, const fe *data, unsigned width, unsigned ncosets, size_t coset_stride, size_t col_stride, unsigned sub, size_t sub_stride,
-                         bool sharded, const uint32_t *nodes, size_t nleaves, const std::vector<size_t> &pos) {
+                         bool sharded, const uint32_t *nodes, size_t nleaves, const std::vector<size_t> &pos, const uint32_t *top = nullptr) {
         Opening o;
         sharded = sharded && G > 1;
         OpenBatch::Rows r{data, width, sharded ? (unsigned)bl : ncosets, coset_stride, col_stride, sub ? sub : 1, sub_stride, B.idx.size(), pos.size(), B.rows_words};
@@ -1017,10 +1062,11 @@ struct csg_ctx {
         if (sharded) { if (B.sharded_words != o.rows_off) throw StateError("sharded openings must be planned first"); B.sharded_words = B.rows_words; }
         B.rows.push_back(r);
         o.slots = batch_opening_nodes(nleaves, pos);
-        OpenBatch::Digs dj{nodes, B.idx.size(), 0, B.dig_count};
-        for (auto &sl : o.slots) { B.idx.insert(B.idx.end(), sl.begin(), sl.end()); dj.count += sl.size(); }
+        OpenBatch::Digs dj{nodes, top, B.idx.size(), 0, B.dig_count};
+        for (auto &sl : o.slots) { for (uint32_t v : sl) B.idx.push_back(top ? tree_ref(v) : v); dj.count += sl.size(); }
         o.dig_off = B.dig_count;
         B.dig_count += dj.count;
+        if (top) { if (B.sharded_digs != o.dig_off) throw StateError("openings of sharded trees must be planned first"); B.sharded_digs = B.dig_count; }
         B.digs.push_back(dj);
         return o;
     }
@@ -1032,7 +1078,8 @@ struct csg_ctx {
         for (auto &r : B.rows)
             gather_rows(r.data, r.width, r.ncosets, r.coset_stride, r.col_stride, d_idx.p + r.idx_off, r.npos, d_rows.p + r.rows_off, st, r.sub, r.sub_stride);
         if (B.sharded_words) reduce_rows(d_rows.p, B.sharded_words);
-        for (auto &g : B.digs) gather_digests(g.nodes, d_idx.p + g.idx_off, g.count, d_dig.p + 8 * g.dig_off, st);
+        for (auto &g : B.digs) gather_digests(g.nodes, d_idx.p + g.idx_off, g.count, d_dig.p + 8 * g.dig_off, st, g.top);
+        if (B.sharded_digs) reduce_rows((uint64_t *)d_dig.p, B.sharded_digs * 4);
         if (d == 1) from_montgomery(last.evals, d_rows.p + rem_off, last.m, st);
         else planes_to_canonical(last.evals, last.m, last.m, d, d_rows.p + rem_off, st);
         rows.resize(B.rows_words); digs.resize(B.dig_count * 32);
