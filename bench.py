@@ -439,7 +439,9 @@ def main():
                              "host_memory": "pageable (numpy array): staged through the library's pinned ring by the host threads"},
             "build_trace_and_prove": {"value": (world * num_tx / (wit_ms / steps / 1e3)) if wit_ms else None, "unit": UNIT, "ms_per_step": wit_ms / steps,
                                       "note": "TransactionExample::prove() as a whole: witness generated on the device (csg_build_trace_transaction_device), "
-                                              "2.2 KB per transaction H2D, then the proof; the host builder needs ~0.4 s for the same batch"},
+                                              "2.2 KB per transaction H2D, then the proof; the host builder needs ~0.4 s for the same batch.  With "
+                                              "csg_tx_batch_build_device the batch metadata (account tree, paths, signatures) is built by kernels too: +23 ms "
+                                              "instead of 1.3 s on the host (tools/batch_time.py, profiles/r2_batch_time.json)"},
             "gpu_launches": launches,
             "clocks": clock_summary,
             "roofline": roof,
@@ -451,7 +453,8 @@ def main():
         if sh_ms:
             line["sharded_proof"] = {
                 "note": f"ONE proof of the same {num_tx}-transaction batch split over the {world} GPUs by LDE coset (each GPU owns {BLOWUP // world} of the "
-                        f"{BLOWUP} cosets; NCCL all-gathers of coefficients, leaf digests, composition slices and DEEP evaluations); proof bytes "
+                        f"{BLOWUP} cosets and the Merkle subtree of 1/{world} of the leaves; NCCL all-gathers of coefficients, composition slices, out-of-domain values, "
+                        "DEEP evaluations and subtree roots, one all-to-all of leaf digests per commitment, sums of opened rows and path nodes); proof bytes "
                         "identical to the single-GPU proof on every rank; times are device events, max over ranks",
                 "ms_per_proof": sh_ms / steps, "tx_per_s": num_tx / (sh_ms / steps / 1e3), "speedup_vs_one_gpu": ms_per_step / (sh_ms / steps),
                 "comm_ms_per_proof": sh_comm_ms / steps, "stage_ms_rank0": {k: v / steps for k, v in sh_stage.items()},

@@ -132,9 +132,11 @@ int csg_open_fri_layer(csg_ctx *ctx, size_t layer, const uint64_t *positions, si
 /* ---- one proof sharded over several GPUs by LDE coset (the reference has no multi-device path) -----------
  * `world` contexts, one per GPU (world a power of two dividing the blowup factor), each owning blowup/world cosets of the
  * LDE domain: column blocks are interpolated per context and the coefficients all-gathered; extension, row hashing,
- * constraint evaluation, composition LDE and DEEP quotients run on the owned cosets only; leaf digests, per-coset
- * composition interpolants and DEEP evaluations are all-gathered; trees and FRI are then built by every context, so every
- * context follows the same transcript and returns the same proof bytes (identical to the single-GPU proof).
+ * constraint evaluation, composition LDE and DEEP quotients run on the owned cosets only; leaf digests travel by all-to-all into
+ * contiguous leaf ranges so that every context builds the Merkle subtree of its range (the G roots are all-gathered, the top
+ * levels replicated; path nodes are collected from the owning contexts at opening time); per-coset composition interpolants, OOD
+ * values and DEEP evaluations are all-gathered; FRI is built by every context, so every context follows the same transcript and
+ * returns the same proof bytes (identical to the single-GPU proof).
  * After attaching, EVERY context of the group makes the same sequence of calls (csg_set_air .. csg_prove_loaded, or
  * csg_prove) with the same arguments; calls block until the peers arrive.
  *   csg_dist_init        one process per GPU (torchrun): NCCL; rank 0 creates the id with csg_dist_unique_id and the host
