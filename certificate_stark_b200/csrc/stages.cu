@@ -80,27 +80,38 @@ __global__ void sum_slices_kernel(const fe *__restrict__ in, fe *__restrict__ ou
 
 constexpr unsigned EVAL_THREADS = 256, EVAL_CHUNK = 32;
 struct EvalPoints { fe z[4], z_stride[4]; };   // z_stride = z^EVAL_THREADS
+// One pass over a column for ALL points: thread t of a CTA owns the coefficients base + t + j*THREADS and forms
+// sum_j c_j (z^THREADS)^j per point as independent lazily reduced multiply-accumulates against a shared table of powers (the Horner
+// form it replaces was one dependent multiply-add chain per thread and point, and read the column once per point).
+template <int NPTS>
 __global__ void __launch_bounds__(EVAL_THREADS) eval_polys_kernel(const fe *__restrict__ polys, unsigned long long stride, unsigned long long n,
                                                                  EvalPoints pts, fe *__restrict__ partial) {
     __shared__ fe red[EVAL_THREADS];
-    const unsigned t = threadIdx.x, c = blockIdx.y, p = blockIdx.z;
+    __shared__ fe zpow[NPTS][EVAL_CHUNK];
+    const unsigned t = threadIdx.x, c = blockIdx.y;
     const unsigned long long base = blockIdx.x * (unsigned long long)(EVAL_THREADS * EVAL_CHUNK);
     const fe *poly = polys + c * stride;
-    const fe zs = pts.z_stride[p];
-    fe v = 0;
-    // coefficients base + t + j*THREADS, Horner in z^THREADS from the top
-    for (int j = EVAL_CHUNK - 1; j >= 0; j--) {
-        unsigned long long m = base + t + (unsigned long long)j * EVAL_THREADS;
-        fe cm = m < n ? poly[m] : 0;
-        v = add(mul(v, zs), cm);
-    }
-    red[t] = mul(v, f63::pow(pts.z[p], base + t));
+    if (t < NPTS * EVAL_CHUNK) zpow[t / EVAL_CHUNK][t % EVAL_CHUNK] = f63::pow(pts.z_stride[t / EVAL_CHUNK], t % EVAL_CHUNK);
     __syncthreads();
-    for (unsigned s = EVAL_THREADS / 2; s > 0; s >>= 1) {
-        if (t < s) red[t] = add(red[t], red[t + s]);
+    acc192 v[NPTS];
+#pragma unroll 8
+    for (int j = 0; j < (int)EVAL_CHUNK; j++) {
+        const unsigned long long m = base + t + (unsigned long long)j * EVAL_THREADS;
+        const fe cm = m < n ? poly[m] : 0;
+#pragma unroll
+        for (int p = 0; p < NPTS; p++) v[p].mac(cm, zpow[p][j]);
+    }
+#pragma unroll
+    for (int p = 0; p < NPTS; p++) {
+        red[t] = mul(v[p].reduce(), f63::pow(pts.z[p], base + t));
+        __syncthreads();
+        for (unsigned s = EVAL_THREADS / 2; s > 0; s >>= 1) {
+            if (t < s) red[t] = add(red[t], red[t + s]);
+            __syncthreads();
+        }
+        if (t == 0) partial[((unsigned long long)p * gridDim.y + c) * gridDim.x + blockIdx.x] = red[0];
         __syncthreads();
     }
-    if (t == 0) partial[((unsigned long long)p * gridDim.y + c) * gridDim.x + blockIdx.x] = red[0];
 }
 
 template <int NCOMB>
@@ -294,8 +305,13 @@ void eval_polys_at(const fe *polys, size_t stride, size_t ncols, size_t n, const
     scratch.reserve(total);
     EvalPoints pts{};
     for (size_t p = 0; p < npoints; p++) { pts.z[p] = points_host[p]; pts.z_stride[p] = f63::pow(points_host[p], EVAL_THREADS); }
-    dim3 grid(nblk, (unsigned)ncols, (unsigned)npoints);
-    CSG_LAUNCH(st, eval_polys_kernel, grid, EVAL_THREADS, 0, polys, (unsigned long long)stride, (unsigned long long)n, pts, scratch.p);
+    dim3 grid(nblk, (unsigned)ncols);
+    switch (npoints) {
+    case 1: CSG_LAUNCH(st, eval_polys_kernel<1>, grid, EVAL_THREADS, 0, polys, (unsigned long long)stride, (unsigned long long)n, pts, scratch.p); break;
+    case 2: CSG_LAUNCH(st, eval_polys_kernel<2>, grid, EVAL_THREADS, 0, polys, (unsigned long long)stride, (unsigned long long)n, pts, scratch.p); break;
+    case 3: CSG_LAUNCH(st, eval_polys_kernel<3>, grid, EVAL_THREADS, 0, polys, (unsigned long long)stride, (unsigned long long)n, pts, scratch.p); break;
+    default: CSG_LAUNCH(st, eval_polys_kernel<4>, grid, EVAL_THREADS, 0, polys, (unsigned long long)stride, (unsigned long long)n, pts, scratch.p); break;
+    }
     std::vector<fe> part(total);
     CSG_CUDA(cudaMemcpyAsync(part.data(), scratch.p, total * sizeof(fe), cudaMemcpyDeviceToHost, st.s));
     CSG_CUDA(cudaStreamSynchronize(st.s));
