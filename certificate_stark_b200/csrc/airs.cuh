@@ -155,6 +155,16 @@ struct CombT {
         t.mac(b, v);
         q[0] = t.lo; q[part_stride] = t.mid; q[2 * part_stride] = t.hi;
     }
+    // Split mode on the device: a CTA barrier.  The linear-rest code is 130 KB of straight-line instructions that every warp
+    // walks once per row tile, and instruction fetch was its top stall (ncu: no_instruction); a barrier every few hundred
+    // instructions keeps the four warps of a CTA inside the same stretch, so one instruction-cache fill serves all of them:
+    // cons_rest 6.97 -> 6.53 ms at 2^20 rows (gpurun_out/ab_rsync*.txt; one more barrier per loop iteration measured slower).
+    // Every thread of the CTA reaches it: the split kernels have no divergent exit after their bounds check.
+    CSG_HD void sync() const {
+#if defined(__CUDA_ARCH__) && !defined(CSG_NO_REST_SYNC)
+        if (SPLIT) __syncthreads();
+#endif
+    }
     CSG_HD fe part_value(int g, int j = 0) const {   // split mode: B_g of component j, reduced
         const uint64_t *q = part + (size_t)(j * MAX_SPLIT_GROUPS + g) * 3 * part_stride;
         f63::acc192w t;
@@ -273,11 +283,13 @@ CSG_HD void merkle_auth_path(const Frame &f, CB &C, int base, fe tx_hash, fe has
             keep.add(C, o + i, f63::sub(c, f.next(o + i)));                 // copy_flag and init_flag*(1-bit) share this difference
             to_rate.add(C, o + HRW + i, f63::sub(c, f.next(o + HRW + i)));  // init_flag*bit: the hash moves to the rate half
         }
+        C.sync();
     }
     CSG_REST_LOOP
     for (int i = 0; i < HRW; i++) place_bit.add(C, base + i, f63::sub(f.next(base + HSW + 1 + i), f.next(base + i)));
     CSG_REST_LOOP
     for (int i = HRW; i < HSW; i++) place_nbit.add(C, base + i, f63::sub(f.next(base + HSW + 1 + i), f.next(base + i)));
+    C.sync();
     keep.flush(C);
     to_rate.flush(C);
     place_bit.flush(C);
@@ -423,6 +435,7 @@ CSG_HD void schnorr_light(const Frame &f, CB &C, fe doubling, fe addition, const
         hold.add(C, LIMBS + 1 + i, f63::sub(f.cur(LIMBS + 1 + i), f.next(LIMBS + 1 + i)));
     }
     hold.flush(C);
+    C.sync();
     // enforce_hash_copy (src/schnorr/air.rs:309-330)
     FlagAcc a(copy_hash);
     CSG_REST_LOOP
@@ -624,6 +637,7 @@ CSG_HD void rest_transaction(const Frame &f, const PV &pv, CB &C) {
     {   // setup row of a transaction: leaf consistency and copies into the carried registers (src/air.rs:405-504)
         FlagAcc a(setup);
         value_block(f, C, a);
+        C.sync();
         CSG_REST_LOOP
         for (int o = 0; o < APW; o++) {
             a.add(C, SENDER_KEY_RES + o, f63::sub(f.next(SENDER_KEY + o), f.cur(SENDER_INITIAL + o)));
@@ -634,6 +648,7 @@ CSG_HD void rest_transaction(const Frame &f, const PV &pv, CB &C) {
         a.add(C, NONCE_COPY_RES, f63::sub(f.next(NONCE_COPY), f.cur(SENDER_INITIAL + APW + 1)));
         a.flush(C);
     }
+    C.sync();
     {   // carried registers stay put afterwards (src/air.rs:506-529); note the overlapping slot ranges are the reference's
         FlagAcc a(pv(TX_VALUE_COPY));
         CSG_REST_LOOP
@@ -646,11 +661,13 @@ CSG_HD void rest_transaction(const Frame &f, const PV &pv, CB &C) {
         a.add(C, NONCE_COPY_RES, f63::sub(f.next(NONCE_COPY), f.cur(NONCE_COPY)));
         a.flush(C);
     }
+    C.sync();
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int path = 0; path < 2; path++) merkle_auth_path(f, C, path == 0 ? SENDER_INITIAL : RECEIVER_INITIAL, tx_hash, hash_input, hashf);
+    for (int path = 0; path < 2; path++) { merkle_auth_path(f, C, path == 0 ? SENDER_INITIAL : RECEIVER_INITIAL, tx_hash, hash_input, hashf); C.sync(); }
     merkle_roots(f, C, finish);
+    C.sync();
 
     // message elements entering the Schnorr hash come from the carried key/delta/nonce registers (src/air.rs:542-565)
     const fe k0 = pv(TX_INTERNAL), k1 = pv(TX_INTERNAL + 1), k2 = pv(TX_INTERNAL + 2), k3 = pv(TX_INTERNAL + 3);
@@ -667,6 +684,7 @@ CSG_HD void rest_transaction(const Frame &f, const PV &pv, CB &C) {
     };
     const fe digest[4] = {pv(TX_DIGEST), pv(TX_DIGEST + 1), pv(TX_DIGEST + 2), pv(TX_DIGEST + 3)};
     schnorr_light(f, C, doubling, addition, digest, copy_hash, in);
+    C.sync();
 
     {   // range proofs of delta and sigma (src/air.rs:582-609); the sigma finish check compares the delta registers, as the reference does
         FlagAcc a(pv(TX_RANGE_STEP));
