@@ -198,7 +198,11 @@ int csg_dist_info(const csg_ctx *ctx, int *rank, int *world) {
     *rank = ctx->comm ? ctx->comm->rank : 0; *world = ctx->comm ? ctx->comm->world : 1;
     return CSG_OK;
 }
-int csg_get_timings(const csg_ctx *ctx, csg_timings *out) { if (!ctx || !out) return CSG_ERR_ARG; *out = ctx->tm; return CSG_OK; }
+int csg_get_timings(const csg_ctx *ctx, csg_timings *out) {
+    if (!ctx || !out) return CSG_ERR_ARG;
+    // stage times are event pairs read on demand (no host synchronisation per stage): collect the outstanding ones first
+    return guarded(const_cast<csg_ctx *>(ctx), [&] { const_cast<csg_ctx *>(ctx)->flush_timers(); *out = ctx->tm; });
+}
 
 
 }  // extern "C"

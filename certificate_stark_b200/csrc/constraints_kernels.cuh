@@ -377,10 +377,15 @@ void launch_split(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, co
             for (unsigned t = 0; t < Lg; t++) { acc = add(acc, cur); cur = mul(cur, step); }
             mix[jl * Lg + je] = mul(acc, linv);
         }
+    std::vector<fe> even_inv(L);
+    for (unsigned j = 0; j < L; j++) even_inv[j] = inv(h.shift[2 * j]);
     auto extend = [&](const fe *even, fe *coef, fe *mixed, fe *odd, unsigned np) {
+        // (the shift vectors are pageable host memory: their copies are staged before cudaMemcpyAsync returns, so nothing
+        // here waits for the stream -- two synchronisations per proof less, 0.2 ms of a one-transaction proof with the
+        // inversions that used to be repeated per polynomial)
         std::vector<fe> sinv(np * L), sodd(np * L);
         for (unsigned p = 0; p < np; p++)
-            for (unsigned j = 0; j < L; j++) { sinv[p * L + j] = inv(h.shift[2 * j]); sodd[p * L + j] = h.shift[2 * j + 1]; }
+            for (unsigned j = 0; j < L; j++) { sinv[p * L + j] = even_inv[j]; sodd[p * L + j] = h.shift[2 * j + 1]; }
         if (xch) {   // own even cosets into this rank's slice, all-gather, then only the rows of the mix this rank needs
             const size_t slice = (size_t)np * L * n;
             if (slice * G > xch->buf_elems) throw std::runtime_error("exchange buffer of the sharded split is too small");
@@ -392,7 +397,6 @@ void launch_split(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, co
             coset_mix(coef, mixed, n, L, np, mix.data(), st);
         }
         coset_ntt_entries(rt, sc, mixed, odd, (size_t)np * L, h.logn, sodd.data(), st);
-        CSG_CUDA(cudaStreamSynchronize(st.s));   // the staging vectors are read by async copies
     };
     // the banks' formula outputs in split mode: which degree groups the point slots of each bank fall into
     static const bool ecc_split = getenv("CSG_NO_ECC_SPLIT") == nullptr;
@@ -417,13 +421,16 @@ void launch_split(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, co
         CSG_CUDA(cudaFuncSetAttribute((cons_ecc_low_kernel<AIR, DEG>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     auto mark = [&](int k) { if (ev) CSG_CUDA(cudaEventRecord(ev[k], st.s)); };
+    host_mark("  cons: split setup");
     mark(0);
     CSG_LAUNCH(st, (cons_low_kernel<AIR, 0, DEG>), dim3(gx, L, NR), CONS_THREADS, smem, args_dev, lde, W, ptab, low_parts, 0u);
     mark(1);
     if (ecc_split) {
         CSG_LAUNCH(st, (cons_ecc_low_kernel<AIR, DEG>), dim3((gx + ECC_SUPER - 1) / ECC_SUPER * 4 * ECC_SUPER, L, 1), CONS_THREADS, smem, args_dev, lde, ptab, M, eccl_even);
         mark(5);   // ev[1] .. ev[5]: the curve-formula kernel alone, the largest single launch of a proof
+        host_mark("  cons: low + curve-low launched");
         extend(eccl_even, eccl_coef, eccl_mix, eccl_odd, DEG * M.total);
+        host_mark("  cons: curve polynomials extended");
         CSG_LAUNCH(st, (cons_ecc_merge_kernel<AIR, DEG>), dim3(gx, ce, 2), CONS_THREADS, 0, args_dev, lde, W, ptab, M, (const fe *)eccl_even, (const fe *)eccl_odd, hi,
                    (unsigned)NE);
     } else {
@@ -435,7 +442,9 @@ void launch_split(const ConsArgs *args_dev, const ConsArgs &h, const fe *lde, co
     mark(3);
     CSG_LAUNCH(st, (cons_low_kernel<AIR, 3, DEG>), dim3(gx, L, 1), CONS_THREADS, smem, args_dev, lde, W, ptab, low_parts, (unsigned)NR);
     sum_slices(low_parts, low_sum, slab, NR + 1, st);
+    host_mark("  cons: merge, final item, rest launched");
     extend(low_sum, low_coef, low_mix, low_odd, NPD);   // interpolate on the even cosets, evaluate on the odd ones
+    host_mark("  cons: low polynomials extended");
     if (h.nbgroups > 0)
         CSG_LAUNCH(st, boundary_inverse_kernel, dim3((unsigned)((n + INV_CHUNK * INV_THREADS - 1) / (INV_CHUNK * INV_THREADS)), ce, h.nbgroups),
                    INV_THREADS, 0, args_dev, W, binv);

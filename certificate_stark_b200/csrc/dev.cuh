@@ -1,6 +1,9 @@
 // Device plumbing shared by the .cu files of libcsg: error handling, a launch-counting stream wrapper and a
 // trivially simple device buffer.  No torch types anywhere: the library is plain CUDA runtime behind a C ABI.
 #pragma once
+#include <chrono>
+#include <utility>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -22,6 +25,16 @@ inline void cuda_check(cudaError_t e, const char *what, const char *file, int li
     }
 }
 #define CSG_CUDA(x) ::csg::cuda_check((x), #x, __FILE__, __LINE__)
+
+// CSG_HOST_TRACE: host clock marks of the proof in flight on this thread (prover_ctx.cuh prints them); a no-op otherwise
+struct HostTrace {
+    std::chrono::steady_clock::time_point t0;
+    std::vector<std::pair<const char *, double>> marks;
+};
+inline thread_local HostTrace *g_host_trace = nullptr;
+inline void host_mark(const char *what) {
+    if (g_host_trace) g_host_trace->marks.emplace_back(what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - g_host_trace->t0).count());
+}
 
 // the proving stream; every kernel launch of the library goes through LAUNCH so that launches are counted
 struct Stream {

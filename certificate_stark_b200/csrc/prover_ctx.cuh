@@ -50,16 +50,49 @@ enum Stage { S_NONE, S_AIR, S_TRACE, S_COMMITTED, S_EVALUATED, S_COMPOSED, S_OOD
 
 class Timer {   // device time of a stage, CUDA events on the proving stream; the events live as long as the context
   public:
-    ~Timer() { if (a_) { cudaEventDestroy(a_); cudaEventDestroy(b_); } }
+    ~Timer() { for (auto &p : own_) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
     void start(Stream &st) {
-        if (!a_) { CSG_CUDA(cudaEventCreate(&a_)); CSG_CUDA(cudaEventCreate(&b_)); }
+        if (crowded()) flush();   // a level-2 caller that never reads the timings
+        if (used_ == own_.size()) { cudaEvent_t a, b; CSG_CUDA(cudaEventCreate(&a)); CSG_CUDA(cudaEventCreate(&b)); own_.emplace_back(a, b); }
         l0_ = st.launches;
-        CSG_CUDA(cudaEventRecord(a_, st.s));
+        CSG_CUDA(cudaEventRecord(own_[used_].first, st.s));
     }
     unsigned launches = 0;   // kernels launched between the last start() and stop()
-    float stop(Stream &st) { launches = (unsigned)(st.launches - l0_); CSG_CUDA(cudaEventRecord(b_, st.s)); CSG_CUDA(cudaEventSynchronize(b_)); float ms = 0; CSG_CUDA(cudaEventElapsedTime(&ms, a_, b_)); return ms; }
+    // blocking form: waits for the stage and returns its time (the callers that need the stage complete anyway)
+    float stop(Stream &st) {
+        launches = (unsigned)(st.launches - l0_);
+        cudaEvent_t a = own_[used_].first, b = own_[used_].second;
+        CSG_CUDA(cudaEventRecord(b, st.s)); CSG_CUDA(cudaEventSynchronize(b));
+        float ms = 0; CSG_CUDA(cudaEventElapsedTime(&ms, a, b)); return ms;
+    }
+    // deferred form: the stage's time is written (add: added) to *dst by the next flush().  No host synchronisation per stage --
+    // a proof of a small trace is a few dozen short kernels, and waiting out each stage only to read a clock cost 0.12-0.15 ms
+    // of a 0.6-1.4 ms proof (tools/small_latency.py).
+    void stop(Stream &st, float *dst, bool add = false) {
+        launches = (unsigned)(st.launches - l0_);
+        CSG_CUDA(cudaEventRecord(own_[used_].second, st.s));
+        pending_.push_back({own_[used_].first, own_[used_].second, dst, add});
+        used_++;
+    }
+    // the same for a pair of events recorded elsewhere (they must not be re-recorded before the flush)
+    void span(cudaEvent_t a, cudaEvent_t b, float *dst, bool add = false) { pending_.push_back({a, b, dst, add}); }
+    void zero(float *dst) { pending_.push_back({nullptr, nullptr, dst, false}); }   // *dst = 0, in order with the spans
+    bool crowded() const { return pending_.size() >= 256; }
+    void discard() { pending_.clear(); used_ = 0; }   // nobody asked for the times of the previous proof
+    void flush() {
+        for (const Pending &q : pending_) {
+            float ms = 0;
+            if (q.a) { CSG_CUDA(cudaEventSynchronize(q.b)); CSG_CUDA(cudaEventElapsedTime(&ms, q.a, q.b)); }
+            *q.dst = q.add ? *q.dst + ms : ms;
+        }
+        pending_.clear();
+        used_ = 0;
+    }
   private:
-    cudaEvent_t a_ = nullptr, b_ = nullptr;
+    struct Pending { cudaEvent_t a, b; float *dst; bool add; };
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> own_;
+    std::vector<Pending> pending_;
+    size_t used_ = 0;
     unsigned long long l0_ = 0;
 };
 
@@ -142,10 +175,14 @@ struct csg_ctx {
     }
     DBuf<ConsArgs> d_cargs;
     std::unique_ptr<ConsArgs> h_cargs;
+    bool cargs_domain_ready = false;   // the per-AIR part of *h_cargs (domain constants, assertion polynomials) has been filled
     std::vector<std::unique_ptr<FriLayer>> fri;   // pool: buffers survive from proof to proof; nfri layers are live
     size_t nfri = 0;
     DBuf<uint64_t> d_rows;
     Timer stage_timer, query_timer;
+    // The stage times of a proof are read from their event pairs only when csg_get_timings asks (some 25 pairs: 70-85 us of
+    // driver calls, a tenth of a small proof); a proof nobody asked about is dropped when the next one starts.
+    void flush_timers() { stage_timer.flush(); query_timer.flush(); }
 
     fe z = 0;
     std::vector<fe> ood_cur, ood_next, ood_comp;
@@ -159,6 +196,10 @@ struct csg_ctx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // csg_timer_start / csg_timer_stop
     cudaEvent_t cons_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool split_low_degree = getenv("CSG_NO_SPLIT") == nullptr;   // CSG_NO_SPLIT=1: evaluate every constraint on every coset (A/B testing)
+    // Below this trace length the split's extra launches cost more than the arithmetic it saves (tools/small_latency.py: one
+    // transaction 1.28 -> 1.18 ms, one signature 1.06 -> 0.95 ms without it; break-even at 2^14 rows).  The proof is the same
+    // either way; CSG_SPLIT_MIN_ROWS=0 forces the split on small traces (tests).
+    size_t split_min_rows = getenv("CSG_SPLIT_MIN_ROWS") ? strtoull(getenv("CSG_SPLIT_MIN_ROWS"), nullptr, 10) : (size_t)1 << 14;
     cudaStream_t copy_stream = nullptr;          // H2D copies of trace column chunks, overlapped with their extension
     std::vector<cudaEvent_t> chunk_ev;
     int trace_repr = CSG_REPR_CANONICAL;         // representation of the words in d_io (csg_load_trace / csg_prove_trace)
@@ -224,6 +265,7 @@ struct csg_ctx {
     // a coset LDE of the length-P column with shifts s_kc^(n/P); columns of equal period go through the NTT together
     void build_periodic_tables() {
         h_cargs.reset(new ConsArgs());
+        cargs_domain_ready = false;
         ConsArgs &A = *h_cargs;
         memset(&A, 0, sizeof A);
         const size_t np = air.periodic.size();
@@ -389,15 +431,16 @@ struct csg_ctx {
             if (c_hi < w) coset_ntt_columns(roots, ntt, scratch.p + c_hi * n, n, d_lde.p + c_hi * n, n, w * n, w - c_hi, logn, lde_tables, st);
         }
         std::swap(d_polys.p, scratch.p); std::swap(d_polys.n, scratch.n);   // d_polys = coefficients
-        tm.lde = t.stop(st); tm.stage_launches[0] = t.launches;
+        t.stop(st, &tm.lde); tm.stage_launches[0] = t.launches;
         if (host) {   // the copy ran under the extension: its own duration (first byte .. last byte), not time added to the proof
-            nfri = 0; tm.h2d = 0;
-            if (c_hi > c_lo) { CSG_CUDA(cudaEventSynchronize(h2d_b)); CSG_CUDA(cudaEventElapsedTime(&tm.h2d, h2d_a, h2d_b)); }
+            nfri = 0;
+            t.zero(&tm.h2d);
+            if (c_hi > c_lo) t.span(h2d_a, h2d_b, &tm.h2d);
         }
         t.start(st);
         commit_rows(d_lde.p, (unsigned)w, w * n, d_tnodes, d_ttop);
         download_root(subtrees() ? d_ttop : d_tnodes, root);
-        tm.commit_trace = t.stop(st); tm.stage_launches[1] = t.launches;
+        t.stop(st, &tm.commit_trace); tm.stage_launches[1] = t.launches;
         stage = S_COMMITTED;
     }
 
@@ -496,53 +539,64 @@ struct csg_ctx {
         Timer &t = stage_timer;
         t.start(st);
         ConsArgs &A = *h_cargs;
-        const fe g = root_of_unity(logn);
-        A.logn = logn; A.ncosets = (unsigned)cel; A.col_stride = n; A.width = air.width;
         A.ext_degree = all_components ? (unsigned)d : 1;
-        A.g_last = f63::pow(g, n - 1);
-        A.nconstraints = (unsigned)air.num_constraints(); A.ngroups = (unsigned)tg.adj.size();
         for (size_t i = 0; i < air.num_constraints(); i++) { A.alpha[i] = t_ab[2 * i]; A.beta[i] = t_ab[2 * i + 1]; A.group[i] = tg.group_of[i]; }
-        for (size_t gi = 0; gi < tg.adj.size(); gi++) A.adj_mod[gi] = tg.adj[gi] % n;
+        A.nconstraints = (unsigned)air.num_constraints(); A.ngroups = (unsigned)tg.adj.size();
         fill_rescue_tables(air.id, A);
-        A.nbgroups = (unsigned)bg.groups.size(); A.nassertions = (unsigned)air.assertions.size();
-        for (size_t gi = 0; gi < bg.groups.size(); gi++) {
-            A.b_adj_mod[gi] = bg.groups[gi].adj % n; A.b_steps[gi] = bg.groups[gi].num_steps; A.b_offset[gi] = bg.groups[gi].offset;
-        }
-        for (size_t kc = 0; kc < cel; kc++) {
-            const fe s = ce_shift[kc];
-            A.lde_coset_stride[kc] = (unsigned long long)((kc0 + kc) * (b / ce) - k0) * air.width * n;
-            A.shift[kc] = s;
-            A.zinv[kc] = inv(sub(f63::pow(s, n), ONE));
-            for (size_t gi = 0; gi < tg.adj.size(); gi++) A.shift_adj[kc][gi] = f63::pow(s, tg.adj[gi]);
+        for (size_t i = 0; i < air.assertions.size(); i++) { A.a_alpha[i] = b_ab[2 * i]; A.a_beta[i] = b_ab[2 * i + 1]; }
+        host_mark("  cons: coefficient tables");
+        if (!cargs_domain_ready) {
+            // everything that depends on the AIR, the domain and the public inputs only: computed for the first proof after
+            // csg_set_air and kept (some 150 host exponentiations and the assertion polynomials -- a fifth of the host time of
+            // a one-transaction proof)
+            const fe g = root_of_unity(logn);
+            A.logn = logn; A.ncosets = (unsigned)cel; A.col_stride = n; A.width = air.width;
+            A.g_last = f63::pow(g, n - 1);
+            for (size_t gi = 0; gi < tg.adj.size(); gi++) A.adj_mod[gi] = tg.adj[gi] % n;
+            A.nbgroups = (unsigned)bg.groups.size(); A.nassertions = (unsigned)air.assertions.size();
             for (size_t gi = 0; gi < bg.groups.size(); gi++) {
-                A.b_shift_adj[kc][gi] = f63::pow(s, bg.groups[gi].adj);
-                A.b_shift_steps[kc][gi] = f63::pow(s, bg.groups[gi].num_steps);
+                A.b_adj_mod[gi] = bg.groups[gi].adj % n; A.b_steps[gi] = bg.groups[gi].num_steps; A.b_offset[gi] = bg.groups[gi].offset;
             }
-        }
-        // assertion values; a sequence becomes its interpolating polynomial, evaluated in-kernel at x * g^-first_step
-        std::vector<fe> polys;
-        const fe g_inv = inv(g);
-        for (size_t i = 0; i < air.assertions.size(); i++) {
-            const Assertion &s = air.assertions[i];
-            A.a_col[i] = s.column; A.a_group[i] = bg.group_of[i];
-            A.a_alpha[i] = b_ab[2 * i]; A.a_beta[i] = b_ab[2 * i + 1];
-            A.a_value[i] = s.values[0]; A.a_poly_len[i] = (unsigned)s.values.size(); A.a_poly_off[i] = polys.size();
-            A.a_xoff[i] = s.first_step ? f63::pow(g_inv, s.first_step) : ONE;
-            if (s.values.size() > 1) {
-                std::vector<fe> c = host_interpolate(s.values);
-                polys.insert(polys.end(), c.begin(), c.end());
+            for (size_t kc = 0; kc < cel; kc++) {
+                const fe s = ce_shift[kc];
+                A.lde_coset_stride[kc] = (unsigned long long)((kc0 + kc) * (b / ce) - k0) * air.width * n;
+                A.shift[kc] = s;
+                A.zinv[kc] = inv(sub(f63::pow(s, n), ONE));
+                for (size_t gi = 0; gi < tg.adj.size(); gi++) A.shift_adj[kc][gi] = f63::pow(s, tg.adj[gi]);
+                for (size_t gi = 0; gi < bg.groups.size(); gi++) {
+                    A.b_shift_adj[kc][gi] = f63::pow(s, bg.groups[gi].adj);
+                    A.b_shift_steps[kc][gi] = f63::pow(s, bg.groups[gi].num_steps);
+                }
             }
+            // assertion values; a sequence becomes its interpolating polynomial, evaluated in-kernel at x * g^-first_step
+            std::vector<fe> polys;
+            const fe g_inv = inv(g);
+            for (size_t i = 0; i < air.assertions.size(); i++) {
+                const Assertion &s = air.assertions[i];
+                A.a_col[i] = s.column; A.a_group[i] = bg.group_of[i];
+                A.a_value[i] = s.values[0]; A.a_poly_len[i] = (unsigned)s.values.size(); A.a_poly_off[i] = polys.size();
+                A.a_xoff[i] = s.first_step ? f63::pow(g_inv, s.first_step) : ONE;
+                if (s.values.size() > 1) {
+                    std::vector<fe> c = host_interpolate(s.values);
+                    polys.insert(polys.end(), c.begin(), c.end());
+                }
+            }
+            d_apoly.reserve(polys.size() ? polys.size() : 1);
+            if (!polys.empty()) {   // pageable source: wait for the copy before `polys` goes away
+                CSG_CUDA(cudaMemcpyAsync(d_apoly.p, polys.data(), polys.size() * sizeof(fe), cudaMemcpyHostToDevice, st.s));
+                CSG_CUDA(cudaStreamSynchronize(st.s));
+            }
+            cargs_domain_ready = true;
         }
-        d_apoly.reserve(polys.size() ? polys.size() : 1);
-        if (!polys.empty()) CSG_CUDA(cudaMemcpyAsync(d_apoly.p, polys.data(), polys.size() * sizeof(fe), cudaMemcpyHostToDevice, st.s));
         d_cargs.reserve(1);
         CSG_CUDA(cudaMemcpyAsync(d_cargs.p, &A, sizeof A, cudaMemcpyHostToDevice, st.s));
         const size_t comb_plane = (cel ? cel : 1) * n;
         d_comb.reserve(comb_plane * d);
         d_parts.reserve(constraint_scratch_elements(air.id, n, cel ? cel : 1) * (all_components ? d : 1));
+        host_mark("  cons: args upload, scratch");
         if (!cons_ev[0]) for (auto &e : cons_ev) CSG_CUDA(cudaEventCreate(&e));
         // the low-degree splits interpolate across the even cosets: alone, or with an exchange when every rank owns whole pairs
-        const bool split = split_low_degree && (G == 1 || (ce == b && bl % 2 == 0));
+        const bool split = split_low_degree && n >= split_min_rows && (G == 1 || (ce == b && bl % 2 == 0));
         SplitExchange xch{(unsigned)G, (unsigned)rank, [](void *self, void *buf, size_t bytes) { static_cast<csg_ctx *>(self)->gather(buf, bytes); }, this, nullptr, 0};
         if (split && G > 1) {
             d_xch.reserve((size_t)16 * d * (ce / 2) * n);   // <= 16 polynomials per component on the even cosets of the whole proof
@@ -554,12 +608,12 @@ struct csg_ctx {
         else if (cel) csg::eval_constraints(air.id, d_cargs.p, A, d_lde.p, roots.W.p, d_ptab.p, d_apoly.p, d_parts.p, d_comb.p + plane * comb_plane, st, cons_ev,
                                             split ? &roots : nullptr, split ? &ntt : nullptr, px);
         else for (auto &e : cons_ev) CSG_CUDA(cudaEventRecord(e, st.s));
-        const float ms = t.stop(st);   // also keeps `polys` alive until the copy has completed
-        tm.constraints = plane ? tm.constraints + ms : ms;
+        t.stop(st, &tm.constraints, plane != 0);   // (`polys` is pageable memory: its copy was staged before cudaMemcpyAsync returned)
         tm.stage_launches[2] = plane ? tm.stage_launches[2] + t.launches : t.launches;
         float *parts_ms[4] = {&tm.cons_rescue, &tm.cons_ecc_banks, &tm.cons_ecc_final, &tm.cons_rest};
-        for (int k = 0; k < 4; k++) { float pm = 0; CSG_CUDA(cudaEventElapsedTime(&pm, cons_ev[k], cons_ev[k + 1])); *parts_ms[k] = plane ? *parts_ms[k] + pm : pm; }
-        { float pm = 0; CSG_CUDA(cudaEventElapsedTime(&pm, cons_ev[1], cons_ev[5])); tm.cons_ecc_low = plane ? tm.cons_ecc_low + pm : pm; }
+        for (int k = 0; k < 4; k++) t.span(cons_ev[k], cons_ev[k + 1], parts_ms[k], plane != 0);
+        t.span(cons_ev[1], cons_ev[5], &tm.cons_ecc_low, plane != 0);
+        if (d > 1 && !all_components) t.flush();   // evaluated plane by plane: the next plane records the same events again
         if (plane + 1 == d || all_components) stage = S_EVALUATED;
     }
     // E-valued coefficients: the constraint values are base-field elements, so component j of the merged column is the same
@@ -635,7 +689,7 @@ struct csg_ctx {
         coset_ntt_columns(roots, ntt, d_cpolys.p, n, d_clde.p, n, cw * n, cw, logn, lde_shift.data(), bl, st);
         commit_rows(d_clde.p, (unsigned)cw, cw * n, d_cnodes, d_ctop);
         download_root(subtrees() ? d_ctop : d_cnodes, root);
-        tm.composition = t.stop(st); tm.stage_launches[3] = t.launches;
+        t.stop(st, &tm.composition); tm.stage_launches[3] = t.launches;
         stage = S_COMPOSED;
     }
 
@@ -664,7 +718,7 @@ struct csg_ctx {
         const fe zm = f63::pow(z, ce);
         ood_comp.resize(ce);
         eval_polys_at(d_cpolys.p, n, ce, n, &zm, 1, ood_comp.data(), scratch2, st);
-        tm.ood_deep = t.stop(st); tm.stage_launches[4] = t.launches;
+        t.stop(st, &tm.ood_deep); tm.stage_launches[4] = t.launches;
         stage = S_OOD;
     }
     void deep(const fe *trace_ab, const fe *comp_d, fe lambda, fe mu) {
@@ -697,8 +751,8 @@ struct csg_ctx {
         if (fri.empty()) fri.emplace_back(new FriLayer());
         nfri = 1;
         fri[0]->evals = d_deep.p; fri[0]->m = lde_n; fri[0]->committed = false;
-        tm.ood_deep += t.stop(st); tm.stage_launches[4] += t.launches;   // also keeps coef alive until the copies have completed
-        tm.fri = 0; tm.stage_launches[5] = 0;
+        t.stop(st, &tm.ood_deep, true); tm.stage_launches[4] += t.launches;   // also keeps coef alive until the copies have completed
+        t.zero(&tm.fri); tm.stage_launches[5] = 0;
         stage = S_DEEP;
     }
 
@@ -741,7 +795,7 @@ struct csg_ctx {
                 basis = x_mul(d, basis, phi);
             }
         }
-        tm.ood_deep = t.stop(st); tm.stage_launches[4] = t.launches;
+        t.stop(st, &tm.ood_deep); tm.stage_launches[4] = t.launches;
         stage = S_OOD;
     }
     void deep_x(const xe *trace_ab, const xe *comp_d, const xe &lambda, const xe &mu) {
@@ -787,8 +841,8 @@ struct csg_ctx {
         if (fri.empty()) fri.emplace_back(new FriLayer());
         nfri = 1;
         fri[0]->evals = d_deep.p; fri[0]->m = lde_n; fri[0]->committed = false;
-        tm.ood_deep += t.stop(st); tm.stage_launches[4] += t.launches;
-        tm.fri = 0; tm.stage_launches[5] = 0;
+        t.stop(st, &tm.ood_deep, true); tm.stage_launches[4] += t.launches;
+        t.zero(&tm.fri); tm.stage_launches[5] = 0;
         stage = S_DEEP;
     }
 
@@ -805,7 +859,7 @@ struct csg_ctx {
         merkle_build(L.nodes.p, q, (int)opt.hash_fn, st);
         download_root(L.nodes, root);
         L.committed = true;
-        tm.fri += t.stop(st); tm.stage_launches[5] += t.launches;
+        t.stop(st, &tm.fri, true); tm.stage_launches[5] += t.launches;
     }
     void fri_fold(fe alpha) { fri_fold_x(x_from(alpha)); }
     void fri_fold_x(const xe &alpha) {
@@ -832,15 +886,15 @@ struct csg_ctx {
         else { FoldArgsX ax{a, alpha, d}; fri_fold4_ext(L.evals, m, m, roots.W.p, ax, N.owned.p, q, st); }
         N.evals = N.owned.p; N.m = q; N.committed = false;
         nfri++;
-        tm.fri += t.stop(st); tm.stage_launches[5] += t.launches;
+        t.stop(st, &tm.fri, true); tm.stage_launches[5] += t.launches;
     }
     size_t num_fri_folds() const { size_t r = 0, d = lde_n; while (d > opt.fri_max_remainder_size) { d /= 4; r++; } return r; }
 
     // ------------------------------------------------------------------------------------------ stage 9
     void upload_positions(const std::vector<uint32_t> &p32) {
         d_idx.reserve(std::max<size_t>(p32.size(), 4096));
+        // no wait here: every caller keeps p32 alive until it has downloaded what the positions select
         CSG_CUDA(cudaMemcpyAsync(d_idx.p, p32.data(), p32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st.s));
-        CSG_CUDA(cudaStreamSynchronize(st.s));
     }
     // rows (canonical, row-major) of a coset-major matrix at the given natural positions
     // sharded (the LDE matrices of a split proof): every context gathers the rows of its own cosets, zeros elsewhere, and the
@@ -916,7 +970,14 @@ struct csg_ctx {
     void prove_loaded(uint8_t **proof, size_t *proof_len, const uint64_t *host = nullptr, int host_repr = CSG_REPR_CANONICAL, const uint64_t *const *host_cols = nullptr) {
         if (!host && !host_cols) need(S_TRACE, "csg_load_trace must be called first");
         auto t0 = std::chrono::steady_clock::now();
+        // CSG_HOST_TRACE: host clock at the stage boundaries of this call, printed to stderr (where the time of a small proof
+        // goes: launches, round trips of the Fiat-Shamir transcript, host arithmetic)
+        static const bool host_trace = getenv("CSG_HOST_TRACE") != nullptr;
+        HostTrace trace{t0, {}};
+        struct TraceScope { bool on; TraceScope(bool o, HostTrace *t) : on(o) { if (on) g_host_trace = t; } ~TraceScope() { if (on) g_host_trace = nullptr; } } trace_scope(host_trace, &trace);
+        auto mark = [&](const char *what) { host_mark(what); };
         const unsigned long long launches0 = st.launches;
+        stage_timer.discard(); query_timer.discard();
         comm_used = 0;
         const int hf = (int)opt.hash_fn;
         const size_t w = air.width, nc = air.num_constraints(), na = air.assertions.size();
@@ -927,14 +988,19 @@ struct csg_ctx {
         auto base = [](const std::vector<xe> &v) { std::vector<fe> o; for (const xe &e : v) o.push_back(e.c[0]); return o; };
 
         uint8_t trace_root[32], comp_root[32];
+        mark("setup");
         extend_and_commit_trace(trace_root, host, host_repr, host_cols);
+        mark("extend+commit trace");
         coin.reseed(trace_root);
         std::vector<xe> t_ab(2 * nc), b_ab(2 * na + 2, x_zero());
         for (size_t i = 0; i < 2 * nc; i++) t_ab[i] = coin.draw_x(d);
         for (size_t i = 0; i < 2 * na; i++) b_ab[i] = coin.draw_x(d);
+        mark("draw coefficients");
         if (d == 1) eval_constraints(base(t_ab).data(), base(b_ab).data());
         else eval_constraints_x(t_ab.data(), b_ab.data());
+        mark("constraints (enqueue)");
         commit_composition(comp_root);
+        mark("composition + commit");
         coin.reseed(comp_root);
 
         const xe zz = coin.draw_x(d);
@@ -949,6 +1015,7 @@ struct csg_ctx {
         hash_elements_host(hf, flat(xood_cur).data(), w * d, dg); coin.reseed(dg);
         hash_elements_host(hf, flat(xood_next).data(), w * d, dg); coin.reseed(dg);
         hash_elements_host(hf, flat(xood_comp).data(), ce * d, dg); coin.reseed(dg);
+        mark("out-of-domain frame");
 
         std::vector<xe> dab(2 * w), dd(ce);
         for (size_t c = 0; c < w; c++) { dab[2 * c] = coin.draw_x(d); dab[2 * c + 1] = coin.draw_x(d); (void)coin.draw_x(d); }
@@ -956,6 +1023,7 @@ struct csg_ctx {
         const xe lambda = coin.draw_x(d), mu = coin.draw_x(d);
         if (d == 1) deep(base(dab).data(), base(dd).data(), lambda.c[0], mu.c[0]);
         else deep_x(dab.data(), dd.data(), lambda, mu);
+        mark("deep (enqueue)");
 
         const size_t nlayers = num_fri_folds() + 1;
         std::vector<std::vector<uint8_t>> fri_roots(nlayers, std::vector<uint8_t>(32));
@@ -965,6 +1033,7 @@ struct csg_ctx {
             const xe alpha = coin.draw_x(d);
             if (l + 1 < nlayers) fri_fold_x(alpha);
         }
+        mark("fri layers");
 
         Timer &tq = query_timer;
         tq.start(st);
@@ -972,6 +1041,7 @@ struct csg_ctx {
         while (coin.check_leading_zeros(nonce) < opt.grinding_factor) nonce++;
         coin.reseed_with_int(nonce);
         std::vector<size_t> pos = coin.draw_integers(opt.num_queries, lde_n);
+        mark("grinding + positions");
 
         Bytes pf;
         write_context(pf);
@@ -1001,7 +1071,9 @@ struct csg_ctx {
         B.rows_words += rem_len;
         std::vector<uint64_t> rows;
         std::vector<uint8_t> digs;
+        mark("plan openings");
         run_openings(B, rows, digs, last, rem_off);
+        mark("openings round trip");
         auto emit = [&](const Opening &o) {
             pf.u32((uint32_t)(o.rows_len * 8));
             for (size_t k = 0; k < o.rows_len; k++) pf.u64(rows[o.rows_off + k]);
@@ -1024,7 +1096,8 @@ struct csg_ctx {
         for (size_t k = 0; k < rem_len; k++) pf.u64(rows[rem_off + k]);
         pf.u8(1);
         pf.u64(nonce);
-        tm.queries = tq.stop(st); tm.stage_launches[6] = tq.launches;
+        tq.stop(st, &tm.queries); tm.stage_launches[6] = tq.launches;
+        mark("serialise");
         tm.kernel_launches = st.launches - launches0;
         tm.comm = comm_ms();
         tm.total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1033,6 +1106,12 @@ struct csg_ctx {
         if (!*proof) throw std::bad_alloc();
         memcpy(*proof, pf.v.data(), pf.v.size());
         *proof_len = pf.v.size();
+        if (host_trace) {
+            mark("timers + copy out");
+            double prev = 0;
+            fprintf(stderr, "[csg host trace] %zu x %zu, %llu launches\n", (size_t)air.width, n, (unsigned long long)tm.kernel_launches);
+            for (auto &m : trace.marks) { fprintf(stderr, "  %-24s +%8.1f us  (at %8.1f)\n", m.first, m.second - prev, m.second); prev = m.second; }
+        }
         stage = S_TRACE;   // the resident trace (d_io) can be proved again
     }
     // ---- batched openings

@@ -162,6 +162,22 @@ def test_transaction_proof_identical_to_oracle(ctx, oracle, csg, num_tx, hash_fn
     assert oracle.verify(oracle.AIR_TRANSACTION, wrong, got) != 0      # src/tests.rs:32-37
 
 
+@pytest.mark.parametrize("ext", [1, 2, 3])
+def test_low_degree_split_and_direct_evaluation_give_the_same_proof(ctx, csg, monkeypatch, ext):
+    # small traces evaluate every constraint on every coset (fewer launches); from 2^14 rows on the low-degree constraints are
+    # evaluated on half of the cosets and extended.  CSG_SPLIT_MIN_ROWS=0 forces the second path on the small traces here.
+    cases = [(csg.AIR_TRANSACTION, csg.TransactionBatch(seed=1, num_tx=2).transaction_trace()),
+             (csg.AIR_SCHNORR, csg.SignatureBatch(seed=5, num_sig=2).schnorr_trace())]
+    opt = csg.ProofOptions(field_extension=ext)
+    direct = [ctx.prove(air, trace, pub, opt) for air, (trace, pub) in cases]
+    launches_direct = ctx.timings()["kernel_launches"]
+    monkeypatch.setenv("CSG_SPLIT_MIN_ROWS", "0")
+    with csg.Context(0) as forced:
+        split = [forced.prove(air, trace, pub, opt) for air, (trace, pub) in cases]
+        assert forced.timings()["kernel_launches"] > launches_direct     # the split really ran
+    assert split == direct
+
+
 def test_reproving_a_resident_trace_gives_the_same_bytes(ctx, csg):
     batch = csg.TransactionBatch(seed=9, num_tx=2)
     trace, pub = batch.transaction_trace()

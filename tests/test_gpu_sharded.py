@@ -57,6 +57,18 @@ def test_range_two_columns_over_eight_ranks(csg, oracle):
     sharded_equals_single(csg, oracle, csg.AIR_RANGE, trace, pub, csg.ProofOptions(), 8)
 
 
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("ext", [1, 3])
+def test_split_exchange_between_ranks_on_a_small_trace(csg, oracle, monkeypatch, world, ext):
+    # ranks that own whole even/odd coset pairs keep the low-degree split and exchange the interpolants; by default only traces
+    # of 2^14 rows or more take that path (the headline test), CSG_SPLIT_MIN_ROWS=0 forces it here
+    trace, pub = csg.TransactionBatch(seed=13, num_tx=2).transaction_trace()
+    with csg.Context(0) as one:
+        want = one.prove(csg.AIR_TRANSACTION, trace, pub, csg.ProofOptions(field_extension=ext))
+    monkeypatch.setenv("CSG_SPLIT_MIN_ROWS", "0")
+    assert sharded_equals_single(csg, oracle, csg.AIR_TRANSACTION, trace, pub, csg.ProofOptions(field_extension=ext), world) == want
+
+
 def test_world_must_divide_blowup(csg):
     trace, pub = csg.build_rescue_trace(np.arange(42, 49, dtype=np.uint64), 128)
     with csg.LocalGroup(8) as grp:

@@ -1,0 +1,5 @@
+#!/bin/bash
+timeout 1700 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -14 gpurun_out/pytest_gpu.log
+python tools/small_latency.py --reps 200 --out gpurun_out/small_latency.json > gpurun_out/small_lazy.txt 2>&1; cut -c1-330 gpurun_out/small_lazy.txt
+bash tools/ab_lib.sh
