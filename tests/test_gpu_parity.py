@@ -189,6 +189,24 @@ def test_reproving_a_resident_trace_gives_the_same_bytes(ctx, csg):
     assert t["kernel_launches"] > 0 and t["total"] > 0
 
 
+def test_stage_timings_are_read_on_demand(ctx, csg):
+    # csg_get_timings: the stage times are event pairs collected when asked for, and describe the LAST proof only
+    trace, pub = csg.TransactionBatch(seed=9, num_tx=4).transaction_trace()
+    ctx.prove(csg.AIR_TRANSACTION, trace, pub, csg.ProofOptions())
+    stages = ("lde", "commit_trace", "constraints", "composition", "ood_deep", "fri", "queries")
+    t1 = ctx.timings()
+    assert all(t1[k] > 0 for k in stages)
+    assert sum(t1[k] for k in stages) <= t1["total"] * 1.02
+    assert ctx.timings() == t1                                   # reading twice changes nothing
+    for _ in range(3):                                           # proofs nobody asks about leave nothing behind
+        ctx.reload_resident_trace()
+        ctx.prove_loaded()
+    t2 = ctx.timings()
+    assert sum(t2[k] for k in stages) <= t2["total"] * 1.02
+    assert t2["fri"] < 2 * t1["fri"] + 0.05
+    assert 0 < sum(t2["stage_launches"].values()) <= t2["kernel_launches"] == t1["kernel_launches"]
+
+
 def test_example_facade(csg, oracle):
     ex = csg.get_example(2, seed=4)
     proof = ex.prove()                                   # witness built on the device
