@@ -9,6 +9,7 @@ missing or no CUDA device can be opened, every entry point raises.
 from __future__ import annotations
 
 import ctypes as C
+from typing import Optional
 import os
 import subprocess
 from pathlib import Path
@@ -88,6 +89,8 @@ def lib() -> C.CDLL:
         "csg_load_trace": (C.c_int, [vp, _u64p, C.c_int]), "csg_reload_resident_trace": (C.c_int, [vp]),
         "csg_prove_loaded": (C.c_int, [vp, C.POINTER(_u8p), _szp]),
         "csg_prove_trace": (C.c_int, [vp, _u64p, C.c_int, C.POINTER(_u8p), _szp]),
+        "csg_prefetch_trace": (C.c_int, [vp, _u64p, C.c_int]),
+        "csg_prove_prefetched": (C.c_int, [vp, _u64p, C.c_int, C.POINTER(_u8p), _szp]),
         "csg_host_alloc": (vp, [C.c_size_t]), "csg_host_free": (None, [vp]), "csg_host_register": (C.c_int, [vp, C.c_size_t]),
         "csg_host_unregister": (C.c_int, [vp]),
         "csg_extend_and_commit_trace": (C.c_int, [vp, _u8p]), "csg_eval_constraints": (C.c_int, [vp, _u64p, _u64p]),
@@ -252,6 +255,18 @@ class Context:
         under the extension, pageable memory is staged through the library's own pinned buffers"""
         out, n = _u8p(), C.c_size_t()
         self._check(lib().csg_prove_trace(self._h, C.cast(host_ptr, _u64p), repr, C.byref(out), C.byref(n)))
+        return self._take_proof(out, n)
+
+    def prefetch_trace_ptr(self, host_ptr: int, repr: int = REPR_CANONICAL):
+        """start the copy of a trace at a raw HOST pointer (keep it alive until the prove_prefetched_ptr that proves it has
+        started); returns at once for page-locked memory"""
+        self._check(lib().csg_prefetch_trace(self._h, C.cast(host_ptr, _u64p), repr))
+
+    def prove_prefetched_ptr(self, next_host_ptr: Optional[int] = None, repr: int = REPR_CANONICAL) -> bytes:
+        """proof of the prefetched trace; the copy of the trace at next_host_ptr (if any) runs under it"""
+        out, n = _u8p(), C.c_size_t()
+        nxt = C.cast(next_host_ptr, _u64p) if next_host_ptr else C.cast(None, _u64p)
+        self._check(lib().csg_prove_prefetched(self._h, nxt, repr, C.byref(out), C.byref(n)))
         return self._take_proof(out, n)
 
     def reload_resident_trace(self):

@@ -23,7 +23,9 @@ class Bytes {
     void u8(uint8_t x) { v.push_back(x); }
     void u16(uint16_t x) { for (int i = 0; i < 2; i++) v.push_back((uint8_t)(x >> (8 * i))); }
     void u32(uint32_t x) { for (int i = 0; i < 4; i++) v.push_back((uint8_t)(x >> (8 * i))); }
-    void u64(uint64_t x) { for (int i = 0; i < 8; i++) v.push_back((uint8_t)(x >> (8 * i))); }
+    void u64(uint64_t x) { put(&x, 8); }
+    void u64s(const uint64_t *x, size_t n) { put(x, 8 * n); }   // n little-endian words at once (the opened rows of a proof)
+    static_assert(__BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__, "the serialiser writes host words as little-endian bytes");
     void element(fe m) { u64(f63::from_mont(m)); }   // BaseElement::write_into: canonical little-endian
 };
 

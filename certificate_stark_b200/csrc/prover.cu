@@ -60,6 +60,13 @@ int csg_prove_trace(csg_ctx *ctx, const uint64_t *trace, int repr, uint8_t **pro
         ctx->prove_loaded(proof, proof_len, trace, repr);
     });
 }
+int csg_prefetch_trace(csg_ctx *ctx, const uint64_t *trace, int repr) { return guarded(ctx, [&] { ctx->prefetch_trace(trace, repr); }); }
+int csg_prove_prefetched(csg_ctx *ctx, const uint64_t *next_trace, int next_repr, uint8_t **proof, size_t *proof_len) {
+    return guarded(ctx, [&] {
+        if (!proof || !proof_len) throw ArgError("null argument");
+        ctx->prove_prefetched(next_trace, next_repr, proof, proof_len);
+    });
+}
 // the same with one pointer per column: a winterfell TraceTable keeps each column in its own Vec
 int csg_prove_columns(csg_ctx *ctx, int air_id, const uint64_t *const *columns, int repr, size_t trace_len, const uint64_t *pub, size_t npub,
                       const csg_options *opt, uint8_t **proof, size_t *proof_len) {

@@ -224,7 +224,28 @@ struct csg_ctx {
         // winterfell caps the remainder at 1024 elements; its byte length is serialised as a u16 (8192 elements would wrap to 0)
         if (o->fri_max_remainder_size < 4 || o->fri_max_remainder_size > 1024 || (o->fri_max_remainder_size & (o->fri_max_remainder_size - 1)))
             throw ArgError("FRI remainder size must be a power of two in 4..1024");
-        try { air = make_air(air_id, trace_len, pub, npub); } catch (const std::invalid_argument &e) { throw ArgError(e.what()); }
+        // The same AIR, length, options and sharding as the last call -- a prover proving batch after batch, where only the public
+        // inputs (assertion values) differ: the root table, the periodic-column tables and the coset scale tables on the device
+        // stay as they are, and so does a prefetched trace.
+        const bool same_shape = stage >= S_AIR && air.id == air_id && n == trace_len && memcmp(&opt, o, sizeof opt) == 0 &&
+                                G == (comm ? (size_t)comm->world : 1) && rank == (comm ? (size_t)comm->rank : 0);
+        bool same_periodic = same_shape;
+        {
+            AirDesc fresh;
+            try { fresh = make_air(air_id, trace_len, pub, npub); } catch (const std::invalid_argument &e) { throw ArgError(e.what()); }
+            // (the Schnorr AIR's periodic columns carry the public keys and messages: those tables follow the public inputs)
+            same_periodic = same_periodic && fresh.periodic.size() == air.periodic.size();
+            for (size_t c = 0; same_periodic && c < fresh.periodic.size(); c++) same_periodic = fresh.periodic[c].values == air.periodic[c].values;
+            air = std::move(fresh);
+        }
+        if (same_shape && same_periodic) {
+            tg = transition_groups(air);
+            bg = boundary_groups(air);
+            cargs_domain_ready = false;   // assertion values and their polynomials are refreshed by the next constraint evaluation
+            nfri = 0;
+            stage = S_AIR;
+            return;
+        }
         opt = *o;
         d = (int)o->field_extension;
         if (d > 1) xk = ext_consts();
@@ -258,6 +279,7 @@ struct csg_ctx {
         build_periodic_tables();
         lde_tables.build(lde_shift.data(), bl, logn, st);
         nfri = 0;
+        if (next_pending) { CSG_CUDA(cudaStreamSynchronize(copy_stream)); next_pending = false; }   // a prefetched trace of another shape is dropped
         stage = S_AIR;
     }
 
@@ -318,6 +340,43 @@ struct csg_ctx {
         tm.h2d = t.stop(st);
         nfri = 0;
         stage = S_TRACE;
+    }
+    // ---- a stream of traces: the copy of the NEXT trace runs on the copy stream under the proof of the current one.
+    // Two trace buffers take turns (d_io: being proved / resident; d_next: being filled).  Proofs are synchronous calls, so
+    // when a copy into d_next starts nothing in flight reads that buffer: it was d_io two proofs ago.
+    DBuf<uint64_t> d_next;
+    cudaEvent_t next_a = nullptr, next_b = nullptr;
+    bool next_pending = false;
+    int next_repr = CSG_REPR_CANONICAL;
+    void prefetch_trace(const uint64_t *trace, int repr) {
+        need(S_AIR, "csg_set_air must be called first");
+        check_repr(repr);
+        if (!trace) throw ArgError("null trace");
+        if (next_pending) throw StateError("a prefetched trace is already waiting: csg_prove_prefetched proves it");
+        csg_shard_plan plan;
+        shard_plan(rank, G, b, ce, air.width, &plan);   // a sharded proof reads only the column block this rank interpolates
+        d_next.reserve((size_t)air.width * n);
+        if (!copy_stream) CSG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        if (!next_a) { CSG_CUDA(cudaEventCreate(&next_a)); CSG_CUDA(cudaEventCreate(&next_b)); }
+        CSG_CUDA(cudaEventRecord(next_a, copy_stream));
+        if (plan.num_columns)
+            CSG_CUDA(cudaMemcpyAsync(d_next.p + (size_t)plan.first_column * n, trace + (size_t)plan.first_column * n,
+                                     (size_t)plan.num_columns * n * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
+        CSG_CUDA(cudaEventRecord(next_b, copy_stream));
+        next_repr = repr;
+        next_pending = true;
+    }
+    void prove_prefetched(const uint64_t *next_trace, int next_trace_repr, uint8_t **proof, size_t *proof_len) {
+        if (!next_pending) throw StateError("csg_prefetch_trace must be called first");
+        CSG_CUDA(cudaEventSynchronize(next_b));   // it ran under the previous proof; also: the caller's buffer is free from here on
+        CSG_CUDA(cudaEventElapsedTime(&tm.h2d, next_a, next_b));
+        std::swap(d_io.p, d_next.p); std::swap(d_io.n, d_next.n);
+        trace_repr = next_repr;
+        next_pending = false;
+        nfri = 0;
+        stage = S_TRACE;
+        if (next_trace) prefetch_trace(next_trace, next_trace_repr);
+        prove_loaded(proof, proof_len);
     }
     // for benchmarking with inputs already resident: the trace as left on the device by the last load_trace
     void reload_resident() {
@@ -1044,6 +1103,7 @@ struct csg_ctx {
         mark("grinding + positions");
 
         Bytes pf;
+        pf.v.reserve(256 * 1024);
         write_context(pf);
         pf.u16((uint16_t)((2 + nlayers) * 32));
         pf.put(trace_root, 32); pf.put(comp_root, 32);
@@ -1076,7 +1136,7 @@ struct csg_ctx {
         mark("openings round trip");
         auto emit = [&](const Opening &o) {
             pf.u32((uint32_t)(o.rows_len * 8));
-            for (size_t k = 0; k < o.rows_len; k++) pf.u64(rows[o.rows_off + k]);
+            pf.u64s(rows.data() + o.rows_off, o.rows_len);
             Bytes paths;
             paths.u8((uint8_t)o.slots.size());
             size_t at = o.dig_off;
@@ -1093,7 +1153,7 @@ struct csg_ctx {
         pf.u8((uint8_t)(nlayers - 1));
         for (const Opening &o : o_fri) emit(o);
         pf.u16((uint16_t)(rem_len * 8));
-        for (size_t k = 0; k < rem_len; k++) pf.u64(rows[rem_off + k]);
+        pf.u64s(rows.data() + rem_off, rem_len);
         pf.u8(1);
         pf.u64(nonce);
         tq.stop(st, &tm.queries); tm.stage_launches[6] = tq.launches;

@@ -106,6 +106,14 @@ int csg_load_trace(csg_ctx *ctx, const uint64_t *trace, int repr);           /* 
 int csg_prove_loaded(csg_ctx *ctx, uint8_t **proof, size_t *proof_len);      /* proof of the resident trace */
 /* proof of a trace in HOST memory for the AIR set by csg_set_air: the H2D copy is pipelined with the trace extension */
 int csg_prove_trace(csg_ctx *ctx, const uint64_t *trace, int repr, uint8_t **proof, size_t *proof_len);
+/* A stream of traces for the AIR set by csg_set_air (a prover service proving batch after batch): the copy of the NEXT trace runs on
+ * its own stream under the proof of the current one, so in the steady state a proof costs what it costs with the trace already in
+ * HBM.  csg_prefetch_trace starts the copy of the first trace and returns at once; csg_prove_prefetched proves the trace that is
+ * waiting and, when next_trace is not NULL, starts the copy of that one first.  The memory of a prefetched trace must stay valid
+ * until the csg_prove_prefetched call that proves it has started (page-locked memory -- csg_host_alloc / csg_host_register --
+ * for the copy to be asynchronous; pageable memory works but is copied synchronously).  One trace can wait at a time. */
+int csg_prefetch_trace(csg_ctx *ctx, const uint64_t *trace, int repr);
+int csg_prove_prefetched(csg_ctx *ctx, const uint64_t *next_trace, int next_repr, uint8_t **proof, size_t *proof_len);
 int csg_reload_resident_trace(csg_ctx *ctx);                                 /* re-arm the trace left in HBM by the last csg_load_trace (benchmarks) */
 int csg_extend_and_commit_trace(csg_ctx *ctx, uint8_t root[32]);             /* Trace::extend + build_commitment */
 /* t_coeffs: (alpha,beta) per transition constraint; b_coeffs: (alpha,beta) per assertion in winterfell's sorted order */
