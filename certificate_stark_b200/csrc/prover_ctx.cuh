@@ -422,7 +422,24 @@ struct csg_ctx {
         csg_shard_plan plan;
         shard_plan(rank, G, b, ce, w, &plan);
         const size_t cpr = plan.columns_per_rank, c_lo = plan.first_column, c_hi = c_lo + plan.num_columns, wpad = cpr * G;
-        const size_t CHUNK = host ? 8 : cpr;   // nothing to overlap when the trace is already resident: one chunk
+        // nothing to overlap when the trace is already resident: one chunk.  From host memory the extension can only start once
+        // the first chunk has arrived, so the chunks ramp up -- 1, 3, 4, then 8 columns (8 MB first: 0.15 ms of PCIe instead of
+        // 1.2 ms; end to end 61.2 -> 60.7 ms per 1024-transaction proof, gpurun_out/s3b/e2e_chunks.txt) -- CSG_H2D_CHUNKS="a,b,c"
+        // overrides the schedule, the last entry repeating
+        std::vector<size_t> chunks;
+        if (!host) chunks.push_back(cpr);
+        else {
+            static const std::vector<size_t> sched = [] {
+                std::vector<size_t> v;
+                if (const char *e = getenv("CSG_H2D_CHUNKS"))
+                    for (const char *q = e; *q;) { char *end; const unsigned long x = strtoul(q, &end, 10); if (end == q) break; if (x) v.push_back(x); q = *end ? end + 1 : end; }
+                if (v.empty()) v = {1, 3, 4, 8};
+                return v;
+            }();
+            for (size_t c = c_lo, k = 0; c < c_hi; k++) { const size_t s = std::min(sched[std::min(k, sched.size() - 1)], c_hi - c); chunks.push_back(s); c += s; }
+        }
+        size_t CHUNK = 1;
+        for (size_t s : chunks) CHUNK = std::max(CHUNK, s);
         Timer &t = stage_timer;
         t.start(st);
         d_io.reserve(w * n); d_polys.reserve(wpad * n); scratch.reserve(wpad * n); d_lde.reserve(w * n * bl);
@@ -431,7 +448,7 @@ struct csg_ctx {
         const bool staged = host && any_pageable;
         if (host) {
             if (!copy_stream) CSG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-            while (chunk_ev.size() < (cpr + CHUNK - 1) / CHUNK + 1) { cudaEvent_t e; CSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); chunk_ev.push_back(e); }
+            while (chunk_ev.size() < chunks.size() + 1) { cudaEvent_t e; CSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); chunk_ev.push_back(e); }
             if (!h2d_a) { CSG_CUDA(cudaEventCreate(&h2d_a)); CSG_CUDA(cudaEventCreate(&h2d_b)); }
             if (staged && stage_words < CHUNK * n) {
                 for (auto &b : stage_buf) { if (b) cudaFreeHost(b); b = nullptr; }
@@ -444,8 +461,8 @@ struct csg_ctx {
             CSG_CUDA(cudaStreamWaitEvent(copy_stream, chunk_ev[0], 0));
             CSG_CUDA(cudaEventRecord(h2d_a, copy_stream));
         }
-        for (size_t c0 = c_lo, k = 0; c0 < c_hi; c0 += CHUNK, k++) {
-            const size_t nc = std::min(CHUNK, c_hi - c0);
+        for (size_t c0 = c_lo, k = 0; k < chunks.size() && c0 < c_hi; c0 += chunks[k], k++) {
+            const size_t nc = chunks[k];
             if (host) {
                 bool contiguous = true;
                 for (size_t j = 1; j < nc; j++) contiguous = contiguous && colptr[c0 + j] == colptr[c0] + j * n;
@@ -467,7 +484,7 @@ struct csg_ctx {
                     CSG_CUDA(cudaMemcpyAsync(d_io.p + (c0 + j) * n, colptr[c0 + j], n * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
                 if (staged) CSG_CUDA(cudaEventRecord(stage_ev[k % STAGE_BUFS], copy_stream));
                 CSG_CUDA(cudaEventRecord(chunk_ev[k], copy_stream));
-                if (c0 + CHUNK >= c_hi) CSG_CUDA(cudaEventRecord(h2d_b, copy_stream));
+                if (c0 + nc >= c_hi) CSG_CUDA(cudaEventRecord(h2d_b, copy_stream));
                 CSG_CUDA(cudaStreamWaitEvent(st.s, chunk_ev[k], 0));
             }
             // the representation change of the caller's words costs nothing: interpolation is linear, so the factor R^2 of
