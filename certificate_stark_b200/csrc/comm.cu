@@ -24,6 +24,7 @@ struct NcclApi {
     int (*CommDestroy)(void *) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -49,13 +50,14 @@ NcclApi &nccl() {
         api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
         api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
         api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
         api.Send = (decltype(api.Send))sym("ncclSend");
         api.Recv = (decltype(api.Recv))sym("ncclRecv");
         api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
         api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
         api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     });
-    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.AllReduce || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd || !api.GetErrorString)
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.AllReduce || !api.Broadcast || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd || !api.GetErrorString)
         throw std::runtime_error("NCCL is not available: libnccl.so.2 could not be loaded (set CSG_NCCL_LIB to its path)");
     return api;
 }
@@ -68,6 +70,9 @@ struct NcclComm final : Comm {
     ~NcclComm() override { if (comm) nccl().CommDestroy(comm); }
     void all_gather(void *buf, size_t bytes, Stream &st) override {
         nccl_check(nccl().AllGather((const char *)buf + (size_t)rank * bytes, buf, bytes, NCCL_UINT8, comm, st.s), "ncclAllGather");
+    }
+    void broadcast(void *buf, size_t bytes, int root, Stream &st) override {
+        nccl_check(nccl().Broadcast(buf, buf, bytes, NCCL_UINT8, root, comm, st.s), "ncclBroadcast");
     }
     void all_to_all(const void *send, void *recv, size_t bytes, Stream &st) override {
         nccl_check(nccl().GroupStart(), "ncclGroupStart");
@@ -117,6 +122,14 @@ struct LocalComm final : Comm {
                 CSG_CUDA(cudaMemcpyAsync((char *)buf + (size_t)p * bytes, (const char *)grp->ptr[p] + (size_t)p * bytes, bytes, cudaMemcpyDefault, st.s));
         CSG_CUDA(cudaStreamSynchronize(st.s));
         grp->barrier();                                  // nobody reuses a buffer a peer is still reading
+    }
+    void broadcast(void *buf, size_t bytes, int root, Stream &st) override {
+        CSG_CUDA(cudaStreamSynchronize(st.s));           // the root's slice is complete, the receivers' buffers are free
+        grp->ptr[rank] = buf;
+        grp->barrier();
+        if (rank != root) CSG_CUDA(cudaMemcpyAsync(buf, grp->ptr[root], bytes, cudaMemcpyDefault, st.s));
+        CSG_CUDA(cudaStreamSynchronize(st.s));
+        grp->barrier();
     }
     void all_to_all(const void *send, void *recv, size_t bytes, Stream &st) override {
         CSG_CUDA(cudaStreamSynchronize(st.s));           // own send buffer is complete

@@ -22,6 +22,9 @@ struct Comm {
     // in place: buf holds `world` slices of `bytes`; slice `rank` has been produced on stream s; on return (stream order)
     // every slice is filled
     virtual void all_gather(void *buf, size_t bytes, Stream &st) = 0;
+    // `bytes` at buf, produced on stream st by rank `root`, arrive at the same address on every other rank (stream order).
+    // An all-gather issued slice by slice: the receivers can start on slice q while slice q+1 is still on the links.
+    virtual void broadcast(void *buf, size_t bytes, int root, Stream &st) = 0;
     // recv slice p <- slice `rank` of peer p's send buffer; `world` slices of `bytes` each on both sides (send != recv).
     // The digest exchange of a commitment: every rank hashed the rows of its cosets and needs the leaves of a contiguous range.
     virtual void all_to_all(const void *send, void *recv, size_t bytes, Stream &st) = 0;

@@ -142,6 +142,7 @@ struct csg_ctx {
     size_t comm_used = 0;
     Stream comm_stream;                    // the coefficient all-gather overlaps the extension of the own columns
     cudaEvent_t ev_intt = nullptr, ev_gathered = nullptr;
+    std::vector<cudaEvent_t> block_ev;     // block q of the coefficient exchange has landed
 
     DBuf<uint64_t> d_io, d_wit_in;
     // device-side batch builder (batch_gen.cu): plan uploads, node versions, signatures; tables cached per context
@@ -494,17 +495,38 @@ struct csg_ctx {
         }
         if (G > 1) {
             // The coefficient all-gather (the largest exchange) runs on its own stream while this context already extends the
-            // columns it interpolated itself; the other ranks' columns follow once they have arrived.
+            // columns it interpolated itself; the other ranks' columns follow once they have arrived.  With 2 and 4 ranks the
+            // gather is hidden entirely under the own block (47 / 24 columns); with 8 it is not (12 columns: 0.3 ms of transforms
+            // against ~1 ms of gather).  CSG_COEF_BLOCKWISE=1 issues it block by block instead -- one broadcast per column block,
+            // in rank order, each block extended as soon as it has landed -- but a broadcast drives one sender's links at a time
+            // where the all-gather drives all of them: 10.2 against 9.6 ms for this stage at 2 ranks (profiles/r2_coef_exchange.txt).
+            static const bool one_gather = getenv("CSG_COEF_BLOCKWISE") == nullptr;
             if (!comm_stream.s) CSG_CUDA(cudaStreamCreateWithFlags(&comm_stream.s, cudaStreamNonBlocking));
             if (!ev_intt) { CSG_CUDA(cudaEventCreateWithFlags(&ev_intt, cudaEventDisableTiming)); CSG_CUDA(cudaEventCreateWithFlags(&ev_gathered, cudaEventDisableTiming)); }
+            while (block_ev.size() < G) { cudaEvent_t e; CSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); block_ev.push_back(e); }
             CSG_CUDA(cudaEventRecord(ev_intt, st.s));
             if (c_hi > c_lo) coset_ntt_columns(roots, ntt, scratch.p + c_lo * n, n, d_lde.p + c_lo * n, n, w * n, c_hi - c_lo, logn, lde_tables, st);
             CSG_CUDA(cudaStreamWaitEvent(comm_stream.s, ev_intt, 0));
-            gather(scratch.p, cpr * n * sizeof(fe), &comm_stream);
-            CSG_CUDA(cudaEventRecord(ev_gathered, comm_stream.s));
-            CSG_CUDA(cudaStreamWaitEvent(st.s, ev_gathered, 0));
-            if (c_lo > 0) coset_ntt_columns(roots, ntt, scratch.p, n, d_lde.p, n, w * n, c_lo, logn, lde_tables, st);
-            if (c_hi < w) coset_ntt_columns(roots, ntt, scratch.p + c_hi * n, n, d_lde.p + c_hi * n, n, w * n, w - c_hi, logn, lde_tables, st);
+            if (one_gather) {
+                gather(scratch.p, cpr * n * sizeof(fe), &comm_stream);
+                CSG_CUDA(cudaEventRecord(ev_gathered, comm_stream.s));
+                CSG_CUDA(cudaStreamWaitEvent(st.s, ev_gathered, 0));
+                if (c_lo > 0) coset_ntt_columns(roots, ntt, scratch.p, n, d_lde.p, n, w * n, c_lo, logn, lde_tables, st);
+                if (c_hi < w) coset_ntt_columns(roots, ntt, scratch.p + c_hi * n, n, d_lde.p + c_hi * n, n, w * n, w - c_hi, logn, lde_tables, st);
+            } else {
+                for (unsigned q = 0; q < G; q++) {
+                    const size_t q_lo = std::min((size_t)q * cpr, w), q_hi = std::min(q_lo + cpr, w);
+                    bcast(scratch.p + (size_t)q * cpr * n, cpr * n * sizeof(fe), (int)q, &comm_stream);
+                    if (q == rank || q_hi == q_lo) continue;
+                    CSG_CUDA(cudaEventRecord(block_ev[q], comm_stream.s));
+                    CSG_CUDA(cudaStreamWaitEvent(st.s, block_ev[q], 0));
+                    coset_ntt_columns(roots, ntt, scratch.p + q_lo * n, n, d_lde.p + q_lo * n, n, w * n, q_hi - q_lo, logn, lde_tables, st);
+                }
+                // later stages read every block on the proving stream: it has waited for each one it transformed; an empty tail
+                // block (fewer columns than ranks) still has to be in before the buffer is reused
+                CSG_CUDA(cudaEventRecord(ev_gathered, comm_stream.s));
+                CSG_CUDA(cudaStreamWaitEvent(st.s, ev_gathered, 0));
+            }
         }
         std::swap(d_polys.p, scratch.p); std::swap(d_polys.n, scratch.n);   // d_polys = coefficients
         t.stop(st, &tm.lde); tm.stage_launches[0] = t.launches;
@@ -533,6 +555,13 @@ struct csg_ctx {
         comm_events();
         CSG_CUDA(cudaEventRecord(comm_ev[comm_used].first, cs.s));
         comm->all_gather(buf, bytes, cs);
+        CSG_CUDA(cudaEventRecord(comm_ev[comm_used++].second, cs.s));
+    }
+    void bcast(void *buf, size_t bytes, int root, Stream *on = nullptr) {
+        Stream &cs = on ? *on : st;
+        comm_events();
+        CSG_CUDA(cudaEventRecord(comm_ev[comm_used].first, cs.s));
+        comm->broadcast(buf, bytes, root, cs);
         CSG_CUDA(cudaEventRecord(comm_ev[comm_used++].second, cs.s));
     }
     void reduce_rows(uint64_t *buf, size_t count) {
