@@ -53,14 +53,21 @@ CONS_KERNELS = {   # name: (description, algorithmic bytes per ce row, fraction 
 }
 
 
-def csrc_sha16():
+# csrc/ files that hold no kernel of a single-GPU proof: the C++ host driver, the C-ABI wrappers and the collectives of sharded proofs.
+# A change there moves launches around, not the instructions a launch executes (the launch counts per stage are measured live).
+HOST_DRIVER_FILES = {"prover_ctx.cuh", "prover.cu", "abi_kernels.cu", "abi_witness.cu", "comm.cu", "comm.cuh"}
+
+
+def csrc_sha16(read=None, include_host_driver=False):
     """fingerprint of the kernel sources: profiles/traffic.json (ncu counters of one proof) is only quoted when it was captured
-    from exactly these sources"""
+    from exactly these sources.  read(name) -> bytes overrides the working tree (tools/restamp_traffic.py reads a commit)."""
     import hashlib
     h = hashlib.sha256()
     d = ROOT / "certificate_stark_b200" / "csrc"
     for f in sorted(list(d.glob("*.cu")) + list(d.glob("*.cuh")) + list(d.glob("*.h"))):
-        h.update(f.name.encode()); h.update(f.read_bytes())
+        if f.name in HOST_DRIVER_FILES and not include_host_driver:
+            continue
+        h.update(f.name.encode()); h.update(read(f.name) if read else f.read_bytes())
     return h.hexdigest()[:16]
 
 
@@ -74,7 +81,7 @@ if _t.exists():
         TRAFFIC = json.loads(_t.read_text())
     except Exception:
         TRAFFIC = {}
-TRAFFIC_FRESH = bool(TRAFFIC) and TRAFFIC.get("_captured_at", {}).get("csrc_sha16") == csrc_sha16()
+TRAFFIC_FRESH = bool(TRAFFIC) and TRAFFIC.get("_captured_at", {}).get("kernel_sha16") == csrc_sha16()
 
 
 def measured_peaks():

@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
         "csg_get_timings": (C.c_int, [vp, C.POINTER(Timings)]),
         "csg_dist_unique_id": (C.c_int, [_u8p]), "csg_dist_init": (C.c_int, [vp, C.c_int, C.c_int, _u8p]),
         "csg_dist_plan": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ShardPlan)]),
+        "csg_dist_trace_chunks": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]),
         "csg_dist_init_local": (C.c_int, [C.POINTER(vp), C.c_int]), "csg_dist_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "csg_timer_start": (C.c_int, [vp]), "csg_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "csg_tx_batch_new": (vp, [C.c_uint64, C.c_size_t, C.c_uint]), "csg_tx_batch_free": (None, [vp]), "csg_tx_batch_size": (C.c_size_t, [vp]),
@@ -381,6 +382,15 @@ def dist_plan(rank: int, world: int, blowup: int, ce_blowup: int, width: int) ->
     if lib().csg_dist_plan(rank, world, blowup, ce_blowup, width, C.byref(p)):
         raise CsgError("world must be a power of two dividing the blowup factor, rank below it")
     return p
+
+
+def dist_trace_chunks(rank: int, world: int, blowup: int, ce_blowup: int, width: int, from_host: bool) -> list:
+    """column chunks in which that rank copies / extends its column block in stage 1 (csg_dist_trace_chunks); host-only"""
+    sizes = (C.c_uint32 * max(1, width))()
+    count = C.c_size_t(0)
+    if lib().csg_dist_trace_chunks(rank, world, blowup, ce_blowup, width, int(bool(from_host)), sizes, width, C.byref(count)):
+        raise CsgError("world must be a power of two dividing the blowup factor, rank below it")
+    return [int(sizes[k]) for k in range(count.value)]
 
 
 def dist_unique_id() -> bytes:

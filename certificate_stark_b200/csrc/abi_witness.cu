@@ -193,6 +193,15 @@ int csg_dist_plan(int rank, int world, uint32_t blowup, uint32_t ce_blowup, uint
     if (!out || rank < 0 || world < 1 || (world & (world - 1))) return CSG_ERR_ARG;
     return shard_plan((size_t)rank, (size_t)world, blowup, ce_blowup, width, out) ? CSG_OK : CSG_ERR_ARG;
 }
+int csg_dist_trace_chunks(int rank, int world, uint32_t blowup, uint32_t ce_blowup, uint32_t width, int from_host, uint32_t *sizes, size_t cap, size_t *count) {
+    csg_shard_plan plan;
+    if (!count || (cap && !sizes) || csg_dist_plan(rank, world, blowup, ce_blowup, width, &plan) != CSG_OK) return CSG_ERR_ARG;
+    const std::vector<size_t> chunks = trace_chunks(from_host != 0, plan.first_column, (size_t)plan.first_column + plan.num_columns);
+    *count = chunks.size();
+    if (chunks.size() > cap) return CSG_ERR_ARG;
+    for (size_t k = 0; k < chunks.size(); k++) sizes[k] = (uint32_t)chunks[k];
+    return CSG_OK;
+}
 int csg_dist_info(const csg_ctx *ctx, int *rank, int *world) {
     if (!ctx || !rank || !world) return CSG_ERR_ARG;
     *rank = ctx->comm ? ctx->comm->rank : 0; *world = ctx->comm ? ctx->comm->world : 1;

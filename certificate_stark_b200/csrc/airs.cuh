@@ -41,7 +41,7 @@
 #define CSG_REST_LOOP
 #endif
 #ifndef CSG_RESCUE_FWD_UNROLL
-#define CSG_RESCUE_FWD_UNROLL 7   // seven state loads in flight ahead of their cubes: cons_rescue 6.51 -> 6.31 ms against 2 (14: no better)
+#define CSG_RESCUE_FWD_UNROLL 2
 #endif
 
 namespace airs {

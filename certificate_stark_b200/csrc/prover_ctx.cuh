@@ -101,6 +101,27 @@ class Timer {   // device time of a stage, CUDA events on the proving stream; th
 
 using namespace csg;
 
+// The column chunks in which stage 1 walks a rank's column block [c_lo, c_hi).  Nothing to overlap when the trace is already
+// resident: one chunk.  From host memory the extension can only start once the first chunk has arrived, so the chunks ramp up --
+// 1, 3, 4, then 8 columns (8 MB first: 0.15 ms of PCIe instead of 1.2 ms; end to end 61.2 -> 60.7 ms per 1024-transaction proof,
+// profiles/r2_e2e_chunks.txt); CSG_H2D_CHUNKS="a,b,c" overrides the schedule, the last entry repeating.  The sizes add up to
+// c_hi - c_lo exactly: the last rank of a sharded proof owns fewer columns than columns_per_rank, and the buffers hold `width`
+// columns, not world * columns_per_rank (csg_dist_trace_chunks exposes this to the CPU tests).
+static std::vector<size_t> trace_chunks(bool from_host, size_t c_lo, size_t c_hi) {
+    std::vector<size_t> chunks;
+    if (c_hi <= c_lo) return chunks;
+    if (!from_host) { chunks.push_back(c_hi - c_lo); return chunks; }
+    static const std::vector<size_t> sched = [] {
+        std::vector<size_t> v;
+        if (const char *e = getenv("CSG_H2D_CHUNKS"))
+            for (const char *q = e; *q;) { char *end; const unsigned long x = strtoul(q, &end, 10); if (end == q) break; if (x) v.push_back(x); q = *end ? end + 1 : end; }
+        if (v.empty()) v = {1, 3, 4, 8};
+        return v;
+    }();
+    for (size_t c = c_lo, k = 0; c < c_hi; k++) { const size_t sz = std::min(sched[std::min(k, sched.size() - 1)], c_hi - c); chunks.push_back(sz); c += sz; }
+    return chunks;
+}
+
 // which part of a sharded proof a rank owns: a contiguous block of LDE cosets (and the ce cosets among them), and the block
 // of trace columns it interpolates.  The one place this geometry is defined; csg_dist_plan exposes it to callers.
 static bool shard_plan(size_t rank, size_t world, size_t b, size_t ce, size_t w, csg_shard_plan *out) {
@@ -423,22 +444,7 @@ struct csg_ctx {
         csg_shard_plan plan;
         shard_plan(rank, G, b, ce, w, &plan);
         const size_t cpr = plan.columns_per_rank, c_lo = plan.first_column, c_hi = c_lo + plan.num_columns, wpad = cpr * G;
-        // nothing to overlap when the trace is already resident: one chunk.  From host memory the extension can only start once
-        // the first chunk has arrived, so the chunks ramp up -- 1, 3, 4, then 8 columns (8 MB first: 0.15 ms of PCIe instead of
-        // 1.2 ms; end to end 61.2 -> 60.7 ms per 1024-transaction proof, gpurun_out/s3b/e2e_chunks.txt) -- CSG_H2D_CHUNKS="a,b,c"
-        // overrides the schedule, the last entry repeating
-        std::vector<size_t> chunks;
-        if (!host) chunks.push_back(cpr);
-        else {
-            static const std::vector<size_t> sched = [] {
-                std::vector<size_t> v;
-                if (const char *e = getenv("CSG_H2D_CHUNKS"))
-                    for (const char *q = e; *q;) { char *end; const unsigned long x = strtoul(q, &end, 10); if (end == q) break; if (x) v.push_back(x); q = *end ? end + 1 : end; }
-                if (v.empty()) v = {1, 3, 4, 8};
-                return v;
-            }();
-            for (size_t c = c_lo, k = 0; c < c_hi; k++) { const size_t s = std::min(sched[std::min(k, sched.size() - 1)], c_hi - c); chunks.push_back(s); c += s; }
-        }
+        const std::vector<size_t> chunks = trace_chunks(host != nullptr, c_lo, c_hi);
         size_t CHUNK = 1;
         for (size_t s : chunks) CHUNK = std::max(CHUNK, s);
         Timer &t = stage_timer;
@@ -463,7 +469,7 @@ struct csg_ctx {
             CSG_CUDA(cudaEventRecord(h2d_a, copy_stream));
         }
         for (size_t c0 = c_lo, k = 0; k < chunks.size() && c0 < c_hi; c0 += chunks[k], k++) {
-            const size_t nc = chunks[k];
+            const size_t nc = std::min(chunks[k], c_hi - c0);   // never past the block: d_io holds exactly w columns
             if (host) {
                 bool contiguous = true;
                 for (size_t j = 1; j < nc; j++) contiguous = contiguous && colptr[c0 + j] == colptr[c0] + j * n;

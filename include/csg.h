@@ -160,6 +160,10 @@ int csg_dist_info(const csg_ctx *ctx, int *rank, int *world);
  * it interpolates -- the only columns csg_prove / csg_prove_trace read from the caller's trace on that rank.  Needs no GPU. */
 typedef struct { uint32_t first_coset, num_cosets, first_ce_coset, num_ce_cosets, first_column, num_columns, columns_per_rank; } csg_shard_plan;
 int csg_dist_plan(int rank, int world, uint32_t blowup, uint32_t ce_blowup, uint32_t width, csg_shard_plan *out);
+/* the column chunks in which that rank walks its column block in stage 1 (copy from the caller's memory overlapped with the
+ * extension when from_host != 0, one chunk for a resident trace): sizes[0 .. *count), adding up to num_columns.  *count is set even
+ * when cap is too small (CSG_ERR_ARG).  Needs no GPU; the CPU tests check the geometry of every world size with it. */
+int csg_dist_trace_chunks(int rank, int world, uint32_t blowup, uint32_t ce_blowup, uint32_t width, int from_host, uint32_t *sizes, size_t cap, size_t *count);
 
 /* per-stage device times of the last proof, milliseconds (CUDA events on the proving stream) */
 typedef struct {

@@ -84,6 +84,33 @@ def test_shard_plans_partition_cosets_and_columns(csg):
         csg.dist_plan(0, 3, 8, 8, 94)
 
 
+def test_trace_chunks_stay_inside_a_ranks_column_block(csg):
+    # csg_dist_trace_chunks is the walk of stage 1 over a rank's column block (copy + extension chunk by chunk from host memory,
+    # one chunk for a resident trace).  The last rank owns FEWER columns than columns_per_rank whenever world does not divide the
+    # width (94 columns over 8 ranks: 7 x 12 + 10) and the trace buffers hold exactly `width` columns: a chunk that runs past the
+    # block reads past the buffer (an 8-GPU bench of round 2 died of exactly that on rank 7).
+    for width, blowup, ce in [(94, 8, 8), (65, 8, 4), (56, 8, 8), (14, 4, 4), (2, 8, 2), (58, 4, 4), (94, 32, 8)]:
+        for world in [1, 2, 4, 8, 16, 32]:
+            if world > blowup:
+                continue
+            for from_host in (False, True):
+                covered = []
+                for r in range(world):
+                    p = csg.dist_plan(r, world, blowup, ce, width)
+                    chunks = csg.dist_trace_chunks(r, world, blowup, ce, width, from_host)
+                    assert sum(chunks) == p.num_columns and all(c >= 1 for c in chunks)
+                    if not from_host:
+                        assert chunks == ([p.num_columns] if p.num_columns else [])
+                    elif p.num_columns:
+                        assert chunks[0] <= 2          # the extension starts after the first column(s), not after the block
+                    c = p.first_column
+                    for sz in chunks:
+                        covered += list(range(c, c + sz))
+                        c += sz
+                    assert c <= width
+                assert covered == list(range(width))
+
+
 ID_WORKER = r"""
 import os, sys, json, hashlib
 sys.path.insert(0, os.environ["CSG_ROOT"])

@@ -46,7 +46,7 @@ def main():
     proof = ordered[-per_proof:]
     sl = line["stage_launches"]
     assert sum(sl[s] for s in STAGES) == per_proof, (sl, per_proof)
-    out = {"_captured_at": {"csrc_sha16": bench.csrc_sha16(), "commit": commit,
+    out = {"_captured_at": {"kernel_sha16": bench.csrc_sha16(), "csrc_sha16": bench.csrc_sha16(include_host_driver=True), "commit": commit,
                             "command": "ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_*.sum,smsp__inst_executed_pipe_{alu,fma}.sum "
                                        "--clock-control none python bench.py --profile --steps 1 (1024 tx); last proof of the run"},
            "stages": {}, "kernels": {}}
