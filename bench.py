@@ -500,4 +500,15 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as exc:   # noqa: BLE001
+        if isinstance(exc, SystemExit) and exc.code in (0, None):
+            raise
+        # A rank that fails must END, at once: its peers are blocked inside collectives that it will never join, and the normal
+        # interpreter shutdown of a process whose CUDA context has faulted can itself block in the NCCL / CUDA teardown -- the
+        # launcher then never sees the failure and the whole job sits there until someone's time limit kills it.
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(exc.code if isinstance(exc, SystemExit) and isinstance(exc.code, int) else 1)
