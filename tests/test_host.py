@@ -174,3 +174,16 @@ def test_bench_stage_roofline_arithmetic():
     assert abs(r["lde"]["achieved"] - 94 * n * 88 / 18.94e-3 / 1e9) < 1e-6 and 0.06 < r["lde"]["frac"] < 0.08
     assert 0.2 < r["commit_trace"]["frac"] < 0.3
     assert bench.stage_roofline({}, n, 6544.0)["lde"]["achieved"] is None   # a missing stage does not raise
+
+
+def test_committed_counters_belong_to_the_committed_kernels():
+    # profiles/traffic.json (ncu counters of one proof) is what bench.py's INT roofline quotes; it carries a fingerprint of the kernel
+    # sources it was captured from and bench.py drops it when the kernels have changed since.  In a committed tree the two must agree:
+    # a kernel change without a new counter pass would silently turn the bench line's roofline back into the HBM-only form.
+    import bench
+    cap = bench.TRAFFIC.get("_captured_at", {})
+    assert cap.get("kernel_sha16") == bench.csrc_sha16(), "kernel sources changed since the ncu counter pass: re-run tools/gpu_calls/run_s3a.sh (tools/make_traffic.py)"
+    assert bench.TRAFFIC_FRESH
+    # host-driver files are outside the fingerprint, kernels are inside
+    assert "prover_ctx.cuh" in bench.HOST_DRIVER_FILES and "ntt.cu" not in bench.HOST_DRIVER_FILES and "airs.cuh" not in bench.HOST_DRIVER_FILES
+    assert bench.csrc_sha16(include_host_driver=True) != bench.csrc_sha16()
