@@ -211,3 +211,13 @@ def test_verifier_survives_mutated_proofs(csg, oracle, tmp_path):
         out = subprocess.run([str(exe), str(air), str(tmp_path / f"{k}.pub"), str(tmp_path / f"{k}.proof"), str(iters), str(1000 + k)],
                              capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
         assert out.returncode == 0 and "accepted 0" in out.stdout, (out.stdout + out.stderr)[-3000:]
+
+
+def test_host_builders_are_sanitizer_clean(tmp_path):
+    # the host witness / batch builders write into caller buffers sized by the header's comments (94 x 1024*num_tx, 65 x 512*num_tx,
+    # 56 x 512*num_sig, 38*num_sig, ...): tests/host_sanitize.cpp gives them exact-size heap buffers under ASan + UBSan + LSan
+    exe = tmp_path / "host_sanitize"
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                           str(ROOT / "tests" / "host_sanitize.cpp"), "-x", "c++", str(ROOT / "certificate_stark_b200" / "csrc" / "host" / "witness.cpp"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1"))
+    assert out.returncode == 0 and "0 failures" in out.stdout, (out.stdout + out.stderr)[-3000:]
